@@ -1,0 +1,1272 @@
+// Device half of libdblink_b200: the Gibbs sweep of dblink's record-linkage model on one B200.
+//
+// Reference (cleanzr/dblink @ dc3dd0d, src/main/scala/com/github/cleanzr/dblink/, GU = GibbsUpdates.scala):
+//   State.nextState State.scala:78-99 -> updatePartition GU:156-211
+//     link draw per record        GU:363-395 (PCG-II), GU:399-466 (PCG-I / Gibbs, dense form)   -> k_link
+//     entity values per (e, attr) GU:534-599, 605-646, 702-755                                   -> k_values
+//     distortions per (r, attr)   GU:324-359                                                     -> k_dist
+//     new partition id            GU:206, partitioning/MutableBST.scala:61-79                    -> k_entity_post
+//   updateSummaryVariables GU:219-301                                   -> k_entity_post / k_dist accumulators
+//   the shuffle GU:144                                                  -> relayout() (sort by block id)
+//
+// Numerics: all likelihood arithmetic is IEEE binary64 with no FMA contraction (-fmad=false) so that the
+// CPU oracle (oracle/dbl_oracle.c, -ffp-contract=off) reproduces every draw bit for bit.  Draw protocol:
+// DESIGN.md section 4.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <cub/cub.cuh>
+#include <string>
+#include <vector>
+
+#include "dbl_internal.h"
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      ctx->set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                       \
+      return DBL_ERR_CUDA;                                                                      \
+    }                                                                                           \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// device-side model
+// ---------------------------------------------------------------------------------------------------
+struct AttrDev {
+  int V, is_const, kmax, pad;
+  const double *phi, *probs, *norm, *invnorm, *pk, *cdf, *logphi, *lognorm, *expsim;
+  const int *rowptr, *col;
+};
+struct TreeDev {
+  int n_nodes;
+  const int *attr, *kind, *split, *set_ptr, *set_val, *leaf_no;
+};
+
+constexpr int TE = 128;       // entities per tile of the block-sorted entity table
+constexpr int LINK_WARPS = 8; // records per CTA of the link kernel
+
+__host__ __device__ inline size_t tile_words(int A) { return (size_t)A * TE + 2 * TE; }  // int32 words per tile
+
+// ---------------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool row_find(const AttrDev &at, int v1, int v2, double &e) {
+  int lo = at.rowptr[v1], hi = at.rowptr[v1 + 1] - 1;
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1;
+    const int c = at.col[mid];
+    if (c == v2) { e = at.expsim[mid]; return true; }
+    if (c < v2) lo = mid + 1; else hi = mid - 1;
+  }
+  return false;
+}
+
+__device__ __forceinline__ int invcdf(const double *cdf, int V, double u) {
+  int lo = 0, hi = V;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (cdf[mid] > u) hi = mid; else lo = mid + 1;
+  }
+  return lo < V ? lo : V - 1;
+}
+
+__device__ __forceinline__ int tree_leaf(const TreeDev &t, const int *yrow) {
+  int node = 0;
+  while (node < t.n_nodes && t.attr[node] >= 0) {
+    const int v = yrow[t.attr[node]];
+    bool right;
+    if (t.kind[node]) {
+      int lo = t.set_ptr[node], hi = t.set_ptr[node + 1] - 1;
+      right = false;
+      while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        const int s = t.set_val[mid];
+        if (s == v) { right = true; break; }
+        if (s < v) lo = mid + 1; else hi = mid - 1;
+      }
+    } else {
+      right = v > t.split[node];
+    }
+    node = right ? 2 * node + 2 : 2 * node + 1;
+  }
+  return t.leaf_no[node];
+}
+
+__device__ __forceinline__ double shfl_xor_d(double v, int d) { return __shfl_xor_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ double shfl_d(double v, int l) { return __shfl_sync(0xffffffffu, v, l); }
+
+// 5-level xor butterfly: every lane ends with the same sum (the protocol's "step total")
+__device__ __forceinline__ double butterfly_sum(double v) {
+  v = v + shfl_xor_d(v, 16);
+  v = v + shfl_xor_d(v, 8);
+  v = v + shfl_xor_d(v, 4);
+  v = v + shfl_xor_d(v, 2);
+  v = v + shfl_xor_d(v, 1);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_entity_post: per entity N(e) = prod_{non-const a} n_a(y_a); new block id (GU:206); entity part of the
+// summary: isolates (GU:267-269) and sum_a log phi_a(y_a) (GU:234-237, 271-274).
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_entity_post(int64_t E, int A, const int *__restrict__ y, const AttrDev *__restrict__ attrs,
+                              TreeDev tree, double *__restrict__ entN, int *__restrict__ blk,
+                              const int *__restrict__ ent_rec_ptr, long long *__restrict__ counts, int iso_slot,
+                              double *__restrict__ loglik) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double ll = 0.0;
+  int iso = 0;
+  if (e < E) {
+    const int *ye = y + e * A;
+    double n = 1.0;
+    for (int a = 0; a < A; ++a) {
+      const AttrDev &at = attrs[a];
+      const int v = ye[a];
+      if (!at.is_const) n = n * at.norm[v];
+      ll += at.logphi[v];
+    }
+    entN[e] = n;
+    blk[e] = tree.n_nodes > 0 ? tree_leaf(tree, ye) : 0;
+    if (ent_rec_ptr) iso = (ent_rec_ptr[e] == ent_rec_ptr[e + 1]);
+  }
+  if (counts) {
+    typedef cub::BlockReduce<double, 256> BR;
+    typedef cub::BlockReduce<int, 256> BRI;
+    __shared__ typename BR::TempStorage t1;
+    __shared__ typename BRI::TempStorage t2;
+    const double s = BR(t1).Sum(ll);
+    const int c = BRI(t2).Sum(iso);
+    if (threadIdx.x == 0) {
+      atomicAdd(loglik, s);
+      if (c) atomicAdd((unsigned long long *)&counts[iso_slot], (unsigned long long)c);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// layout ("re-partitioning", replaces the shuffle GU:144): entities and records grouped by block
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_iota(int64_t n, int *out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int)i;
+}
+__global__ void k_hist(int64_t n, const int *__restrict__ key, int *__restrict__ cnt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(&cnt[key[i]], 1);
+}
+__global__ void k_rec_block_keys(int64_t R, const int *__restrict__ link, const int *__restrict__ blk,
+                                 int *__restrict__ key) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < R) key[r] = blk[link[r]];
+}
+// prefix sums over the P blocks (P is 2^numLevels: small) -- one CTA, Hillis-Steele over chunks
+__global__ void k_block_scan(int P, const int *__restrict__ ent_cnt, const int *__restrict__ rec_cnt,
+                             int *__restrict__ ent_ptr, int *__restrict__ tile_ptr, int *__restrict__ rec_ptr,
+                             int *__restrict__ cta_ptr, int warps_per_cta) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int e = 0, t = 0, r = 0, c = 0;
+    for (int b = 0; b < P; ++b) {
+      ent_ptr[b] = e; tile_ptr[b] = t; rec_ptr[b] = r; cta_ptr[b] = c;
+      e += ent_cnt[b];
+      t += (ent_cnt[b] + TE - 1) / TE;
+      r += rec_cnt[b];
+      c += (rec_cnt[b] + warps_per_cta - 1) / warps_per_cta;
+    }
+    ent_ptr[P] = e; tile_ptr[P] = t; rec_ptr[P] = r; cta_ptr[P] = c;
+  }
+}
+// tiled, block-sorted copy of the entity table: tile = { int32 y[A][TE]; double N[TE] }
+__global__ void k_build_tiles(int64_t E, int A, const int *__restrict__ y, const double *__restrict__ entN,
+                              const int *__restrict__ blk_sorted, const int *__restrict__ ent_sorted,
+                              const int *__restrict__ ent_ptr, const int *__restrict__ tile_ptr,
+                              int *__restrict__ tiles) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= E) return;
+  const int b = blk_sorted[i];
+  const int e = ent_sorted[i];
+  const int j = (int)(i - ent_ptr[b]);
+  int *tile = tiles + (size_t)(tile_ptr[b] + j / TE) * tile_words(A);
+  const int slot = j % TE;
+  for (int a = 0; a < A; ++a) tile[a * TE + slot] = y[(int64_t)e * A + a];
+  reinterpret_cast<double *>(tile + (size_t)A * TE)[slot] = entN[e];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_link: one warp per record, dense scoring of every entity of the record's block + categorical draw.
+// v0: tiles are read straight from global/L2 (the block's table is L2 resident).
+// ---------------------------------------------------------------------------------------------------
+struct RecAttr {
+  int kind;  // 0 skip, 1 const compare, 2 non-const sparse row, 3 missing non-const (PCG-II), 4 must match
+  int x;
+  int len;
+  int pad;
+  double rmatch;
+  const int *col;
+  const double *val;
+  const double *tab;  // invnorm (kind 3) / norm (kind 2 of PCG-I)
+};
+
+struct LinkParams {
+  int A, F, P, sampler;
+  uint64_t seed;
+  uint32_t iter;
+  const AttrDev *attrs;
+  const int *x, *file, *link;
+  const unsigned *zmask;
+  const double *theta;
+  const int *ent_ptr, *tile_ptr, *rec_ptr, *cta_ptr, *ent_sorted, *rec_sorted;
+  const int *tiles;
+  int *newlink;
+  int *status;
+  unsigned long long *pairs;
+};
+
+__device__ __forceinline__ double weight_pcg2(const RecAttr *ra, int A, const int *ycol, double N) {
+  double w = N;
+  for (int a = 0; a < A; ++a) {
+    const RecAttr c = ra[a];
+    if (c.kind == 0) continue;
+    const int yv = ycol[a * TE];
+    if (c.kind == 1) {
+      if (yv == c.x) w = w * c.rmatch;
+    } else if (c.kind == 2) {
+      if (yv == c.x) {
+        w = w * c.rmatch;
+      } else {
+        int lo = 0, hi = c.len - 1;
+        while (lo <= hi) {
+          const int mid = (lo + hi) >> 1;
+          const int cv = c.col[mid];
+          if (cv == yv) { w = w * c.val[mid]; break; }
+          if (cv < yv) lo = mid + 1; else hi = mid - 1;
+        }
+      }
+    } else {  // kind 3
+      w = w * c.tab[yv];
+    }
+  }
+  return w;
+}
+
+__device__ __forceinline__ double weight_pcg1(const RecAttr *ra, int A, const int *ycol) {
+  for (int a = 0; a < A; ++a)
+    if (ra[a].kind == 4 && ycol[a * TE] != ra[a].x) return 0.0;
+  double w = 1.0;
+  for (int a = 0; a < A; ++a) {
+    const RecAttr c = ra[a];
+    if (c.kind != 2) continue;
+    const int yv = ycol[a * TE];
+    w = w * c.tab[yv];
+    int lo = 0, hi = c.len - 1;
+    while (lo <= hi) {
+      const int mid = (lo + hi) >> 1;
+      const int cv = c.col[mid];
+      if (cv == yv) { w = w * c.val[mid]; break; }
+      if (cv < yv) lo = mid + 1; else hi = mid - 1;
+    }
+  }
+  return w;
+}
+
+__global__ void __launch_bounds__(LINK_WARPS * 32) k_link(LinkParams p) {
+  __shared__ RecAttr s_ra[LINK_WARPS][DBL_MAX_ATTRS];
+  const int cta = blockIdx.x;
+  if (cta >= p.cta_ptr[p.P]) return;
+  int lo = 0, hi = p.P;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (p.cta_ptr[mid] <= cta) lo = mid; else hi = mid;
+  }
+  const int b = lo;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ridx = p.rec_ptr[b] + (cta - p.cta_ptr[b]) * LINK_WARPS + warp;
+  if (ridx >= p.rec_ptr[b + 1]) return;
+  const int r = p.rec_sorted[ridx];
+  const int A = p.A;
+  const bool pcg2 = (p.sampler == DBL_PCG_II);
+
+  // per-record constants, lane a prepares attribute a
+  RecAttr *ra = s_ra[warp];
+  if (lane < A) {
+    const AttrDev &at = p.attrs[lane];
+    const int xv = p.x[(int64_t)r * A + lane];
+    RecAttr c;
+    c.kind = 0; c.x = xv; c.len = 0; c.pad = 0; c.rmatch = 1.0; c.col = nullptr; c.val = nullptr; c.tab = nullptr;
+    if (pcg2) {
+      if (xv < 0) {
+        if (!at.is_const) { c.kind = 3; c.tab = at.invnorm; }
+      } else {
+        const double th = p.theta[lane * p.F + p.file[r]];
+        double d = th * at.phi[xv];
+        if (at.is_const) {
+          c.kind = 1;
+          c.rmatch = 1.0 + (1.0 - th) / d;
+        } else {
+          d = d * at.norm[xv];
+          double ediag = 1.0;
+          row_find(at, xv, xv, ediag);
+          c.kind = 2;
+          c.rmatch = ediag + (1.0 - th) / d;
+          c.col = at.col + at.rowptr[xv];
+          c.val = at.expsim + at.rowptr[xv];
+          c.len = at.rowptr[xv + 1] - at.rowptr[xv];
+        }
+      }
+    } else if (xv >= 0) {
+      const bool dist = (p.zmask[r] >> lane) & 1u;
+      if (!dist) c.kind = 4;
+      else if (!at.is_const) {
+        c.kind = 2;
+        c.tab = at.norm;
+        c.col = at.col + at.rowptr[xv];
+        c.val = at.expsim + at.rowptr[xv];
+        c.len = at.rowptr[xv + 1] - at.rowptr[xv];
+      }
+    }
+    ra[lane] = c;
+  }
+  __syncwarp();
+
+  const int n = p.ent_ptr[b + 1] - p.ent_ptr[b];
+  const int nsteps = (n + 31) >> 5;
+  int spc = (nsteps + 31) >> 5;
+  if (spc < 1) spc = 1;
+  const int nchunks = (nsteps + spc - 1) / spc;
+  const size_t tw = tile_words(A);
+  const int *tiles = p.tiles + (size_t)p.tile_ptr[b] * tw;
+
+  auto weight_at = [&](int step) -> double {
+    const int j = (step << 5) + lane;
+    if (j >= n) return 0.0;
+    const int *tile = tiles + (size_t)(j / TE) * tw;
+    const int slot = j % TE;
+    if (pcg2) {
+      const double N = reinterpret_cast<const double *>(tile + (size_t)A * TE)[slot];
+      return weight_pcg2(ra, A, tile + slot, N);
+    }
+    return weight_pcg1(ra, A, tile + slot);
+  };
+
+  // pass 1: step totals accumulated sequentially, lane c keeps the running total at the end of chunk c
+  double run = 0.0, Q = 0.0;
+  {
+    int next_mark = spc, chunk = 0;
+    for (int s = 0; s < nsteps; ++s) {
+      const double c = butterfly_sum(weight_at(s));
+      run = run + c;
+      if (s + 1 == next_mark || s + 1 == nsteps) {
+        if (lane == chunk) Q = run;
+        ++chunk;
+        next_mark += spc;
+      }
+    }
+  }
+  const double total = run;
+  if (!(total > 0.0) || isinf(total)) {  // reference: IllegalArgumentException("zero probability mass")
+    if (lane == 0) { atomicOr(p.status, 1); p.newlink[r] = p.link[r]; }
+    return;
+  }
+  const U2 u = uniform2(p.seed, PH_LINK, p.iter, (uint32_t)r, 0u);
+  const double t = u.u0 * total;
+
+  unsigned m = __ballot_sync(0xffffffffu, lane < nchunks && Q > t);
+  const int chunk = m ? (__ffs(m) - 1) : (nchunks - 1);
+  double rsum = shfl_d(Q, chunk > 0 ? chunk - 1 : 0);
+  if (chunk == 0) rsum = 0.0;
+
+  // pass 2: locate the step inside the chunk (same operations in the same order as pass 1)
+  const int s0 = chunk * spc, s1 = min(s0 + spc, nsteps);
+  int step = s1 - 1;
+  double wl = 0.0;
+  for (int s = s0; s < s1; ++s) {
+    wl = weight_at(s);
+    const double c = butterfly_sum(wl);
+    if (rsum + c > t) { step = s; break; }
+    if (s + 1 < s1) rsum = rsum + c;
+  }
+  // inside the step: Kogge-Stone inclusive scan over lanes
+  double P = wl;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const double o = shfl_up_d(P, d);
+    if (lane >= d) P = P + o;
+  }
+  m = __ballot_sync(0xffffffffu, rsum + P > t);
+  int pick;
+  if (m) pick = __ffs(m) - 1;
+  else {
+    const unsigned pos = __ballot_sync(0xffffffffu, wl > 0.0);
+    pick = pos ? (31 - __clz(pos)) : 0;
+  }
+  if (lane == 0) {
+    int j = (step << 5) + pick;
+    if (j >= n) j = n - 1;
+    p.newlink[r] = p.ent_sorted[p.ent_ptr[b] + j];
+    atomicAdd(p.pairs, (unsigned long long)n);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_values: one thread per (entity, attribute).  updateEntityValueCollapsed GU:576-599 +
+// perturbedDistYCollapsed GU:534-570 (PCG-I/II); updateEntityValue GU:605-646 + perturbedDistY GU:702-727.
+// ---------------------------------------------------------------------------------------------------
+struct ValParams {
+  int A, F, sampler;
+  uint64_t seed;
+  uint32_t iter;
+  int64_t E;
+  const AttrDev *attrs;
+  const int *x, *file;
+  const unsigned *zmask;
+  const double *theta;
+  const int *ent_rec_ptr, *rec_by_ent;
+  int *y;
+};
+
+struct BaseDist {
+  const AttrDev *at;
+  int k;
+  const double *pk, *cdf;
+  double zk;
+};
+__device__ __forceinline__ double base_weight(const AttrDev &at, int k, int v) {
+  double w = at.probs[v];
+  if (!at.is_const)
+    for (int i = 0; i < k; ++i) w = w * at.norm[v];
+  return w;
+}
+__device__ void base_init(BaseDist &b, const AttrDev &at, int k) {
+  b.at = &at;
+  if (at.is_const) k = 0;
+  b.k = k;
+  if (k <= at.kmax) {
+    b.pk = at.pk + (size_t)k * at.V;
+    b.cdf = at.cdf + (size_t)k * at.V;
+    b.zk = 0.0;
+  } else {  // beyond the cached powers (getSimNormDist cache miss, AttributeIndex.scala:199-205)
+    b.pk = nullptr; b.cdf = nullptr;
+    double z = 0.0;
+    for (int v = 0; v < at.V; ++v) z += base_weight(at, k, v);
+    b.zk = z;
+  }
+}
+__device__ __forceinline__ double base_prob(const BaseDist &b, int v) {
+  return b.pk ? b.pk[v] : base_weight(*b.at, b.k, v) / b.zk;
+}
+__device__ int base_draw(const BaseDist &b, double u) {
+  if (b.cdf) return invcdf(b.cdf, b.at->V, u);
+  double c = 0.0;
+  for (int v = 0; v < b.at->V; ++v) {
+    c += base_weight(*b.at, b.k, v) / b.zk;
+    if (c > u) return v;
+  }
+  return b.at->V - 1;
+}
+
+// factor contributed by record r to candidate value v; false when v is outside the record's support
+__device__ __forceinline__ bool g_factor(const ValParams &p, const AttrDev &at, int a, int r, bool collapsed, int v,
+                                         double &g) {
+  const int xr = p.x[(int64_t)r * p.A + a];
+  if (at.is_const) {
+    if (v != xr || !collapsed) return false;
+    const double th = p.theta[a * p.F + p.file[r]];
+    g = 1.0 + (1.0 / th - 1.0) / at.phi[xr];  // GU:553
+    return true;
+  }
+  double e;
+  if (!row_find(at, xr, v, e)) return false;
+  if (collapsed && v == xr) {
+    const double th = p.theta[a * p.F + p.file[r]];
+    g = e + (1.0 / th - 1.0) / (at.phi[xr] * at.norm[xr]);  // GU:557,560
+  } else {
+    g = e;
+  }
+  return true;
+}
+__device__ __forceinline__ bool in_support(const ValParams &p, const AttrDev &at, int a, int r, int v) {
+  const int xr = p.x[(int64_t)r * p.A + a];
+  if (at.is_const) return v == xr;
+  double e;
+  return row_find(at, xr, v, e);
+}
+
+__global__ void k_values(ValParams p) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= p.E * p.A) return;
+  const int64_t e = tid / p.A;
+  const int a = (int)(tid % p.A);
+  const AttrDev &at = p.attrs[a];
+  const bool collapsed = (p.sampler == DBL_PCG_I || p.sampler == DBL_PCG_II);
+  const U2 u = uniform2(p.seed, PH_VALUE, p.iter, (uint32_t)e, (uint32_t)a);
+  const int lo = p.ent_rec_ptr[e], hi = p.ent_rec_ptr[e + 1];
+  const int *rec = p.rec_by_ent;
+
+  int k = 0;
+  for (int i = lo; i < hi; ++i) k += (p.x[(int64_t)rec[i] * p.A + a] >= 0);
+  BaseDist b;
+  if (k == 0) {  // GU:588-589
+    base_init(b, at, 0);
+    p.y[tid] = base_draw(b, u.u1);
+    return;
+  }
+  if (!collapsed) {
+    for (int i = lo; i < hi; ++i) {  // GU:619-630
+      const int r = rec[i];
+      const int xr = p.x[(int64_t)r * p.A + a];
+      if (xr >= 0 && !((p.zmask[r] >> a) & 1u)) { p.y[tid] = xr; return; }
+    }
+    if (at.is_const) {  // GU:633-634
+      base_init(b, at, 0);
+      p.y[tid] = base_draw(b, u.u1);
+      return;
+    }
+  }
+  base_init(b, at, k);  // GU:584-586
+  double total = 0.0, target = 0.0, cum = 0.0;
+  int picked = -1, last_pos = -1;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int i = lo; i < hi; ++i) {
+      const int r = rec[i];
+      const int xr = p.x[(int64_t)r * p.A + a];
+      if (xr < 0) continue;
+      const int nv = at.is_const ? 1 : (at.rowptr[xr + 1] - at.rowptr[xr]);
+      const int *vals = at.is_const ? nullptr : (at.col + at.rowptr[xr]);
+      for (int q = 0; q < nv; ++q) {
+        const int v = at.is_const ? xr : vals[q];
+        bool seen = false;
+        for (int j = lo; j < i && !seen; ++j) {
+          const int rj = rec[j];
+          if (p.x[(int64_t)rj * p.A + a] < 0) continue;
+          seen = in_support(p, at, a, rj, v);
+        }
+        if (seen) continue;
+        double G = 1.0;
+        for (int j = i; j < hi; ++j) {
+          const int rj = rec[j];
+          if (p.x[(int64_t)rj * p.A + a] < 0) continue;
+          double g;
+          if (g_factor(p, at, a, rj, collapsed, v, g)) G = G * g;
+        }
+        const double W = base_prob(b, v) * (G - 1.0);  // GU:567 / 724
+        if (pass == 0) {
+          total += W;
+        } else {
+          cum += W;
+          if (W > 0.0) last_pos = v;
+          if (picked < 0 && cum > target) picked = v;
+        }
+      }
+    }
+    if (pass == 0) {
+      if (u.u0 < 1.0 / (1.0 + total)) {  // GU:593-594
+        p.y[tid] = base_draw(b, u.u1);
+        return;
+      }
+      target = u.u1 * total;
+    }
+  }
+  if (picked < 0) picked = last_pos;
+  if (picked < 0) picked = base_draw(b, u.u1);
+  p.y[tid] = picked;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_dist: one thread per record.  updateDistortions GU:324-359 with the new y, fused with the record part
+// of updateSummaryVariables GU:239-266.  draw = 0 only accumulates the summary of the current state.
+// ---------------------------------------------------------------------------------------------------
+struct DistParams {
+  int A, F, draw;
+  uint64_t seed;
+  uint32_t iter;
+  int64_t R;
+  const AttrDev *attrs;
+  const int *x, *file, *link, *y;
+  unsigned *zmask;
+  const double *theta;
+  long long *counts;  // [A*F] aggDist, then [A+1] recDist
+  double *loglik;
+};
+
+__global__ void k_dist(DistParams p) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double ll = 0.0;
+  if (r < p.R) {
+    const int f = p.file[r];
+    const int *ye = p.y + (int64_t)p.link[r] * p.A;
+    unsigned zm = p.zmask[r];
+    int nd = 0;
+    for (int a = 0; a < p.A; ++a) {
+      const AttrDev &at = p.attrs[a];
+      const int xv = p.x[r * p.A + a];
+      const int yv = ye[a];
+      bool z;
+      if (p.draw) {
+        const double th = p.theta[a * p.F + f];
+        if (xv < 0) {
+          const U2 u = uniform2(p.seed, PH_DIST, p.iter, (uint32_t)r, (uint32_t)a);
+          z = u.u0 < th;  // GU:331-334
+        } else if (xv != yv) {
+          z = true;  // GU:352-354
+        } else {
+          const U2 u = uniform2(p.seed, PH_DIST, p.iter, (uint32_t)r, (uint32_t)a);
+          double pr1 = th * at.phi[xv];
+          if (!at.is_const) {
+            double ediag = 1.0;
+            row_find(at, xv, xv, ediag);
+            pr1 = pr1 * at.norm[xv];
+            pr1 = pr1 * ediag;
+          }
+          const double pr0 = 1.0 - th;
+          const double den = pr1 + pr0;
+          const double pz = (den != 0.0) ? pr1 / den : 0.0;  // GU:349-350
+          z = u.u0 < pz;
+        }
+        zm = z ? (zm | (1u << a)) : (zm & ~(1u << a));
+      } else {
+        z = (zm >> a) & 1u;
+      }
+      if (z) {
+        ++nd;
+        atomicAdd((unsigned long long *)&p.counts[a * p.F + f], 1ull);  // GU:246
+        if (xv >= 0) {                                                   // GU:248-258
+          ll += at.logphi[xv];
+          if (!at.is_const) {
+            ll += at.lognorm[yv];
+            double e;
+            if (row_find(at, xv, yv, e)) ll += log(e);
+          }
+        }
+      }
+    }
+    if (p.draw) p.zmask[r] = zm;
+    atomicAdd((unsigned long long *)&p.counts[p.A * p.F + nd], 1ull);  // GU:265
+  }
+  typedef cub::BlockReduce<double, 256> BR;
+  __shared__ typename BR::TempStorage tmp;
+  const double s = BR(tmp).Sum(ll);
+  if (threadIdx.x == 0 && s != 0.0) atomicAdd(p.loglik, s);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_init_state: State.deterministic (State.scala:253-301) -- entity e copies record e (if any), missing
+// values drawn from phi; record r links to entity r mod E; z = (x>=0 && x!=y).
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_init_entities(int64_t E, int64_t R, int A, uint64_t seed, const AttrDev *__restrict__ attrs,
+                                const int *__restrict__ x, int *__restrict__ y) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= E * A) return;
+  const int64_t e = tid / A;
+  const int a = (int)(tid % A);
+  int v = (e < R) ? x[e * A + a] : -1;
+  if (v < 0) {
+    const U2 u = uniform2(seed, PH_INIT, 0u, (uint32_t)e, (uint32_t)a);
+    v = invcdf(attrs[a].cdf, attrs[a].V, u.u1);
+  }
+  y[tid] = v;
+}
+__global__ void k_init_records(int64_t E, int64_t R, int A, const int *__restrict__ x, const int *__restrict__ y,
+                               int *__restrict__ link, unsigned *__restrict__ zmask) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const int64_t e = r % E;
+  link[r] = (int)e;
+  unsigned zm = 0;
+  for (int a = 0; a < A; ++a) {
+    const int xv = x[r * A + a];
+    if (xv >= 0 && xv != y[e * A + a]) zm |= 1u << a;
+  }
+  zmask[r] = zm;
+}
+__global__ void k_pack_z(int64_t R, int A, const uint8_t *__restrict__ z, unsigned *__restrict__ zmask) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  unsigned zm = 0;
+  for (int a = 0; a < A; ++a) zm |= (z[r * A + a] ? 1u : 0u) << a;
+  zmask[r] = zm;
+}
+__global__ void k_unpack_z(int64_t R, int A, const unsigned *__restrict__ zmask, uint8_t *__restrict__ z) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const unsigned zm = zmask[r];
+  for (int a = 0; a < A; ++a) z[r * A + a] = (zm >> a) & 1u;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-side context
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    release();
+    n = count;
+    return cudaMalloc((void **)&p, std::max<size_t>(count, 1) * sizeof(T));
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  ~DevBuf() { release(); }
+};
+
+struct dbl_ctx {
+  int A = 0, F = 0, P = 1, device = 0;
+  uint64_t seed = 0;
+  int rank = 0, world = 1;
+  std::vector<double> alpha, beta;
+  std::string err;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  // model (device)
+  std::vector<DevBuf<double>> dtab;  // per-attr double tables
+  std::vector<DevBuf<int>> itab;
+  DevBuf<AttrDev> attrs;
+  std::vector<AttrDev> h_attrs;
+  DevBuf<int> tree_buf;
+  TreeDev tree{};
+
+  // state
+  int64_t R = 0, E = 0, iteration = 0;
+  bool has_state = false;
+  DevBuf<int> x, file, link, newlink, y, blk;
+  DevBuf<unsigned> zmask;
+  DevBuf<double> entN, theta;
+  std::vector<double> h_theta;
+  std::vector<int64_t> file_sizes;
+
+  // layout
+  DevBuf<int> iota, blk_sorted, ent_sorted, rec_key, rec_key_sorted, rec_sorted, ent_cnt, rec_cnt;
+  DevBuf<int> ent_ptr, tile_ptr, rec_ptr, cta_ptr, tiles;
+  DevBuf<int> link_sorted, rec_by_ent, ent_rec_cnt, ent_rec_ptr;
+  DevBuf<unsigned char> cub_tmp;
+  size_t cub_bytes = 0;
+  int max_ctas = 0;
+
+  // summary
+  DevBuf<long long> counts;  // A*F + (A+1) + 2
+  DevBuf<double> loglik;
+  DevBuf<int> status;
+  DevBuf<unsigned long long> pairs;
+  std::vector<long long> h_counts;
+  double h_loglik_part = 0.0;
+  int64_t h_pairs = 0;
+
+  int64_t launches = 0;
+  double link_ms = 0.0;
+  double last_sweep_ms = 0.0;
+  int64_t link_launches = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_events;
+
+  void set_error(const std::string &s) { err = s; }
+  int n_counts() const { return A * F + (A + 1) + 2; }
+  int iso_slot() const { return A * F + (A + 1); }
+};
+
+static inline int grid_for(int64_t n, int bs) { return (int)std::max<int64_t>(1, (n + bs - 1) / bs); }
+
+static int upload_tree(dbl_ctx *ctx, const dbl_kdtree *t) {
+  if (t) {
+    const int n = t->n_nodes;
+    std::vector<int> pack;
+    pack.insert(pack.end(), t->attr.begin(), t->attr.end());
+    pack.insert(pack.end(), t->kind.begin(), t->kind.end());
+    pack.insert(pack.end(), t->split.begin(), t->split.end());
+    pack.insert(pack.end(), t->set_ptr.begin(), t->set_ptr.end());
+    pack.insert(pack.end(), t->leaf_no.begin(), t->leaf_no.end());
+    pack.insert(pack.end(), t->set_val.begin(), t->set_val.end());
+    for (int i = 0; i < n; ++i)
+      if (t->attr[i] >= ctx->A) { ctx->set_error("partitioner attribute id out of range"); return DBL_ERR_INVALID; }
+    CUDA_TRY(ctx->tree_buf.alloc(pack.size()));
+    CUDA_TRY(cudaMemcpy(ctx->tree_buf.p, pack.data(), pack.size() * sizeof(int), cudaMemcpyHostToDevice));
+    int *base = ctx->tree_buf.p;
+    ctx->tree.n_nodes = n;
+    ctx->tree.attr = base;
+    ctx->tree.kind = base + n;
+    ctx->tree.split = base + 2 * n;
+    ctx->tree.set_ptr = base + 3 * n;
+    ctx->tree.leaf_no = base + 3 * n + (n + 1);
+    ctx->tree.set_val = base + 4 * n + (n + 1);
+    ctx->P = t->n_leaves;
+  } else {
+    ctx->tree.n_nodes = 0;
+    ctx->P = 1;
+  }
+  return DBL_OK;
+}
+
+static int upload_model(dbl_ctx *ctx, const dbl_model_desc *d) {
+  const int A = d->num_attrs;
+  ctx->h_attrs.resize(A);
+  ctx->dtab.resize((size_t)A * 9);
+  ctx->itab.resize((size_t)A * 2);
+  auto up_d = [&](DevBuf<double> &b, const std::vector<double> &v) -> cudaError_t {
+    cudaError_t e = b.alloc(v.size());
+    if (e != cudaSuccess) return e;
+    if (v.empty()) return cudaSuccess;
+    return cudaMemcpy(b.p, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice);
+  };
+  auto up_i = [&](DevBuf<int> &b, const std::vector<int32_t> &v) -> cudaError_t {
+    cudaError_t e = b.alloc(v.size());
+    if (e != cudaSuccess) return e;
+    if (v.empty()) return cudaSuccess;
+    return cudaMemcpy(b.p, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice);
+  };
+  for (int a = 0; a < A; ++a) {
+    const dbl_index *ix = d->indexes[a];
+    DevBuf<double> *t = &ctx->dtab[(size_t)a * 9];
+    DevBuf<int> *ti = &ctx->itab[(size_t)a * 2];
+    CUDA_TRY(up_d(t[0], ix->phi));
+    CUDA_TRY(up_d(t[1], ix->probs));
+    CUDA_TRY(up_d(t[2], ix->norm));
+    CUDA_TRY(up_d(t[3], ix->invnorm));
+    CUDA_TRY(up_d(t[4], ix->pk));
+    CUDA_TRY(up_d(t[5], ix->cdf));
+    CUDA_TRY(up_d(t[6], ix->logphi));
+    CUDA_TRY(up_d(t[7], ix->lognorm));
+    CUDA_TRY(up_d(t[8], ix->expsim));
+    CUDA_TRY(up_i(ti[0], ix->rowptr));
+    CUDA_TRY(up_i(ti[1], ix->col));
+    AttrDev &h = ctx->h_attrs[a];
+    h.V = ix->V; h.is_const = ix->is_const ? 1 : 0; h.kmax = ix->kmax; h.pad = 0;
+    h.phi = t[0].p; h.probs = t[1].p; h.norm = t[2].p; h.invnorm = t[3].p; h.pk = t[4].p; h.cdf = t[5].p;
+    h.logphi = t[6].p; h.lognorm = t[7].p; h.expsim = t[8].p;
+    h.rowptr = ti[0].p; h.col = ti[1].p;
+  }
+  CUDA_TRY(ctx->attrs.alloc(A));
+  CUDA_TRY(cudaMemcpy(ctx->attrs.p, ctx->h_attrs.data(), sizeof(AttrDev) * A, cudaMemcpyHostToDevice));
+  return upload_tree(ctx, d->tree);
+}
+
+extern "C" int dbl_ctx_create(dbl_ctx **out, const dbl_model_desc *d) {
+  if (!out || !d || d->num_attrs <= 0 || d->num_attrs > DBL_MAX_ATTRS || d->num_files <= 0 || !d->indexes ||
+      !d->alpha || !d->beta)
+    return DBL_ERR_INVALID;
+  for (int a = 0; a < d->num_attrs; ++a)
+    if (!d->indexes[a] || !(d->alpha[a] > 0.0) || !(d->beta[a] > 0.0)) return DBL_ERR_INVALID;  // package.scala:165
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return DBL_ERR_CUDA;  // no CPU fallback
+  auto *ctx = new dbl_ctx();
+  ctx->A = d->num_attrs;
+  ctx->F = d->num_files;
+  ctx->seed = d->seed;
+  ctx->rank = d->rank;
+  ctx->world = d->world_size > 0 ? d->world_size : 1;
+  ctx->alpha.assign(d->alpha, d->alpha + ctx->A);
+  ctx->beta.assign(d->beta, d->beta + ctx->A);
+  cudaGetDevice(&ctx->device);
+  *out = ctx;
+  CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreate(&ctx->ev0));
+  CUDA_TRY(cudaEventCreate(&ctx->ev1));
+  int rc = upload_model(ctx, d);
+  if (rc != DBL_OK) return rc;
+  CUDA_TRY(ctx->counts.alloc(ctx->n_counts()));
+  CUDA_TRY(ctx->loglik.alloc(1));
+  CUDA_TRY(ctx->status.alloc(1));
+  CUDA_TRY(ctx->pairs.alloc(1));
+  CUDA_TRY(cudaMemset(ctx->status.p, 0, sizeof(int)));
+  CUDA_TRY(cudaMemset(ctx->pairs.p, 0, sizeof(unsigned long long)));
+  CUDA_TRY(ctx->theta.alloc((size_t)ctx->A * ctx->F));
+  ctx->h_theta.assign((size_t)ctx->A * ctx->F, 0.0);
+  ctx->h_counts.assign(ctx->n_counts(), 0);
+  return DBL_OK;
+}
+
+extern "C" void dbl_ctx_destroy(dbl_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (auto &pe : ctx->pending_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+extern "C" const char *dbl_last_error(const dbl_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" int64_t dbl_num_records(const dbl_ctx *ctx) { return ctx ? ctx->R : 0; }
+extern "C" int64_t dbl_num_entities(const dbl_ctx *ctx) { return ctx ? ctx->E : 0; }
+extern "C" int64_t dbl_iteration(const dbl_ctx *ctx) { return ctx ? ctx->iteration : 0; }
+extern "C" int64_t dbl_kernel_launches(const dbl_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" const char *dbl_version(void) { return "dblink_b200 0.1 (sm_100a)"; }
+
+static int alloc_blocks(dbl_ctx *ctx) {
+  const int P = ctx->P;
+  CUDA_TRY(ctx->ent_cnt.alloc(P));
+  CUDA_TRY(ctx->rec_cnt.alloc(P));
+  CUDA_TRY(ctx->ent_ptr.alloc(P + 1));
+  CUDA_TRY(ctx->tile_ptr.alloc(P + 1));
+  CUDA_TRY(ctx->rec_ptr.alloc(P + 1));
+  CUDA_TRY(ctx->cta_ptr.alloc(P + 1));
+  const size_t max_tiles = (size_t)(ctx->E / TE) + (size_t)P + 1;
+  CUDA_TRY(ctx->tiles.alloc(max_tiles * tile_words(ctx->A)));
+  ctx->max_ctas = (int)((ctx->R + LINK_WARPS - 1) / LINK_WARPS) + P;
+  return DBL_OK;
+}
+
+static int alloc_state(dbl_ctx *ctx, int64_t R, int64_t E) {
+  const int A = ctx->A;
+  if (R <= 0 || E <= 0 || R > 0x7fffffff || E > 0x7fffffff) { ctx->set_error("bad R/E"); return DBL_ERR_INVALID; }
+  ctx->R = R; ctx->E = E;
+  CUDA_TRY(ctx->x.alloc((size_t)R * A));
+  CUDA_TRY(ctx->file.alloc(R));
+  CUDA_TRY(ctx->link.alloc(R));
+  CUDA_TRY(ctx->newlink.alloc(R));
+  CUDA_TRY(ctx->zmask.alloc(R));
+  CUDA_TRY(ctx->y.alloc((size_t)E * A));
+  CUDA_TRY(ctx->blk.alloc(E));
+  CUDA_TRY(ctx->entN.alloc(E));
+  const int64_t M = std::max(R, E);
+  CUDA_TRY(ctx->iota.alloc(M));
+  k_iota<<<grid_for(M, 256), 256, 0, ctx->stream>>>(M, ctx->iota.p);
+  CUDA_TRY(ctx->blk_sorted.alloc(E));
+  CUDA_TRY(ctx->ent_sorted.alloc(E));
+  CUDA_TRY(ctx->rec_key.alloc(R));
+  CUDA_TRY(ctx->rec_key_sorted.alloc(R));
+  CUDA_TRY(ctx->rec_sorted.alloc(R));
+  { int rc = alloc_blocks(ctx); if (rc) return rc; }
+  CUDA_TRY(ctx->link_sorted.alloc(R));
+  CUDA_TRY(ctx->rec_by_ent.alloc(R));
+  CUDA_TRY(ctx->ent_rec_cnt.alloc(E + 1));
+  CUDA_TRY(ctx->ent_rec_ptr.alloc(E + 1));
+  size_t b1 = 0, b2 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, b1, (const int *)nullptr, (int *)nullptr, (const int *)nullptr,
+                                  (int *)nullptr, (int)M, 0, 32, ctx->stream);
+  cub::DeviceScan::ExclusiveSum(nullptr, b2, (const int *)nullptr, (int *)nullptr, (int)(E + 1), ctx->stream);
+  ctx->cub_bytes = std::max(b1, b2) + 256;
+  CUDA_TRY(ctx->cub_tmp.alloc(ctx->cub_bytes));
+  return DBL_OK;
+}
+
+static int bits_for(int64_t n) {
+  int b = 1;
+  while (((int64_t)1 << b) < n) ++b;
+  return b;
+}
+
+// CSR entity -> linked records in ascending record id (LinksIndex, GU:84-119)
+static int build_links_csr(dbl_ctx *ctx) {
+  const int64_t R = ctx->R, E = ctx->E;
+  size_t tb = ctx->cub_bytes;
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, (const int *)ctx->link.p, ctx->link_sorted.p,
+                                           (const int *)ctx->iota.p, ctx->rec_by_ent.p, (int)R, 0, bits_for(E),
+                                           ctx->stream));
+  CUDA_TRY(cudaMemsetAsync(ctx->ent_rec_cnt.p, 0, sizeof(int) * (E + 1), ctx->stream));
+  k_hist<<<grid_for(R, 256), 256, 0, ctx->stream>>>(R, ctx->link.p, ctx->ent_rec_cnt.p);
+  tb = ctx->cub_bytes;
+  CUDA_TRY(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tb, (const int *)ctx->ent_rec_cnt.p, ctx->ent_rec_ptr.p,
+                                         (int)(E + 1), ctx->stream));
+  ctx->launches += 5;
+  return DBL_OK;
+}
+
+// group entities and records by block, build the tiled entity table (replaces the shuffle, GU:144)
+static int relayout(dbl_ctx *ctx) {
+  const int64_t R = ctx->R, E = ctx->E;
+  const int A = ctx->A, P = ctx->P;
+  const int pb = bits_for(P);
+  size_t tb = ctx->cub_bytes;
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, (const int *)ctx->blk.p, ctx->blk_sorted.p,
+                                           (const int *)ctx->iota.p, ctx->ent_sorted.p, (int)E, 0, pb, ctx->stream));
+  k_rec_block_keys<<<grid_for(R, 256), 256, 0, ctx->stream>>>(R, ctx->link.p, ctx->blk.p, ctx->rec_key.p);
+  tb = ctx->cub_bytes;
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, (const int *)ctx->rec_key.p, ctx->rec_key_sorted.p,
+                                           (const int *)ctx->iota.p, ctx->rec_sorted.p, (int)R, 0, pb, ctx->stream));
+  CUDA_TRY(cudaMemsetAsync(ctx->ent_cnt.p, 0, sizeof(int) * P, ctx->stream));
+  CUDA_TRY(cudaMemsetAsync(ctx->rec_cnt.p, 0, sizeof(int) * P, ctx->stream));
+  k_hist<<<grid_for(E, 256), 256, 0, ctx->stream>>>(E, ctx->blk.p, ctx->ent_cnt.p);
+  k_hist<<<grid_for(R, 256), 256, 0, ctx->stream>>>(R, ctx->rec_key.p, ctx->rec_cnt.p);
+  k_block_scan<<<1, 32, 0, ctx->stream>>>(P, ctx->ent_cnt.p, ctx->rec_cnt.p, ctx->ent_ptr.p, ctx->tile_ptr.p,
+                                          ctx->rec_ptr.p, ctx->cta_ptr.p, LINK_WARPS);
+  CUDA_TRY(cudaMemsetAsync(ctx->tiles.p, 0, ctx->tiles.n * sizeof(int), ctx->stream));
+  k_build_tiles<<<grid_for(E, 256), 256, 0, ctx->stream>>>(E, A, ctx->y.p, ctx->entN.p, ctx->blk_sorted.p,
+                                                           ctx->ent_sorted.p, ctx->ent_ptr.p, ctx->tile_ptr.p,
+                                                           ctx->tiles.p);
+  ctx->launches += 10;
+  CUDA_TRY(cudaGetLastError());
+  return DBL_OK;
+}
+
+// entity N / block ids / entity+record summary of the current state
+static int refresh_summary(dbl_ctx *ctx, bool draw_z, int sampler) {
+  const int A = ctx->A, F = ctx->F;
+  (void)sampler;
+  CUDA_TRY(cudaMemsetAsync(ctx->counts.p, 0, sizeof(long long) * ctx->n_counts(), ctx->stream));
+  CUDA_TRY(cudaMemsetAsync(ctx->loglik.p, 0, sizeof(double), ctx->stream));
+  k_entity_post<<<grid_for(ctx->E, 256), 256, 0, ctx->stream>>>(ctx->E, A, ctx->y.p, ctx->attrs.p, ctx->tree,
+                                                               ctx->entN.p, ctx->blk.p, ctx->ent_rec_ptr.p,
+                                                               ctx->counts.p, ctx->iso_slot(), ctx->loglik.p);
+  DistParams dp;
+  dp.A = A; dp.F = F; dp.draw = draw_z ? 1 : 0; dp.seed = ctx->seed; dp.iter = (uint32_t)(ctx->iteration + 1);
+  dp.R = ctx->R; dp.attrs = ctx->attrs.p; dp.x = ctx->x.p; dp.file = ctx->file.p; dp.link = ctx->link.p;
+  dp.y = ctx->y.p; dp.zmask = ctx->zmask.p; dp.theta = ctx->theta.p; dp.counts = ctx->counts.p;
+  dp.loglik = ctx->loglik.p;
+  k_dist<<<grid_for(ctx->R, 256), 256, 0, ctx->stream>>>(dp);
+  ctx->launches += 4;
+  CUDA_TRY(cudaGetLastError());
+  return DBL_OK;
+}
+
+static int fetch_summary(dbl_ctx *ctx) {
+  CUDA_TRY(cudaMemcpyAsync(ctx->h_counts.data(), ctx->counts.p, sizeof(long long) * ctx->n_counts(),
+                           cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(&ctx->h_loglik_part, ctx->loglik.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  int st = 0;
+  CUDA_TRY(cudaMemcpyAsync(&st, ctx->status.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  unsigned long long pr = 0;
+  CUDA_TRY(cudaMemcpyAsync(&pr, ctx->pairs.p, sizeof(pr), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->h_pairs = (int64_t)pr;
+  if (st) {
+    ctx->set_error("zero probability mass in a link draw");
+    cudaMemsetAsync(ctx->status.p, 0, sizeof(int), ctx->stream);
+    return DBL_ERR_ZERO_MASS;
+  }
+  return DBL_OK;
+}
+
+static int finish_new_state(dbl_ctx *ctx) {
+  // file sizes (RecordsCache.fileSizes)
+  std::vector<int> hf(ctx->R);
+  CUDA_TRY(cudaMemcpyAsync(hf.data(), ctx->file.p, sizeof(int) * ctx->R, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->file_sizes.assign(ctx->F, 0);
+  for (int64_t r = 0; r < ctx->R; ++r) {
+    if (hf[r] < 0 || hf[r] >= ctx->F) { ctx->set_error("file id out of range"); return DBL_ERR_INVALID; }
+    ctx->file_sizes[hf[r]]++;
+  }
+  int rc = build_links_csr(ctx);
+  if (rc) return rc;
+  rc = refresh_summary(ctx, false, 0);
+  if (rc) return rc;
+  rc = relayout(ctx);
+  if (rc) return rc;
+  rc = fetch_summary(ctx);
+  if (rc) return rc;
+  ctx->has_state = true;
+  return DBL_OK;
+}
+
+static int check_ids(dbl_ctx *ctx, int64_t R, const int32_t *x) {
+  for (int64_t r = 0; r < R; ++r)
+    for (int a = 0; a < ctx->A; ++a) {
+      const int v = x[r * ctx->A + a];
+      if (v < -1 || v >= ctx->h_attrs[a].V) { ctx->set_error("record value id out of range"); return DBL_ERR_INVALID; }
+    }
+  return DBL_OK;
+}
+
+extern "C" int dbl_set_partitioner(dbl_ctx *ctx, const dbl_kdtree *tree) {
+  if (!ctx) return DBL_ERR_INVALID;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  int rc = upload_tree(ctx, tree);
+  if (rc) return rc;
+  if (!ctx->has_state) return DBL_OK;
+  rc = alloc_blocks(ctx);
+  if (rc) return rc;
+  rc = refresh_summary(ctx, false, 0);  // recomputes block ids (and the unchanged summary)
+  if (rc) return rc;
+  rc = relayout(ctx);
+  if (rc) return rc;
+  return fetch_summary(ctx);
+}
+extern "C" int32_t dbl_num_partitions(const dbl_ctx *ctx) { return ctx ? ctx->P : 0; }
+
+extern "C" int dbl_state_init(dbl_ctx *ctx, int64_t R, const int32_t *x, const int32_t *file, int64_t pop) {
+  if (!ctx || !x || !file) return DBL_ERR_INVALID;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const int64_t E = pop > 0 ? pop : R;
+  int rc = check_ids(ctx, R, x);
+  if (rc) return rc;
+  rc = alloc_state(ctx, R, E);
+  if (rc) return rc;
+  const int A = ctx->A;
+  CUDA_TRY(cudaMemcpyAsync(ctx->x.p, x, sizeof(int) * R * A, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(ctx->file.p, file, sizeof(int) * R, cudaMemcpyHostToDevice, ctx->stream));
+  k_init_entities<<<grid_for(E * A, 256), 256, 0, ctx->stream>>>(E, R, A, ctx->seed, ctx->attrs.p, ctx->x.p, ctx->y.p);
+  k_init_records<<<grid_for(R, 256), 256, 0, ctx->stream>>>(E, R, A, ctx->x.p, ctx->y.p, ctx->link.p, ctx->zmask.p);
+  ctx->launches += 3;
+  for (int a = 0; a < A; ++a)
+    for (int f = 0; f < ctx->F; ++f)
+      ctx->h_theta[a * ctx->F + f] = ctx->alpha[a] / (ctx->alpha[a] + ctx->beta[a]);  // DistortionProbs.scala:38-40
+  CUDA_TRY(cudaMemcpyAsync(ctx->theta.p, ctx->h_theta.data(), sizeof(double) * A * ctx->F, cudaMemcpyHostToDevice,
+                           ctx->stream));
+  ctx->iteration = 0;
+  return finish_new_state(ctx);
+}
+
+extern "C" int dbl_state_upload(dbl_ctx *ctx, int64_t R, int64_t E, const int32_t *x, const int32_t *file,
+                                const uint8_t *z, const int32_t *link, const int32_t *y, const double *theta,
+                                int64_t iteration) {
+  if (!ctx || !x || !file || !z || !link || !y || !theta) return DBL_ERR_INVALID;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  int rc = check_ids(ctx, R, x);
+  if (rc) return rc;
+  for (int64_t r = 0; r < R; ++r)
+    if (link[r] < 0 || link[r] >= E) { ctx->set_error("link out of range"); return DBL_ERR_INVALID; }
+  for (int64_t e = 0; e < E; ++e)
+    for (int a = 0; a < ctx->A; ++a)
+      if (y[e * ctx->A + a] < 0 || y[e * ctx->A + a] >= ctx->h_attrs[a].V) {
+        ctx->set_error("entity value id out of range");
+        return DBL_ERR_INVALID;
+      }
+  rc = alloc_state(ctx, R, E);
+  if (rc) return rc;
+  const int A = ctx->A;
+  DevBuf<uint8_t> zb;
+  CUDA_TRY(zb.alloc((size_t)R * A));
+  CUDA_TRY(cudaMemcpyAsync(ctx->x.p, x, sizeof(int) * R * A, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(ctx->file.p, file, sizeof(int) * R, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(zb.p, z, (size_t)R * A, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(ctx->link.p, link, sizeof(int) * R, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(ctx->y.p, y, sizeof(int) * E * A, cudaMemcpyHostToDevice, ctx->stream));
+  k_pack_z<<<grid_for(R, 256), 256, 0, ctx->stream>>>(R, A, zb.p, ctx->zmask.p);
+  ctx->launches += 2;
+  std::copy(theta, theta + (size_t)A * ctx->F, ctx->h_theta.begin());
+  CUDA_TRY(cudaMemcpyAsync(ctx->theta.p, ctx->h_theta.data(), sizeof(double) * A * ctx->F, cudaMemcpyHostToDevice,
+                           ctx->stream));
+  ctx->iteration = iteration;
+  rc = finish_new_state(ctx);
+  return rc;
+}
+
+extern "C" int dbl_state_download(dbl_ctx *ctx, uint8_t *z, int32_t *link, int32_t *y, double *theta,
+                                  int32_t *block_of_entity) {
+  if (!ctx) return DBL_ERR_INVALID;
+  if (!ctx->has_state) { ctx->set_error("no state"); return DBL_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const int A = ctx->A;
+  DevBuf<uint8_t> zb;
+  if (z) {
+    CUDA_TRY(zb.alloc((size_t)ctx->R * A));
+    k_unpack_z<<<grid_for(ctx->R, 256), 256, 0, ctx->stream>>>(ctx->R, A, ctx->zmask.p, zb.p);
+    ctx->launches += 1;
+    CUDA_TRY(cudaMemcpyAsync(z, zb.p, (size_t)ctx->R * A, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (link) CUDA_TRY(cudaMemcpyAsync(link, ctx->link.p, sizeof(int) * ctx->R, cudaMemcpyDeviceToHost, ctx->stream));
+  if (y) CUDA_TRY(cudaMemcpyAsync(y, ctx->y.p, sizeof(int) * ctx->E * A, cudaMemcpyDeviceToHost, ctx->stream));
+  if (block_of_entity)
+    CUDA_TRY(cudaMemcpyAsync(block_of_entity, ctx->blk.p, sizeof(int) * ctx->E, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (theta) std::copy(ctx->h_theta.begin(), ctx->h_theta.end(), theta);
+  return DBL_OK;
+}
+
+extern "C" int dbl_links_download(dbl_ctx *ctx, int32_t *link_out, int32_t *block_out) {
+  return dbl_state_download(ctx, nullptr, link_out, nullptr, nullptr, block_out);
+}
+
+static void drain_link_events(dbl_ctx *ctx) {
+  for (auto &pe : ctx->pending_events) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, pe.first, pe.second) == cudaSuccess) {
+      ctx->link_ms += ms;
+      ctx->link_launches += 1;
+    }
+    cudaEventDestroy(pe.first);
+    cudaEventDestroy(pe.second);
+  }
+  ctx->pending_events.clear();
+}
+
+extern "C" int dbl_sweep(dbl_ctx *ctx, int sampler, int32_t n_sweeps) {
+  if (!ctx) return DBL_ERR_INVALID;
+  if (sampler < 0 || sampler > 3 || n_sweeps < 0) { ctx->set_error("bad sampler / n_sweeps"); return DBL_ERR_INVALID; }
+  if (!ctx->has_state) { ctx->set_error("dbl_sweep before dbl_state_init/upload"); return DBL_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const int A = ctx->A, F = ctx->F;
+  CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+  for (int s = 0; s < n_sweeps; ++s) {
+    const uint32_t it = (uint32_t)(ctx->iteration + 1);
+    // (1) theta | summary of the previous state (State.scala:83, GU:305-320) -- A*F scalars on the host
+    {
+      std::vector<int64_t> agg((size_t)A * F);
+      for (int i = 0; i < A * F; ++i) agg[i] = ctx->h_counts[i];
+      host_draw_theta(A, F, ctx->alpha.data(), ctx->beta.data(), ctx->seed, agg.data(), ctx->file_sizes.data(), it,
+                      ctx->h_theta.data());
+      CUDA_TRY(cudaMemcpyAsync(ctx->theta.p, ctx->h_theta.data(), sizeof(double) * A * F, cudaMemcpyHostToDevice,
+                               ctx->stream));
+    }
+    // (2) links
+    LinkParams lp;
+    lp.A = A; lp.F = F; lp.P = ctx->P; lp.sampler = sampler; lp.seed = ctx->seed; lp.iter = it;
+    lp.attrs = ctx->attrs.p; lp.x = ctx->x.p; lp.file = ctx->file.p; lp.link = ctx->link.p; lp.zmask = ctx->zmask.p;
+    lp.theta = ctx->theta.p; lp.ent_ptr = ctx->ent_ptr.p; lp.tile_ptr = ctx->tile_ptr.p; lp.rec_ptr = ctx->rec_ptr.p;
+    lp.cta_ptr = ctx->cta_ptr.p; lp.ent_sorted = ctx->ent_sorted.p; lp.rec_sorted = ctx->rec_sorted.p;
+    lp.tiles = ctx->tiles.p; lp.newlink = ctx->newlink.p; lp.status = ctx->status.p; lp.pairs = ctx->pairs.p;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    CUDA_TRY(cudaEventRecord(e0, ctx->stream));
+    k_link<<<ctx->max_ctas, LINK_WARPS * 32, 0, ctx->stream>>>(lp);
+    CUDA_TRY(cudaEventRecord(e1, ctx->stream));
+    ctx->pending_events.emplace_back(e0, e1);
+    ctx->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    std::swap(ctx->link.p, ctx->newlink.p);
+    // (3) entity values
+    int rc = build_links_csr(ctx);
+    if (rc) return rc;
+    ValParams vp;
+    vp.A = A; vp.F = F; vp.sampler = sampler; vp.seed = ctx->seed; vp.iter = it; vp.E = ctx->E;
+    vp.attrs = ctx->attrs.p; vp.x = ctx->x.p; vp.file = ctx->file.p; vp.zmask = ctx->zmask.p; vp.theta = ctx->theta.p;
+    vp.ent_rec_ptr = ctx->ent_rec_ptr.p; vp.rec_by_ent = ctx->rec_by_ent.p; vp.y = ctx->y.p;
+    k_values<<<grid_for(ctx->E * A, 128), 128, 0, ctx->stream>>>(vp);
+    ctx->launches += 1;
+    // (4) N(e), new block ids, distortions, summary
+    rc = refresh_summary(ctx, true, sampler);
+    if (rc) return rc;
+    // (5) re-partition
+    rc = relayout(ctx);
+    if (rc) return rc;
+    ctx->iteration += 1;
+    rc = fetch_summary(ctx);  // also the sync point that bounds the sweep
+    if (rc) return rc;
+  }
+  CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+  CUDA_TRY(cudaEventSynchronize(ctx->ev1));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  ctx->last_sweep_ms = ms;
+  drain_link_events(ctx);
+  return DBL_OK;
+}
+
+extern "C" double dbl_last_sweep_ms(const dbl_ctx *ctx) { return ctx ? ctx->last_sweep_ms : 0.0; }
+
+extern "C" double dbl_link_kernel_ms(dbl_ctx *ctx, int64_t *launches) {
+  if (!ctx) return 0.0;
+  const double ms = ctx->link_ms;
+  if (launches) *launches = ctx->link_launches;
+  ctx->link_ms = 0.0;
+  ctx->link_launches = 0;
+  return ms;
+}
+
+extern "C" int dbl_summary(dbl_ctx *ctx, dbl_summary_head *head, int64_t *agg_dist, int64_t *rec_dist, double *theta) {
+  if (!ctx) return DBL_ERR_INVALID;
+  if (!ctx->has_state) { ctx->set_error("no state"); return DBL_ERR_STATE; }
+  const int A = ctx->A, F = ctx->F;
+  if (head) {
+    head->iteration = ctx->iteration;
+    head->num_isolates = ctx->h_counts[ctx->iso_slot()];
+    double ll = ctx->h_loglik_part;
+    for (int a = 0; a < A; ++a)
+      for (int f = 0; f < F; ++f) {  // GU:286-293
+        const double th = ctx->h_theta[a * F + f];
+        const double nd = (double)ctx->h_counts[a * F + f];
+        ll += (ctx->alpha[a] + nd - 1.0) * std::log(th) +
+              (ctx->beta[a] + (double)ctx->file_sizes[f] - nd - 1.0) * std::log(1.0 - th);
+      }
+    head->log_likelihood = ll;
+    head->pairs_scored = ctx->h_pairs;
+  }
+  if (agg_dist) for (int i = 0; i < A * F; ++i) agg_dist[i] = ctx->h_counts[i];
+  if (rec_dist) for (int i = 0; i <= A; ++i) rec_dist[i] = ctx->h_counts[A * F + i];
+  if (theta) std::copy(ctx->h_theta.begin(), ctx->h_theta.end(), theta);
+  return DBL_OK;
+}

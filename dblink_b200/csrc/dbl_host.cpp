@@ -1,0 +1,389 @@
+// Host half of libdblink_b200: model-table construction, k-d tree, the A x F Beta draws of theta.
+// These are the driver-side pieces of the reference (they run once, or once per sweep on A*F scalars);
+// everything that scales with records/entities is in dbl_engine.cu.
+//
+// Reference paths: src/main/scala/com/github/cleanzr/dblink/ ; GU = GibbsUpdates.scala.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <numeric>
+#include <thread>
+
+#include "dbl_internal.h"
+
+// ---------------------------------------------------------------------------------------------------
+// SimilarityFn.scala:61-98
+// ---------------------------------------------------------------------------------------------------
+int host_levenshtein(const char *a, int la, const char *b, int lb) {
+  if (la == 0) return lb;
+  if (lb == 0) return la;
+  // two-row DP on the shorter string
+  if (lb > la) { std::swap(a, b); std::swap(la, lb); }
+  int buf[2][256];
+  std::vector<int> big;
+  int *prev = buf[0], *cur = buf[1];
+  if (lb + 1 > 256) { big.resize(2 * (size_t)(lb + 1)); prev = big.data(); cur = big.data() + lb + 1; }
+  for (int j = 0; j <= lb; ++j) prev[j] = j;
+  for (int i = 1; i <= la; ++i) {
+    cur[0] = i;
+    const char ca = a[i - 1];
+    for (int j = 1; j <= lb; ++j) {
+      const int sub = prev[j - 1] + (ca != b[j - 1] ? 1 : 0);
+      const int del = prev[j] + 1, ins = cur[j - 1] + 1;
+      cur[j] = std::min(sub, std::min(del, ins));
+    }
+    std::swap(prev, cur);
+  }
+  return prev[lb];
+}
+
+double host_similarity_from_distance(int dist, int la, int lb, double threshold, double max_sim) {
+  const int total = la + lb;
+  double unit = 1.0;                        // SimilarityFn.scala:86-90
+  if (total > 0) {
+    const double d = (double)dist;
+    unit = 1.0 - 2.0 * d / ((double)total + d);
+  }
+  const double factor = max_sim / (max_sim - threshold);  // :63
+  const double s = factor * (max_sim * unit - threshold);  // :66
+  return s > 0.0 ? s : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// AttributeIndex.scala:107-245
+// ---------------------------------------------------------------------------------------------------
+void dbl_index::finish() {
+  norm.assign(V, 1.0);
+  invnorm.assign(V, 1.0);
+  if (!is_const) {
+    for (int v = 0; v < V; ++v) {  // computeSimNormalizations, :234-245
+      double acc = 0.0;
+      int p = rowptr[v];
+      const int pe = rowptr[v + 1];
+      for (int w = 0; w < V; ++w) {
+        double e = 1.0;
+        if (p < pe && col[p] == w) e = expsim[p++];
+        acc += probs[w] * e;
+      }
+      invnorm[v] = acc;
+      norm[v] = 1.0 / acc;
+    }
+  }
+  // base pmfs: weight_k(v) = probs(v) * norm(v)^k by k successive multiplications, normalised
+  // like DiscreteDist does (random/IndexNonUniformDiscreteDist.scala:66-88); cdf = running sum.
+  pk.assign((size_t)(kmax + 1) * V, 0.0);
+  cdf.assign((size_t)(kmax + 1) * V, 0.0);
+  for (int k = 0; k <= kmax; ++k) {
+    double *p = pk.data() + (size_t)k * V, *c = cdf.data() + (size_t)k * V;
+    double z = 0.0;
+    for (int v = 0; v < V; ++v) {
+      double w = probs[v];
+      if (!is_const)
+        for (int i = 0; i < k; ++i) w = w * norm[v];
+      p[v] = w;
+      z += w;
+    }
+    double run = 0.0;
+    for (int v = 0; v < V; ++v) {
+      p[v] = p[v] / z;
+      run += p[v];
+      c[v] = run;
+    }
+  }
+  phi.assign(pk.begin(), pk.begin() + V);
+  logphi.resize(V);
+  lognorm.resize(V);
+  for (int v = 0; v < V; ++v) {
+    logphi[v] = std::log(phi[v]);
+    lognorm[v] = std::log(norm[v]);
+  }
+}
+
+extern "C" int dbl_index_build(dbl_index **out, const char *const *values, const double *weights, int32_t V,
+                               int similarity, double threshold, double max_sim, int32_t kmax) {
+  if (!out || !values || !weights || V <= 0 || kmax < 0) return DBL_ERR_INVALID;  // "index cannot be empty" :111
+  if (similarity != 0 && !(max_sim > 0.0 && threshold >= 0.0 && threshold < max_sim))
+    return DBL_ERR_INVALID;  // SimilarityFn.scala:59-61
+  auto *ix = new dbl_index();
+  ix->V = V;
+  ix->is_const = (similarity == 0);
+  ix->kmax = kmax;
+  std::vector<int> order(V);
+  std::iota(order.begin(), order.end(), 0);
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return std::strcmp(values[a], values[b]) < 0; });
+  ix->values.resize(V);
+  ix->probs.resize(V);
+  double total = 0.0;
+  for (int i = 0; i < V; ++i) total += weights[order[i]];
+  for (int i = 0; i < V; ++i) {
+    ix->values[i] = values[order[i]];
+    ix->probs[i] = weights[order[i]] / total;
+  }
+  ix->rowptr.assign(V + 1, 0);
+  if (!ix->is_const) {
+    // all-pairs thresholded similarity (computeSimValueIndex, :219-231), rows in parallel
+    std::vector<std::vector<std::pair<int32_t, double>>> rows(V);
+    std::vector<int> len(V);
+    for (int i = 0; i < V; ++i) len[i] = (int)ix->values[i].size();
+    std::atomic<int> next{0};
+    auto work = [&]() {
+      for (;;) {
+        const int i = next.fetch_add(16);
+        if (i >= V) break;
+        for (int r = i; r < std::min(V, i + 16); ++r) {
+          auto &row = rows[r];
+          for (int c = 0; c < V; ++c) {
+            const int d = host_levenshtein(ix->values[r].data(), len[r], ix->values[c].data(), len[c]);
+            const double e = std::exp(host_similarity_from_distance(d, len[r], len[c], threshold, max_sim));
+            if (e > 1.0) row.emplace_back(c, e);
+          }
+        }
+      }
+    };
+    unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (V < 512) nt = 1;
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; ++t) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+    for (int r = 0; r < V; ++r) ix->rowptr[r + 1] = ix->rowptr[r] + (int32_t)rows[r].size();
+    ix->col.resize(ix->rowptr[V]);
+    ix->expsim.resize(ix->rowptr[V]);
+    for (int r = 0; r < V; ++r) {
+      int p = ix->rowptr[r];
+      for (auto &ce : rows[r]) { ix->col[p] = ce.first; ix->expsim[p] = ce.second; ++p; }
+    }
+  }
+  ix->finish();
+  *out = ix;
+  return DBL_OK;
+}
+
+extern "C" int dbl_index_from_tables(dbl_index **out, int32_t V, int similarity, const double *probs,
+                                     const int32_t *rowptr, const int32_t *col, const double *expsim, int32_t kmax) {
+  if (!out || !probs || V <= 0 || kmax < 0) return DBL_ERR_INVALID;
+  auto *ix = new dbl_index();
+  ix->V = V;
+  ix->is_const = (similarity == 0);
+  ix->kmax = kmax;
+  ix->probs.assign(probs, probs + V);
+  ix->rowptr.assign(V + 1, 0);
+  if (!ix->is_const) {
+    if (!rowptr || !col || !expsim) { delete ix; return DBL_ERR_INVALID; }
+    ix->rowptr.assign(rowptr, rowptr + V + 1);
+    ix->col.assign(col, col + rowptr[V]);
+    ix->expsim.assign(expsim, expsim + rowptr[V]);
+  }
+  ix->finish();
+  *out = ix;
+  return DBL_OK;
+}
+
+extern "C" void dbl_index_free(dbl_index *ix) { delete ix; }
+extern "C" int32_t dbl_index_num_values(const dbl_index *ix) { return ix ? ix->V : 0; }
+extern "C" int32_t dbl_index_nnz(const dbl_index *ix) { return ix ? ix->rowptr[ix->V] : 0; }
+extern "C" int32_t dbl_index_value_id(const dbl_index *ix, const char *value) {
+  if (!ix || !value || ix->values.empty()) return -1;
+  auto it = std::lower_bound(ix->values.begin(), ix->values.end(), std::string(value));
+  if (it == ix->values.end() || *it != value) return -1;
+  return (int32_t)(it - ix->values.begin());
+}
+extern "C" const char *dbl_index_value(const dbl_index *ix, int32_t v) {
+  if (!ix || v < 0 || v >= (int32_t)ix->values.size()) return nullptr;
+  return ix->values[v].c_str();
+}
+extern "C" int dbl_index_tables(const dbl_index *ix, double *phi, double *norm, int32_t *rowptr, int32_t *col,
+                                double *expsim) {
+  if (!ix) return DBL_ERR_INVALID;
+  if (phi) std::copy(ix->phi.begin(), ix->phi.end(), phi);
+  if (norm) std::copy(ix->norm.begin(), ix->norm.end(), norm);
+  if (rowptr) std::copy(ix->rowptr.begin(), ix->rowptr.end(), rowptr);
+  if (col) std::copy(ix->col.begin(), ix->col.end(), col);
+  if (expsim) std::copy(ix->expsim.begin(), ix->expsim.end(), expsim);
+  return DBL_OK;
+}
+extern "C" double dbl_index_exp_sim(const dbl_index *ix, int32_t v1, int32_t v2) {
+  if (!ix || v1 < 0 || v2 < 0 || v1 >= ix->V || v2 >= ix->V)
+    return std::numeric_limits<double>::quiet_NaN();  // reference: require(...) throws, AttributeIndex.scala:184
+  if (ix->is_const) return 1.0;
+  const auto b = ix->col.begin() + ix->rowptr[v1], e = ix->col.begin() + ix->rowptr[v1 + 1];
+  const auto it = std::lower_bound(b, e, v2);
+  return (it != e && *it == v2) ? ix->expsim[it - ix->col.begin()] : 1.0;  // getOrElse(valueId2, 1.0), :185
+}
+extern "C" double dbl_similarity(int similarity, const char *a, const char *b, double threshold, double max_sim) {
+  if (similarity == 0) return 0.0;  // ConstantSimilarityFn, SimilarityFn.scala:50
+  const int la = (int)std::strlen(a), lb = (int)std::strlen(b);
+  return host_similarity_from_distance(host_levenshtein(a, la, b, lb), la, lb, threshold, max_sim);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// partitioning/KDTreePartitioner.scala:37-62,80-105; MutableBST.scala:51-111; DomainSplitter.scala:43-110
+// ---------------------------------------------------------------------------------------------------
+int32_t dbl_kdtree::leaf_node(const int32_t *yrow) const {
+  int32_t node = 0;
+  while (node < n_nodes && attr[node] >= 0) {
+    const int32_t v = yrow[attr[node]];
+    bool right;
+    if (kind[node]) right = std::binary_search(set_val.begin() + set_ptr[node], set_val.begin() + set_ptr[node + 1], v);
+    else right = v > split[node];
+    node = right ? 2 * node + 2 : 2 * node + 1;
+  }
+  return node;
+}
+
+extern "C" int dbl_kdtree_fit(dbl_kdtree **out, const int32_t *y, int64_t E, int32_t A, int32_t num_levels,
+                              const int32_t *attr_ids, int32_t n_attr_ids) {
+  if (!out || num_levels < 0 || num_levels > 20 || A <= 0) return DBL_ERR_INVALID;
+  if (num_levels > 0 && (!attr_ids || n_attr_ids <= 0 || !y)) return DBL_ERR_INVALID;  // KDTreePartitioner.scala:31
+  for (int i = 0; i < n_attr_ids; ++i)
+    if (attr_ids[i] < 0 || attr_ids[i] >= A) return DBL_ERR_INVALID;
+  auto *t = new dbl_kdtree();
+  const int n = (1 << (num_levels + 1)) - 1;
+  t->n_nodes = n;
+  t->attr.assign(n, -1);
+  t->kind.assign(n, 0);
+  t->split.assign(n, 0);
+  t->leaf_no.assign(n, -1);
+  t->leaf_no[0] = 0;
+  t->n_leaves = 1;
+  std::vector<std::vector<int32_t>> sets(n);
+  std::vector<int32_t> node_of((size_t)std::max<int64_t>(E, 1));
+  for (int level = 0; level < num_levels; ++level) {
+    const int attr = attr_ids[level % n_attr_ids];  // cycle, KDTreePartitioner.scala:45-49
+    // value histogram per frontier node (getNewSplits, :80-105)
+    std::map<int32_t, std::map<int32_t, double>> dom;
+    for (int64_t e = 0; e < E; ++e) dom[t->leaf_node(y + e * A)][y[e * A + attr]] += 1.0;
+    for (auto &nd : dom) {  // ascending node id (the reference's Map order is unspecified)
+      const int32_t node = nd.first;
+      std::vector<std::pair<int32_t, double>> d(nd.second.begin(), nd.second.end());  // ascending value
+      double half = 0.0;
+      for (auto &vw : d) half += vw.second;
+      half = half / 2.0;
+      if (d.size() <= 30) {  // LPTDomainSplitter, DomainSplitter.scala:86-110
+        std::stable_sort(d.begin(), d.end(), [](auto &p, auto &q) { return p.second > q.second; });
+        double left = 0.0, right = 0.0;
+        for (auto &vw : d) {
+          if (left >= right) { sets[node].push_back(vw.first); right += vw.second; }
+          else left += vw.second;
+        }
+        std::sort(sets[node].begin(), sets[node].end());
+        t->kind[node] = 1;
+      } else {  // RanDomainSplitter, DomainSplitter.scala:57-75
+        double cum = 0.0;
+        size_t i = 0;
+        while (cum <= half && i < d.size() - 1) { cum += d[i].second; ++i; }
+        t->kind[node] = 0;
+        t->split[node] = d[i].first;
+      }
+      t->attr[node] = attr;  // MutableBST.splitNode, MutableBST.scala:87-111
+      t->leaf_no[2 * node + 1] = t->leaf_no[node];
+      t->leaf_no[2 * node + 2] = t->n_leaves++;
+    }
+  }
+  t->set_ptr.assign(n + 1, 0);
+  for (int i = 0; i < n; ++i) {
+    t->set_ptr[i + 1] = t->set_ptr[i] + (int32_t)sets[i].size();
+    t->set_val.insert(t->set_val.end(), sets[i].begin(), sets[i].end());
+  }
+  *out = t;
+  return DBL_OK;
+}
+
+extern "C" int dbl_kdtree_from_arrays(dbl_kdtree **out, int32_t n, const int32_t *attr, const int32_t *kind,
+                                      const int32_t *split, const int32_t *set_ptr, const int32_t *set_val,
+                                      const int32_t *leaf_no) {
+  if (!out || n <= 0 || !attr || !kind || !split || !set_ptr || !leaf_no) return DBL_ERR_INVALID;
+  auto *t = new dbl_kdtree();
+  t->n_nodes = n;
+  t->attr.assign(attr, attr + n);
+  t->kind.assign(kind, kind + n);
+  t->split.assign(split, split + n);
+  t->set_ptr.assign(set_ptr, set_ptr + n + 1);
+  if (set_ptr[n] > 0) t->set_val.assign(set_val, set_val + set_ptr[n]);
+  t->leaf_no.assign(leaf_no, leaf_no + n);
+  int nl = 0;
+  for (int i = 0; i < n; ++i)
+    if (attr[i] < 0 && leaf_no[i] + 1 > nl) nl = leaf_no[i] + 1;
+  t->n_leaves = nl;
+  *out = t;
+  return DBL_OK;
+}
+extern "C" void dbl_kdtree_free(dbl_kdtree *t) { delete t; }
+extern "C" int32_t dbl_kdtree_num_nodes(const dbl_kdtree *t) { return t ? t->n_nodes : 0; }
+extern "C" int32_t dbl_kdtree_num_leaves(const dbl_kdtree *t) { return t ? t->n_leaves : 1; }
+extern "C" int32_t dbl_kdtree_set_len(const dbl_kdtree *t) { return t ? (int32_t)t->set_val.size() : 0; }
+extern "C" int dbl_kdtree_export(const dbl_kdtree *t, int32_t *attr, int32_t *kind, int32_t *split, int32_t *set_ptr,
+                                 int32_t *set_val, int32_t *leaf_no) {
+  if (!t) return DBL_ERR_INVALID;
+  if (attr) std::copy(t->attr.begin(), t->attr.end(), attr);
+  if (kind) std::copy(t->kind.begin(), t->kind.end(), kind);
+  if (split) std::copy(t->split.begin(), t->split.end(), split);
+  if (set_ptr) std::copy(t->set_ptr.begin(), t->set_ptr.end(), set_ptr);
+  if (set_val) std::copy(t->set_val.begin(), t->set_val.end(), set_val);
+  if (leaf_no) std::copy(t->leaf_no.begin(), t->leaf_no.end(), leaf_no);
+  return DBL_OK;
+}
+extern "C" int32_t dbl_kdtree_partition_id(const dbl_kdtree *t, const int32_t *yrow) {
+  if (!t) return 0;
+  return t->leaf_no[t->leaf_node(yrow)];  // MutableBST.getLeafNumber, MutableBST.scala:51-54
+}
+
+// ---------------------------------------------------------------------------------------------------
+// updateDistProbs, GU:305-320.  Beta(a,b) = X/(X+Y); X, Y ~ Gamma via Marsaglia & Tsang (2000); normals by
+// Box-Muller; uniforms from Philox stream (phase THETA, id = attr*F + file, sub = call counter).  This runs
+// on the host exactly like the reference runs it on the Spark driver: A*F scalar draws per sweep.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+struct ThetaStream {
+  uint64_t seed;
+  uint32_t iter, id, calls;
+  U2 next() { return uniform2(seed, PH_THETA, iter, id, calls++); }
+  double normal() {
+    const U2 u = next();
+    const double rad = std::sqrt(-2.0 * std::log(u.u0));
+    const double ang = 6.283185307179586476925286766559 * u.u1;
+    return rad * std::cos(ang);
+  }
+  double unif() { return next().u0; }
+  double gamma(double shape) {
+    if (shape < 1.0) {
+      const double g = gamma(shape + 1.0);
+      const double u = unif();
+      return g * std::pow(u, 1.0 / shape);
+    }
+    const double d = shape - 1.0 / 3.0;
+    const double c = 1.0 / std::sqrt(9.0 * d);
+    for (;;) {
+      const double xn = normal();
+      double v = 1.0 + c * xn;
+      if (v <= 0.0) continue;
+      v = v * v * v;
+      const double u = unif();
+      const double lhs = std::log(u);
+      double t1 = 0.5 * xn;
+      t1 = t1 * xn;
+      double rhs = t1 + d;
+      rhs = rhs - d * v;
+      rhs = rhs + d * std::log(v);
+      if (lhs < rhs) return d * v;
+    }
+  }
+};
+}  // namespace
+
+void host_draw_theta(int A, int F, const double *alpha, const double *beta, uint64_t seed, const int64_t *agg_dist,
+                     const int64_t *file_sizes, uint32_t iter, double *theta_out) {
+  for (int a = 0; a < A; ++a)
+    for (int f = 0; f < F; ++f) {
+      const double nd = (double)agg_dist[a * F + f];
+      const double s1 = nd + alpha[a];                         // GU:312
+      const double s2 = (double)file_sizes[f] - nd + beta[a];  // GU:313
+      ThetaStream ts{seed, iter, (uint32_t)(a * F + f), 0};
+      const double gx = ts.gamma(s1);
+      const double gy = ts.gamma(s2);
+      theta_out[a * F + f] = gx / (gx + gy);
+    }
+}

@@ -1,0 +1,342 @@
+"""Host-side mirror of the reference's objects around the Gibbs sweep, backed by the C ABI.
+
+  AttributeIndex      <- AttributeIndex.scala:39-245
+  KDTreePartitioner   <- partitioning/KDTreePartitioner.scala:28-69
+  GibbsEngine         <- State.scala:56-99 (nextState), GibbsUpdates.scala (all update* functions)
+
+Errors follow the reference's conventions: argument problems raise ValueError (Scala `require` ->
+IllegalArgumentException), out-of-range value ids raise IndexError (AttributeIndex.scala:137).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import PCG_I, PCG_II, GIBBS, GIBBS_SEQ, SAMPLERS  # noqa: F401
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+class DblinkError(RuntimeError):
+    pass
+
+
+def _check(rc, what, ctx=None):
+    if rc == _lib.OK:
+        return
+    msg = ""
+    if ctx:
+        msg = _lib.load().dbl_last_error(ctx).decode()
+    if rc == _lib.ERR_INVALID:
+        raise ValueError(f"{what}: invalid argument {msg}")
+    if rc == _lib.ERR_ZERO_MASS:
+        raise ValueError(f"{what}: zero probability mass {msg}")  # IndexNonUniformDiscreteDist.scala:78-79
+    if rc == _lib.ERR_CUDA:
+        raise DblinkError(f"{what}: CUDA failure (dblink_b200 needs a CUDA device; there is no CPU fallback) {msg}")
+    raise DblinkError(f"{what}: error {rc} {msg}")
+
+
+class AttributeIndex:
+    """Index of one attribute domain (AttributeIndex.scala:39-104)."""
+
+    def __init__(self, handle, is_constant):
+        self._h = handle
+        self.is_constant = bool(is_constant)
+        L = _lib.load()
+        self.num_values = L.dbl_index_num_values(handle)
+        self.nnz = L.dbl_index_nnz(handle)
+
+    @classmethod
+    def build(cls, values_weights, similarity="constant", threshold=7.0, max_similarity=10.0,
+              expected_max_cluster_size=10):
+        """AttributeIndex.apply (AttributeIndex.scala:107-127).  similarity: 'constant' | 'levenshtein'."""
+        if not values_weights:
+            raise ValueError("index cannot be empty")  # AttributeIndex.scala:111
+        L = _lib.load()
+        vals = list(values_weights.keys())
+        arr = (C.c_char_p * len(vals))(*[v.encode() for v in vals])
+        w = _f64([values_weights[v] for v in vals])
+        h = C.c_void_p()
+        sim = 0 if similarity == "constant" else 1
+        _check(L.dbl_index_build(C.byref(h), arr, _p(w, _lib.f64p), len(vals), sim, threshold, max_similarity,
+                                 expected_max_cluster_size), "AttributeIndex.build")
+        return cls(h, sim == 0)
+
+    @classmethod
+    def from_tables(cls, probs, rowptr=None, col=None, expsim=None, constant=True, expected_max_cluster_size=10):
+        L = _lib.load()
+        probs = _f64(probs)
+        h = C.c_void_p()
+        if constant:
+            rc = L.dbl_index_from_tables(C.byref(h), len(probs), 0, _p(probs, _lib.f64p), None, None, None,
+                                         expected_max_cluster_size)
+        else:
+            rowptr, col, expsim = _i32(rowptr), _i32(col), _f64(expsim)
+            rc = L.dbl_index_from_tables(C.byref(h), len(probs), 1, _p(probs, _lib.f64p), _p(rowptr, _lib.i32p),
+                                         _p(col, _lib.i32p), _p(expsim, _lib.f64p), expected_max_cluster_size)
+        _check(rc, "AttributeIndex.from_tables")
+        return cls(h, constant)
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.load().dbl_index_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def tables(self):
+        V, nnz = self.num_values, self.nnz
+        phi, norm = np.zeros(V), np.zeros(V)
+        rowptr = np.zeros(V + 1, np.int32)
+        col = np.zeros(max(nnz, 1), np.int32)
+        es = np.zeros(max(nnz, 1))
+        _check(_lib.load().dbl_index_tables(self._h, _p(phi, _lib.f64p), _p(norm, _lib.f64p), _p(rowptr, _lib.i32p),
+                                            _p(col, _lib.i32p), _p(es, _lib.f64p)), "AttributeIndex.tables")
+        return {"phi": phi, "norm": norm, "rowptr": rowptr, "col": col[:nnz], "expsim": es[:nnz]}
+
+    def _require(self, v):
+        if not 0 <= v < self.num_values:
+            raise IndexError("valueId is not in the index")  # AttributeIndex.scala:137
+
+    def value_idx_of(self, value):
+        return _lib.load().dbl_index_value_id(self._h, value.encode())
+
+    def value_of(self, v):
+        self._require(v)
+        r = _lib.load().dbl_index_value(self._h, v)
+        return r.decode() if r is not None else None
+
+    def probability_of(self, v):
+        self._require(v)
+        return float(self.tables()["phi"][v])
+
+    def sim_normalization_of(self, v):
+        self._require(v)
+        return float(self.tables()["norm"][v])
+
+    def sim_values_of(self, v):
+        self._require(v)
+        t = self.tables()
+        lo, hi = t["rowptr"][v], t["rowptr"][v + 1]
+        return {int(c): float(e) for c, e in zip(t["col"][lo:hi], t["expsim"][lo:hi])}
+
+    def exp_sim_of(self, v1, v2):
+        self._require(v1)
+        self._require(v2)
+        return _lib.load().dbl_index_exp_sim(self._h, v1, v2)
+
+
+def similarity(a, b, name="LevenshteinSimilarityFn", threshold=7.0, max_similarity=10.0):
+    """SimilarityFn.getSimilarity (SimilarityFn.scala:50-98)."""
+    if name == "ConstantSimilarityFn":
+        return 0.0
+    if not (max_similarity > 0.0):
+        raise ValueError("`maxSimilarity` must be positive")
+    if not (0.0 <= threshold < max_similarity):
+        raise ValueError("`threshold` must be in the interval [0, maxSimilarity)")
+    return _lib.load().dbl_similarity(1, a.encode(), b.encode(), threshold, max_similarity)
+
+
+class KDTreePartitioner:
+    """partitioning/KDTreePartitioner.scala:28-69."""
+
+    def __init__(self, num_levels=0, attribute_ids=()):
+        if num_levels < 0:
+            raise ValueError("`numLevels` must be non-negative.")
+        if num_levels > 0 and len(attribute_ids) == 0:
+            raise ValueError("`attributeIds` must be non-empty if `numLevels` > 0")
+        self.num_levels = num_levels
+        self.attribute_ids = list(attribute_ids)
+        self._h = None
+
+    def fit(self, entity_values):
+        y = _i32(entity_values)
+        ids = _i32(self.attribute_ids if self.attribute_ids else [0])
+        h = C.c_void_p()
+        _check(_lib.load().dbl_kdtree_fit(C.byref(h), _p(y, _lib.i32p), y.shape[0], y.shape[1], self.num_levels,
+                                          _p(ids, _lib.i32p), len(self.attribute_ids)), "KDTreePartitioner.fit")
+        self._free()
+        self._h = h
+        return self
+
+    @classmethod
+    def from_arrays(cls, attr, kind, split, set_ptr, set_val, leaf_no):
+        self = cls(0, ())
+        a, k, s, sp, ln = _i32(attr), _i32(kind), _i32(split), _i32(set_ptr), _i32(leaf_no)
+        sv = _i32(set_val if len(set_val) else [0])
+        h = C.c_void_p()
+        _check(_lib.load().dbl_kdtree_from_arrays(C.byref(h), len(a), _p(a, _lib.i32p), _p(k, _lib.i32p),
+                                                  _p(s, _lib.i32p), _p(sp, _lib.i32p), _p(sv, _lib.i32p),
+                                                  _p(ln, _lib.i32p)), "KDTreePartitioner.from_arrays")
+        self._h = h
+        return self
+
+    def _free(self):
+        if self._h:
+            _lib.load().dbl_kdtree_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self._free()
+        except Exception:
+            pass
+
+    @property
+    def num_partitions(self):
+        return _lib.load().dbl_kdtree_num_leaves(self._h) if self._h else 1
+
+    def get_partition_id(self, values):
+        v = _i32(values)
+        return _lib.load().dbl_kdtree_partition_id(self._h, _p(v, _lib.i32p)) if self._h else 0
+
+    def export(self):
+        L = _lib.load()
+        n, sl = L.dbl_kdtree_num_nodes(self._h), L.dbl_kdtree_set_len(self._h)
+        out = {k: np.zeros(n, np.int32) for k in ("attr", "kind", "split", "leaf_no")}
+        out["set_ptr"] = np.zeros(n + 1, np.int32)
+        out["set_val"] = np.zeros(max(sl, 1), np.int32)
+        _check(L.dbl_kdtree_export(self._h, _p(out["attr"], _lib.i32p), _p(out["kind"], _lib.i32p),
+                                   _p(out["split"], _lib.i32p), _p(out["set_ptr"], _lib.i32p),
+                                   _p(out["set_val"], _lib.i32p), _p(out["leaf_no"], _lib.i32p)), "KDTree.export")
+        out["set_val"] = out["set_val"][:sl]
+        return out
+
+
+class GibbsEngine:
+    """The Markov chain state on one GPU and its transition operator (State.scala:56-99)."""
+
+    def __init__(self, indexes, alpha, beta, partitioner=None, seed=0, num_files=1, rank=0, world_size=1):
+        if len(indexes) == 0 or len(indexes) > _lib.MAX_ATTRS:
+            raise ValueError("between 1 and 32 matching attributes are supported")
+        self.indexes = list(indexes)
+        self.A = len(self.indexes)
+        self.F = int(num_files)
+        self.alpha, self.beta = _f64(alpha), _f64(beta)
+        if np.any(self.alpha <= 0) or np.any(self.beta <= 0):
+            raise ValueError("shape parameters must be positive")  # package.scala:165
+        self.partitioner = partitioner
+        self.seed = int(seed)
+        L = _lib.load()
+        arr = (C.c_void_p * self.A)(*[ix._h for ix in self.indexes])
+        d = _lib.ModelDesc()
+        d.num_attrs, d.num_files = self.A, self.F
+        d.indexes = C.cast(arr, C.POINTER(C.c_void_p))
+        d.alpha, d.beta = _p(self.alpha, _lib.f64p), _p(self.beta, _lib.f64p)
+        d.tree = partitioner._h if (partitioner is not None and partitioner._h) else None
+        d.seed = self.seed
+        d.rank, d.world_size = rank, world_size
+        h = C.c_void_p()
+        rc = L.dbl_ctx_create(C.byref(h), C.byref(d))
+        self._h = h if h else None
+        _check(rc, "GibbsEngine", self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().dbl_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- state ------------------------------------------------------------------------------------
+    def init_state(self, x, file_ids=None, population_size=0):
+        """State.deterministic (State.scala:205-334)."""
+        x = _i32(x)
+        if x.ndim != 2 or x.shape[1] != self.A:
+            raise ValueError("attribute specifications do not match the records")  # RecordsCache.scala:72
+        f = _i32(file_ids if file_ids is not None else np.zeros(x.shape[0], np.int32))
+        _check(_lib.load().dbl_state_init(self._h, x.shape[0], _p(x, _lib.i32p), _p(f, _lib.i32p),
+                                          int(population_size)), "init_state", self._h)
+
+    def upload_state(self, x, file_ids, z, link, y, theta, iteration=0):
+        x, f, link, y = _i32(x), _i32(file_ids), _i32(link), _i32(y)
+        z = np.ascontiguousarray(z, dtype=np.uint8)
+        theta = _f64(theta)
+        if x.shape[1] != self.A or y.shape[1] != self.A or theta.size != self.A * self.F:
+            raise ValueError("state arrays do not match the model")
+        _check(_lib.load().dbl_state_upload(self._h, x.shape[0], y.shape[0], _p(x, _lib.i32p), _p(f, _lib.i32p),
+                                            _p(z, _lib.u8p), _p(link, _lib.i32p), _p(y, _lib.i32p),
+                                            _p(theta, _lib.f64p), int(iteration)), "upload_state", self._h)
+
+    def set_partitioner(self, partitioner):
+        """Install the partition function fitted on the initial entity values (State.scala:309-316)."""
+        self.partitioner = partitioner
+        h = partitioner._h if (partitioner is not None and partitioner._h) else None
+        _check(_lib.load().dbl_set_partitioner(self._h, h), "set_partitioner", self._h)
+
+    @property
+    def num_partitions(self):
+        return _lib.load().dbl_num_partitions(self._h)
+
+    @property
+    def num_records(self):
+        return _lib.load().dbl_num_records(self._h)
+
+    @property
+    def num_entities(self):
+        return _lib.load().dbl_num_entities(self._h)
+
+    @property
+    def iteration(self):
+        return _lib.load().dbl_iteration(self._h)
+
+    def download_state(self):
+        R, E, A = self.num_records, self.num_entities, self.A
+        z = np.zeros((R, A), np.uint8)
+        link = np.zeros(R, np.int32)
+        y = np.zeros((E, A), np.int32)
+        theta = np.zeros((A, self.F))
+        blk = np.zeros(E, np.int32)
+        _check(_lib.load().dbl_state_download(self._h, _p(z, _lib.u8p), _p(link, _lib.i32p), _p(y, _lib.i32p),
+                                              _p(theta, _lib.f64p), _p(blk, _lib.i32p)), "download_state", self._h)
+        return {"z": z, "link": link, "y": y, "theta": theta, "block": blk}
+
+    def links(self):
+        """(link[R], block_of_entity[E]) -- the input of State.getLinkageStructure (State.scala:102-112)."""
+        link = np.zeros(self.num_records, np.int32)
+        blk = np.zeros(self.num_entities, np.int32)
+        _check(_lib.load().dbl_links_download(self._h, _p(link, _lib.i32p), _p(blk, _lib.i32p)), "links", self._h)
+        return link, blk
+
+    # ---- transition -------------------------------------------------------------------------------
+    def sweep(self, sampler="PCG-I", n=1):
+        """n applications of State.nextState (State.scala:78-99)."""
+        s = SAMPLERS[sampler] if isinstance(sampler, str) else int(sampler)
+        _check(_lib.load().dbl_sweep(self._h, s, int(n)), "sweep", self._h)
+
+    def summary(self):
+        """SummaryVars (package.scala:116-119) of the current state + theta."""
+        head = _lib.SummaryHead()
+        agg = np.zeros((self.A, self.F), np.int64)
+        rec = np.zeros(self.A + 1, np.int64)
+        theta = np.zeros((self.A, self.F))
+        _check(_lib.load().dbl_summary(self._h, C.byref(head), _p(agg, _lib.i64p), _p(rec, _lib.i64p),
+                                       _p(theta, _lib.f64p)), "summary", self._h)
+        return {"iteration": head.iteration, "num_isolates": head.num_isolates, "log_likelihood": head.log_likelihood,
+                "pairs_scored": head.pairs_scored, "agg_dist": agg, "rec_dist": rec, "theta": theta}
+
+    def kernel_launches(self):
+        return _lib.load().dbl_kernel_launches(self._h)
+
+    def last_sweep_ms(self):
+        return _lib.load().dbl_last_sweep_ms(self._h)
+
+    def link_kernel_ms(self):
+        n = C.c_int64(0)
+        ms = _lib.load().dbl_link_kernel_ms(self._h, C.byref(n))
+        return ms, n.value

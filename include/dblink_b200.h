@@ -1,0 +1,156 @@
+/*
+ * dblink_b200.h -- C ABI of the B200-native Gibbs-sweep engine for cleanzr/dblink's record-linkage model.
+ *
+ * The reference (Scala/Spark, no FFI of its own) has exactly one seam around the hot path; every entry
+ * point below names the reference interface it replaces.  Paths are relative to
+ * src/main/scala/com/github/cleanzr/dblink/ of cleanzr/dblink @ dc3dd0d; GU = GibbsUpdates.scala.
+ *
+ * Conventions (JNI/JCuda/ctypes friendly): opaque handles, plain pointers + sizes, int status
+ * (0 = ok, negative = error; dbl_last_error() gives the text), no callbacks, no exceptions across the
+ * boundary.  The caller owns every host buffer; the library owns every device buffer.  One context per
+ * process/GPU; calls on one context are serialised by the caller.  All compute runs on the CUDA device
+ * that is current when dbl_ctx_create() is called -- there is no CPU fallback.
+ */
+#ifndef DBLINK_B200_H
+#define DBLINK_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DBL_OK 0
+#define DBL_ERR_INVALID (-1)   /* bad argument (reference: require(...) -> IllegalArgumentException)            */
+#define DBL_ERR_CUDA (-2)      /* CUDA runtime failure / no usable device                                       */
+#define DBL_ERR_ZERO_MASS (-3) /* a categorical had zero/non-finite mass (random/IndexNonUniformDiscreteDist.scala:71-79) */
+#define DBL_ERR_STATE (-4)     /* call sequence error (e.g. sweep before state upload)                          */
+
+/* sampler = ProjectStep.scala:35,53-58 */
+#define DBL_PCG_I 0            /* collapsedEntityIds=false, collapsedEntityValues=true  (default)               */
+#define DBL_PCG_II 1           /* collapsedEntityIds=true,  collapsedEntityValues=true                          */
+#define DBL_GIBBS 2            /* both false                                                                    */
+#define DBL_GIBBS_SEQ 3        /* "Gibbs-Sequential": same conditionals as DBL_GIBBS (the reference's flag only
+                                  disables its inverted index, GU:194-196)                                      */
+
+#define DBL_MAX_ATTRS 32
+
+typedef struct dbl_index dbl_index;   /* AttributeIndex  (AttributeIndex.scala:39-104)                          */
+typedef struct dbl_kdtree dbl_kdtree; /* KDTreePartitioner / MutableBST (partitioning/KDTreePartitioner.scala)  */
+typedef struct dbl_ctx dbl_ctx;       /* State + broadcast RecordsCache/PartitionFunction (State.scala:56-68)   */
+
+/* ---------------------------------------------------------------------------------------------------
+ * Model tables.  Replaces AttributeIndex.apply (AttributeIndex.scala:107-127): value ids in sorted-string
+ * order, empirical pmf, sparse exp(similarity) rows (computeSimValueIndex :219-231), normalisations
+ * (computeSimNormalizations :234-245), cached base pmfs k=0..kmax (getSimNormDist :197-216,
+ * RecordsCache.scala:112-113).  similarity: 0 = ConstantSimilarityFn, 1 = LevenshteinSimilarityFn
+ * (SimilarityFn.scala:50-107).  `values` need not be sorted; `weights` are the value counts.
+ * ------------------------------------------------------------------------------------------------- */
+int dbl_index_build(dbl_index **out, const char *const *values, const double *weights, int32_t num_values,
+                    int similarity, double threshold, double max_similarity, int32_t kmax);
+/* Same object from pre-computed tables (phi = weight/total as in AttributeIndex.scala:114-115). */
+int dbl_index_from_tables(dbl_index **out, int32_t num_values, int similarity, const double *probs,
+                          const int32_t *rowptr, const int32_t *col, const double *expsim, int32_t kmax);
+void dbl_index_free(dbl_index *);
+int32_t dbl_index_num_values(const dbl_index *);                 /* AttributeIndex.numValues                 */
+int32_t dbl_index_nnz(const dbl_index *);
+int32_t dbl_index_value_id(const dbl_index *, const char *value); /* valueIdxOf; -1 when absent              */
+const char *dbl_index_value(const dbl_index *, int32_t value_id);
+/* copies of the tables (arrays sized num_values, num_values+1, nnz, nnz); any pointer may be NULL */
+int dbl_index_tables(const dbl_index *, double *phi /*probabilityOf*/, double *norm /*simNormalizationOf*/,
+                     int32_t *rowptr, int32_t *col, double *expsim /*simValuesOf*/);
+double dbl_index_exp_sim(const dbl_index *, int32_t v1, int32_t v2); /* expSimOf; NaN when out of range        */
+/* SimilarityFn.getSimilarity (SimilarityFn.scala:65-70, 84-96) */
+double dbl_similarity(int similarity, const char *a, const char *b, double threshold, double max_similarity);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Partition function.  Replaces KDTreePartitioner.fit / getPartitionId
+ * (partitioning/KDTreePartitioner.scala:37-62), MutableBST (MutableBST.scala:51-111) and the
+ * DomainSplitters (DomainSplitter.scala:43-110).  y = E x A entity value ids, row-major.
+ * ------------------------------------------------------------------------------------------------- */
+int dbl_kdtree_fit(dbl_kdtree **out, const int32_t *y, int64_t num_entities, int32_t num_attrs,
+                   int32_t num_levels, const int32_t *attr_ids, int32_t num_attr_ids);
+int dbl_kdtree_from_arrays(dbl_kdtree **out, int32_t num_nodes, const int32_t *attr, const int32_t *kind,
+                           const int32_t *split, const int32_t *set_ptr, const int32_t *set_val,
+                           const int32_t *leaf_no);
+void dbl_kdtree_free(dbl_kdtree *);
+int32_t dbl_kdtree_num_nodes(const dbl_kdtree *);
+int32_t dbl_kdtree_num_leaves(const dbl_kdtree *); /* PartitionFunction.numPartitions */
+int32_t dbl_kdtree_set_len(const dbl_kdtree *);
+int dbl_kdtree_export(const dbl_kdtree *, int32_t *attr, int32_t *kind, int32_t *split, int32_t *set_ptr,
+                      int32_t *set_val, int32_t *leaf_no);
+int32_t dbl_kdtree_partition_id(const dbl_kdtree *, const int32_t *entity_values); /* getPartitionId */
+
+/* ---------------------------------------------------------------------------------------------------
+ * Context = model (RecordsCache + PartitionFunction + Parameters broadcast once, State.scala:216-217,312)
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t num_attrs;                 /* A <= DBL_MAX_ATTRS                                                */
+  int32_t num_files;                 /* F (RecordsCache.fileSizes keys, sorted)                           */
+  const dbl_index *const *indexes;   /* A attribute indexes                                               */
+  const double *alpha;               /* A: distortionPrior alpha (BetaShapeParameters, package.scala:164) */
+  const double *beta;                /* A                                                                 */
+  const dbl_kdtree *tree;            /* NULL = a single block                                             */
+  uint64_t seed;                     /* dblink.randomSeed                                                 */
+  int32_t rank, world_size;          /* block shard owned by this context: blocks b with owner[b]==rank   */
+} dbl_model_desc;
+
+int dbl_ctx_create(dbl_ctx **out, const dbl_model_desc *desc);
+void dbl_ctx_destroy(dbl_ctx *);
+const char *dbl_last_error(const dbl_ctx *); /* never NULL; "" when no error */
+
+/* Install / replace the partition function (PartitionFunction.fit happens on the *initial entity values*,
+ * State.scala:309-312, so the usual order is: create the context with tree = NULL, dbl_state_init,
+ * dbl_state_download(y), dbl_kdtree_fit, dbl_set_partitioner).  The tree is copied to the device; the
+ * caller keeps ownership.  NULL = a single block.  If a state is present it is re-partitioned. */
+int dbl_set_partitioner(dbl_ctx *, const dbl_kdtree *tree);
+int32_t dbl_num_partitions(const dbl_ctx *);
+
+/* Deterministic initial state, State.deterministic (State.scala:205-334): one entity per record (or
+ * population_size entities), values copied from the records, missing values drawn from phi, z = (x>=0 &
+ * x!=y), theta = prior mean (DistortionProbs.scala:33-43).  x = R x A value ids (-1 missing,
+ * RecordsCache.scala:127-130), file = R file ids in [0,F).  population_size <= 0 means R. */
+int dbl_state_init(dbl_ctx *, int64_t num_records, const int32_t *x, const int32_t *file,
+                   int64_t population_size);
+/* Arbitrary state (resume; State.read, State.scala:160-193).  z = R x A bytes, link = R global entity ids,
+ * y = E x A value ids, theta = A x F. */
+int dbl_state_upload(dbl_ctx *, int64_t num_records, int64_t num_entities, const int32_t *x, const int32_t *file,
+                     const uint8_t *z, const int32_t *link, const int32_t *y, const double *theta,
+                     int64_t iteration);
+/* Full state back to the host (State.save, State.scala:122-150); any pointer may be NULL. */
+int dbl_state_download(dbl_ctx *, uint8_t *z, int32_t *link, int32_t *y, double *theta, int32_t *block_of_entity);
+int64_t dbl_num_records(const dbl_ctx *);
+int64_t dbl_num_entities(const dbl_ctx *);
+int64_t dbl_iteration(const dbl_ctx *);
+
+/* n_sweeps applications of the Markov transition operator State.nextState (State.scala:78-99):
+ * updateDistProbs (GU:305-320) -> updatePartitions/updatePartition (GU:124-211: link draw per record
+ * GU:363-466, entity values GU:731-755, distortions GU:324-359, new partition ids GU:206) ->
+ * updateSummaryVariables (GU:219-301).  Everything but the A x F Beta draws runs on the device. */
+int dbl_sweep(dbl_ctx *, int sampler, int32_t n_sweeps);
+
+/* Linkage structure for linkage-chain.parquet (State.getLinkageStructure, State.scala:102-112): record ->
+ * entity links and each entity's current partition id. */
+int dbl_links_download(dbl_ctx *, int32_t *link_out /*R*/, int32_t *block_of_entity_out /*E*/);
+
+/* SummaryVars (package.scala:116-119) + what DiagnosticsWriter prints (DiagnosticsWriter.scala:39-72). */
+typedef struct {
+  int64_t iteration;
+  int64_t num_isolates;
+  double log_likelihood;
+  int64_t pairs_scored; /* (record, candidate) pairs evaluated by link kernels since ctx creation */
+} dbl_summary_head;
+int dbl_summary(dbl_ctx *, dbl_summary_head *head, int64_t *agg_dist /*A*F*/, int64_t *rec_dist /*A+1*/,
+                double *theta /*A*F*/);
+
+/* count of kernels launched by this context since creation (bench.py's gpu_launches) */
+int64_t dbl_kernel_launches(const dbl_ctx *);
+/* CUDA-event time (ms) of the last dbl_sweep call, first operation to last operation on the context's stream */
+double dbl_last_sweep_ms(const dbl_ctx *);
+/* CUDA-event time (ms) spent in the link-scoring kernel since the last call; resets the accumulator */
+double dbl_link_kernel_ms(dbl_ctx *, int64_t *launches);
+const char *dbl_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,160 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar: bit-exact links / entity values / distortion flags / block ids / theta / integer summaries;
+log-likelihood (a floating-point diagnostic reduced in a different order) to 1e-9 relative.
+"""
+import numpy as np
+import pytest
+
+from helpers import oracle_setup, product_setup, random_state, synth_problem
+
+pytestmark = pytest.mark.gpu
+
+SAMPLERS = ["PCG-I", "PCG-II", "Gibbs", "Gibbs-Sequential"]
+
+
+def assert_same_state(eng, st, check_ll=True):
+    d = eng.download_state()
+    np.testing.assert_array_equal(d["theta"], st.theta)
+    np.testing.assert_array_equal(d["link"], st.link)
+    np.testing.assert_array_equal(d["y"], st.y)
+    np.testing.assert_array_equal(d["z"], st.z)
+    np.testing.assert_array_equal(d["block"], st.block)
+    ps, os_ = eng.summary(), st.summary()
+    assert ps["iteration"] == os_["iteration"]
+    assert ps["num_isolates"] == os_["num_isolates"]
+    np.testing.assert_array_equal(ps["agg_dist"], os_["agg_dist"])
+    np.testing.assert_array_equal(ps["rec_dist"], os_["rec_dist"])
+    if check_ll:
+        assert ps["log_likelihood"] == pytest.approx(os_["log_likelihood"], rel=1e-9)
+
+
+@pytest.mark.parametrize("levels,attr_ids", [(0, ()), (2, (2, 3))])
+def test_initial_state(oracle, levels, attr_ids):
+    g = synth_problem(seed=3, R=700)
+    eng, rc, x, file = product_setup(g, 1234, levels, attr_ids)
+    m, st, tree, ox, ofile = oracle_setup(oracle, g, 1234, levels, attr_ids)
+    np.testing.assert_array_equal(x, ox)
+    assert eng.num_partitions == tree.n_leaves
+    assert_same_state(eng, st)
+
+
+@pytest.mark.parametrize("sampler", SAMPLERS)
+@pytest.mark.parametrize("levels,attr_ids", [(0, ()), (2, (2, 3))])
+def test_chain_from_init(oracle, sampler, levels, attr_ids):
+    g = synth_problem(seed=5, R=900, n_files=2)
+    eng, rc, x, file = product_setup(g, 99, levels, attr_ids)
+    m, st, tree, ox, ofile = oracle_setup(oracle, g, 99, levels, attr_ids)
+    for it in range(6):
+        eng.sweep(sampler, 1)
+        assert st.sweep(oracle.SAMPLERS[sampler]) == 0
+        assert_same_state(eng, st)
+    # several sweeps in one call == the same sweeps one by one
+    eng.sweep(sampler, 3)
+    st.sweep(oracle.SAMPLERS[sampler], 3)
+    assert_same_state(eng, st)
+
+
+@pytest.mark.parametrize("sampler", SAMPLERS)
+def test_random_states(oracle, sampler):
+    """single sweeps from random valid states: exercises clusters of many records, isolated entities,
+    distorted/non-distorted mixtures, several files and blocks"""
+    g = synth_problem(seed=11, R=500, n_files=3, missing=0.08, distortion=0.2)
+    eng, rc, x, file = product_setup(g, 7, 3, (3, 2, 0))
+    m, st0, tree, ox, ofile = oracle_setup(oracle, g, 7, 3, (3, 2, 0))
+    Vs = [ix.num_values for ix in rc.indexes]
+    rng = np.random.default_rng(2024)
+    for trial, E in enumerate([500, 60, 1200]):
+        y, link, z = random_state(rng, x, E, Vs)
+        theta = rng.uniform(0.005, 0.3, (len(Vs), 3))
+        eng.upload_state(x, file, z, link, y, theta, iteration=10 * trial)
+        st = oracle.State.from_arrays(m, x, file, z, link, y, theta, 10 * trial)
+        assert_same_state(eng, st)
+        eng.sweep(sampler, 2)
+        assert st.sweep(oracle.SAMPLERS[sampler], 2) == 0
+        assert_same_state(eng, st)
+
+
+@pytest.mark.parametrize("pop", [150, 450, 1000])
+def test_population_sizes(oracle, pop):
+    """populationSize below / above the number of records (State.scala:221-250, 296-301)"""
+    g = synth_problem(seed=21, R=450)
+    eng, rc, x, file = product_setup(g, 5, 1, (2,), pop=pop)
+    m, st, tree, ox, ofile = oracle_setup(oracle, g, 5, 1, (2,), pop=pop)
+    assert eng.num_entities == pop
+    assert_same_state(eng, st)
+    for sampler in ("PCG-I", "PCG-II"):
+        eng.sweep(sampler, 2)
+        st.sweep(oracle.SAMPLERS[sampler], 2)
+        assert_same_state(eng, st)
+
+
+def test_large_cluster_beyond_cached_powers(oracle):
+    """cluster sizes above expectedMaxClusterSize take the uncached base-distribution path
+    (AttributeIndex.scala:197-205)"""
+    g = synth_problem(seed=31, R=300, dup=0.0)
+    eng, rc, x, file = product_setup(g, 17, 0, (), kmax=2)
+    m, st0, tree, ox, ofile = oracle_setup(oracle, g, 17, 0, (), kmax=2)
+    Vs = [ix.num_values for ix in rc.indexes]
+    rng = np.random.default_rng(5)
+    y, link, z = random_state(rng, x, 12, Vs)  # 300 records on 12 entities
+    theta = np.full((len(Vs), 1), 0.05)
+    for sampler in SAMPLERS:
+        eng.upload_state(x, file, z, link, y, theta, 0)
+        st = oracle.State.from_arrays(m, x, file, z, link, y, theta, 0)
+        eng.sweep(sampler, 1)
+        st.sweep(oracle.SAMPLERS[sampler], 1)
+        assert_same_state(eng, st)
+
+
+def test_tiny_and_degenerate_inputs(oracle):
+    from dblink_b200 import synth
+
+    attrs = [synth.SynthAttr("s0", "levenshtein", 40, 1.0)]
+    g = synth.generate(3, 1, attrs, dup=0.0, distortion=0.0, missing=0.0)
+    eng, rc, x, file = product_setup(g, 1)
+    m, st, tree, ox, ofile = oracle_setup(oracle, g, 1)
+    for sampler in SAMPLERS:
+        eng.sweep(sampler, 2)
+        st.sweep(oracle.SAMPLERS[sampler], 2)
+        assert_same_state(eng, st)
+    # records with every attribute missing
+    g = synth_problem(seed=8, R=64, missing=0.0)
+    for r in range(0, 64, 5):
+        g["values"][r] = [None] * len(g["values"][r])
+    eng, rc, x, file = product_setup(g, 2, 1, (0,))
+    m, st, tree, ox, ofile = oracle_setup(oracle, g, 2, 1, (0,))
+    for sampler in SAMPLERS:
+        eng.sweep(sampler, 2)
+        st.sweep(oracle.SAMPLERS[sampler], 2)
+        assert_same_state(eng, st)
+
+
+def test_error_conventions():
+    import dblink_b200 as D
+
+    g = synth_problem(seed=2, R=50)
+    eng, rc, x, file = product_setup(g, 1)
+    with pytest.raises(ValueError):
+        eng.sweep(7, 1)
+    bad = x.copy()
+    bad[0, 0] = 10_000
+    with pytest.raises(ValueError):
+        eng.init_state(bad, file)
+    eng2 = D.GibbsEngine(rc.indexes, [1.0] * 4, [1.0] * 4, None, 1, 1)
+    with pytest.raises(D.DblinkError):
+        eng2.sweep("PCG-I", 1)  # no state yet
+
+
+def test_block_size_many_tiles(oracle):
+    """one block spanning several 128-entity tiles and several draw chunks"""
+    from dblink_b200 import synth
+
+    attrs = [synth.SynthAttr("c0", "constant", 6, 0.5), synth.SynthAttr("s0", "levenshtein", 200, 1.0)]
+    g = synth.generate(9, 2600, attrs, dup=0.2, distortion=0.1, missing=0.02)
+    eng, rc, x, file = product_setup(g, 77)
+    m, st, tree, ox, ofile = oracle_setup(oracle, g, 77)
+    for sampler in ("PCG-II", "PCG-I"):
+        eng.sweep(sampler, 2)
+        st.sweep(oracle.SAMPLERS[sampler], 2)
+        assert_same_state(eng, st)
