@@ -255,7 +255,17 @@ extern "C" int dbl_kdtree_fit(dbl_kdtree **out, const int32_t *y, int64_t E, int
     const int attr = attr_ids[level % n_attr_ids];  // cycle, KDTreePartitioner.scala:45-49
     // value histogram per frontier node (getNewSplits, :80-105)
     std::map<int32_t, std::map<int32_t, double>> dom;
-    for (int64_t e = 0; e < E; ++e) dom[t->leaf_node(y + e * A)][y[e * A + attr]] += 1.0;
+    auto leaf_during_fit = [&](const int32_t *yrow) {  // set_ptr/set_val are only assembled after the last level
+      int32_t node = 0;
+      while (node < n && t->attr[node] >= 0) {
+        const int32_t v = yrow[t->attr[node]];
+        const bool right = t->kind[node] ? std::binary_search(sets[node].begin(), sets[node].end(), v)
+                                         : (v > t->split[node]);
+        node = right ? 2 * node + 2 : 2 * node + 1;
+      }
+      return node;
+    };
+    for (int64_t e = 0; e < E; ++e) dom[leaf_during_fit(y + e * A)][y[e * A + attr]] += 1.0;
     for (auto &nd : dom) {  // ascending node id (the reference's Map order is unspecified)
       const int32_t node = nd.first;
       std::vector<std::pair<int32_t, double>> d(nd.second.begin(), nd.second.end());  // ascending value

@@ -381,7 +381,22 @@ orc_kdtree *orc_kdtree_fit(const int32_t *y, int64_t E, int A, int num_levels, c
   int32_t *node_of = (int32_t *)malloc(sizeof(int32_t) * (size_t)(E ? E : 1));
   for (int level = 0; level < num_levels; ++level) {
     int attr = attr_ids[level % n_attr_ids]; /* KDTreePartitioner.scala:45-49: cycle through attributeIds */
-    for (int64_t e = 0; e < E; ++e) node_of[e] = tree_leaf_node(t, y + e * A);
+    for (int64_t e = 0; e < E; ++e) {
+      /* MutableBST.getLeafNodeId on the tree built so far (set_ptr/set_val are assembled after the last level) */
+      int node = 0;
+      while (node < n_nodes && t->attr[node] >= 0) {
+        int32_t v = y[e * A + t->attr[node]];
+        int right;
+        if (t->kind[node]) {
+          right = 0;
+          for (int q = 0; q < set_n[node] && !right; ++q) right = (sets[node][q] == v);
+        } else {
+          right = v > t->split[node];
+        }
+        node = right ? 2 * node + 2 : 2 * node + 1;
+      }
+      node_of[e] = node;
+    }
     int first = (1 << level) - 1, last = (1 << (level + 1)) - 2;
     for (int node = first; node <= last; ++node) {
       if (t->leaf_no[node] < 0) continue;
@@ -710,9 +725,11 @@ void orc_draw_theta(const orc_model *m, const int64_t *agg_dist, const int64_t *
 /* ------------------------------------------------------------------------------------------ */
 /* Categorical draw protocol (replaces DiscreteDist(weights).sample(), GU:394,427,465, which    */
 /* builds an alias table per draw).  Candidates in canonical order, padded to a multiple of 32; */
-/* a "step" is 32 consecutive candidates, its total is a 5-level xor-butterfly sum; step totals */
-/* are accumulated sequentially; at most 32 "chunks" of steps are check-pointed; the chunk, the  */
-/* step and finally the lane (Kogge-Stone inclusive scan) containing u*total are located.       */
+/* a "step" is 32 consecutive candidates (lane l owns candidate step*32+l); steps are grouped    */
+/* into at most 32 "chunks"; inside a chunk every lane sums its own candidates in step order,    */
+/* the chunk total is a 5-level xor-butterfly sum of the 32 lane sums, chunk totals accumulate   */
+/* sequentially and are check-pointed; u*total is located chunk -> lane (Kogge-Stone inclusive   */
+/* scan of the lane sums) -> step (sequential walk of that lane).                                */
 /* ------------------------------------------------------------------------------------------ */
 
 static double butterfly32(const double *w) {
@@ -742,49 +759,54 @@ int orc_draw_index(const double *w, int64_t n, double u, int *status) {
   int64_t nchunks = (nsteps + spc - 1) / spc;
   double Q[32];
   double run = 0.0;
-  double sw[32];
+  double sw[32], ls[32];
+  /* pass 1: per chunk, lane sums (each lane adds its own candidates in step order), chunk total =
+     butterfly of the lane sums, running total over chunks check-pointed in Q */
   for (int64_t c = 0; c < nchunks; ++c) {
     int64_t s0 = c * spc, s1 = s0 + spc < nsteps ? s0 + spc : nsteps;
-    for (int64_t s = s0; s < s1; ++s) { load_step(w, n, s, sw); run = run + butterfly32(sw); }
+    for (int l = 0; l < 32; ++l) ls[l] = 0.0;
+    for (int64_t s = s0; s < s1; ++s) {
+      load_step(w, n, s, sw);
+      for (int l = 0; l < 32; ++l) ls[l] = ls[l] + sw[l];
+    }
+    run = run + butterfly32(ls);
     Q[c] = run;
   }
   double total = run;
   if (!(total > 0.0) || isinf(total)) { if (status) *status = 1; return -1; }
   double t = u * total;
-  int64_t chunk = -1;
+  int64_t chunk = nchunks - 1; /* u*total < total always holds for u < 1, so the scan below always hits */
   for (int64_t c = 0; c < nchunks; ++c) if (Q[c] > t) { chunk = c; break; }
-  if (chunk < 0) { /* u*total rounded up to total: last chunk that added mass */
-    for (int64_t c = nchunks - 1; c >= 0; --c) { double prev = c ? Q[c - 1] : 0.0; if (Q[c] > prev) { chunk = c; break; } }
-    if (chunk < 0) chunk = nchunks - 1;
-  }
   double r = chunk ? Q[chunk - 1] : 0.0;
+  /* pass 2a: lane sums of that chunk again, Kogge-Stone inclusive scan over lanes -> lane */
   int64_t s0 = chunk * spc, s1 = s0 + spc < nsteps ? s0 + spc : nsteps;
-  int64_t step = -1;
-  int64_t last_pos_step = -1;
+  for (int l = 0; l < 32; ++l) ls[l] = 0.0;
   for (int64_t s = s0; s < s1; ++s) {
     load_step(w, n, s, sw);
-    double c = butterfly32(sw);
-    if (c > 0.0) last_pos_step = s;
-    if (r + c > t) { step = s; break; }
-    r = r + c;
+    for (int l = 0; l < 32; ++l) ls[l] = ls[l] + sw[l];
   }
-  if (step < 0) { /* only reachable through the rounding fallback above */
-    step = last_pos_step >= 0 ? last_pos_step : s1 - 1;
-    r = chunk ? Q[chunk - 1] : 0.0;
-    for (int64_t s = s0; s < step; ++s) { load_step(w, n, s, sw); r = r + butterfly32(sw); }
-  }
-  load_step(w, n, step, sw);
-  /* Kogge-Stone inclusive scan over the 32 lanes */
   double P[32], nP[32];
-  memcpy(P, sw, sizeof(P));
+  memcpy(P, ls, sizeof(P));
   for (int d = 1; d < 32; d <<= 1) {
     for (int l = 0; l < 32; ++l) nP[l] = l >= d ? P[l] + P[l - d] : P[l];
     memcpy(P, nP, sizeof(P));
   }
   int lane = -1;
   for (int l = 0; l < 32; ++l) if (r + P[l] > t) { lane = l; break; }
-  if (lane < 0) for (int l = 31; l >= 0; --l) if (sw[l] > 0.0) { lane = l; break; }
+  if (lane < 0) for (int l = 31; l >= 0; --l) if (ls[l] > 0.0) { lane = l; break; } /* scan vs butterfly rounding */
   if (lane < 0) lane = 0;
+  double base = lane ? r + P[lane - 1] : r;
+  /* pass 2b: walk that lane's candidates of the chunk in step order */
+  double cum = 0.0;
+  int64_t step = -1, last_pos = -1;
+  for (int64_t s = s0; s < s1; ++s) {
+    int64_t j = s * 32 + lane;
+    double wj = j < n ? w[j] : 0.0;
+    cum = cum + wj;
+    if (wj > 0.0) last_pos = s;
+    if (base + cum > t) { step = s; break; }
+  }
+  if (step < 0) step = last_pos >= 0 ? last_pos : s0;
   int64_t j = step * 32 + lane;
   if (j >= n) j = n - 1;
   return (int)j;
@@ -877,31 +899,26 @@ static double protocol_weight(const orc_state *s, int sampler, const rec_attr_t 
   const orc_model *m = s->m;
   int A = m->A;
   double w;
+  /* multiplication order of the protocol: three passes over the attributes, each in attribute order */
   if (sampler == ORC_PCG_II) {
     w = nprod;
-    for (int a = 0; a < A; ++a) {
-      const orc_index *ix = m->idx[a];
-      int32_t yv = ye[a];
-      switch (ra[a].kind) {
-        case 1: if (yv == ra[a].x) w = w * ra[a].rmatch; break;
-        case 2:
-          if (yv == ra[a].x) w = w * ra[a].rmatch;
-          else { double e; if (row_find(ix, ra[a].x, yv, &e)) w = w * e; }
-          break;
-        case 3: w = w * ix->invnorm[yv]; break;
-        default: break;
-      }
+    for (int a = 0; a < A; ++a) /* (i) exact matches */
+      if ((ra[a].kind == 1 || ra[a].kind == 2) && ye[a] == ra[a].x) w = w * ra[a].rmatch;
+    for (int a = 0; a < A; ++a) { /* (ii) similar but different values */
+      double e;
+      if (ra[a].kind == 2 && ye[a] != ra[a].x && row_find(m->idx[a], ra[a].x, ye[a], &e)) w = w * e;
     }
+    for (int a = 0; a < A; ++a) /* (iii) missing record attributes */
+      if (ra[a].kind == 3) w = w * m->idx[a]->invnorm[ye[a]];
   } else {
     w = 1.0;
     for (int a = 0; a < A; ++a)
       if (ra[a].kind == 4 && ye[a] != ra[a].x) return 0.0;
-    for (int a = 0; a < A; ++a) {
-      if (ra[a].kind != 2) continue;
-      const orc_index *ix = m->idx[a];
+    for (int a = 0; a < A; ++a) /* (i) normalisations */
+      if (ra[a].kind == 2) w = w * m->idx[a]->norm[ye[a]];
+    for (int a = 0; a < A; ++a) { /* (ii) similarities (diagonal included) */
       double e;
-      w = w * ix->norm[ye[a]];
-      if (row_find(ix, ra[a].x, ye[a], &e)) w = w * e;
+      if (ra[a].kind == 2 && row_find(m->idx[a], ra[a].x, ye[a], &e)) w = w * e;
     }
   }
   return w;
