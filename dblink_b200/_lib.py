@@ -78,6 +78,7 @@ SIGNATURES = {
     "dbl_links_download": (C.c_int, [vp, i32p, i32p]),
     "dbl_summary": (C.c_int, [vp, C.POINTER(SummaryHead), i64p, i64p, f64p]),
     "dbl_kernel_launches": (C.c_int64, [vp]),
+    "dbl_set_link_mode": (C.c_int, [vp, C.c_int]),
     "dbl_last_sweep_ms": (C.c_double, [vp]),
     "dbl_link_kernel_ms": (C.c_double, [vp, i64p]),
     "dbl_version": (C.c_char_p, []),

@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "dbl_internal.h"
+#include "dbl_link.cuh"
 
 #define CUDA_TRY(expr)                                                                          \
   do {                                                                                          \
@@ -36,35 +37,14 @@
 // ---------------------------------------------------------------------------------------------------
 // device-side model
 // ---------------------------------------------------------------------------------------------------
-struct AttrDev {
-  int V, is_const, kmax, pad;
-  const double *phi, *probs, *norm, *invnorm, *pk, *cdf, *logphi, *lognorm, *expsim;
-  const int *rowptr, *col;
-};
 struct TreeDev {
   int n_nodes;
   const int *attr, *kind, *split, *set_ptr, *set_val, *leaf_no;
 };
 
-constexpr int TE = 128;       // entities per tile of the block-sorted entity table
-constexpr int LINK_WARPS = 8; // records per CTA of the link kernel
-
-__host__ __device__ inline size_t tile_words(int A) { return (size_t)A * TE + 2 * TE; }  // int32 words per tile
-
 // ---------------------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool row_find(const AttrDev &at, int v1, int v2, double &e) {
-  int lo = at.rowptr[v1], hi = at.rowptr[v1 + 1] - 1;
-  while (lo <= hi) {
-    const int mid = (lo + hi) >> 1;
-    const int c = at.col[mid];
-    if (c == v2) { e = at.expsim[mid]; return true; }
-    if (c < v2) lo = mid + 1; else hi = mid - 1;
-  }
-  return false;
-}
-
 __device__ __forceinline__ int invcdf(const double *cdf, int V, double u) {
   int lo = 0, hi = V;
   while (lo < hi) {
@@ -94,20 +74,6 @@ __device__ __forceinline__ int tree_leaf(const TreeDev &t, const int *yrow) {
     node = right ? 2 * node + 2 : 2 * node + 1;
   }
   return t.leaf_no[node];
-}
-
-__device__ __forceinline__ double shfl_xor_d(double v, int d) { return __shfl_xor_sync(0xffffffffu, v, d); }
-__device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
-__device__ __forceinline__ double shfl_d(double v, int l) { return __shfl_sync(0xffffffffu, v, l); }
-
-// 5-level xor butterfly: every lane ends with the same sum (the protocol's "step total")
-__device__ __forceinline__ double butterfly_sum(double v) {
-  v = v + shfl_xor_d(v, 16);
-  v = v + shfl_xor_d(v, 8);
-  v = v + shfl_xor_d(v, 4);
-  v = v + shfl_xor_d(v, 2);
-  v = v + shfl_xor_d(v, 1);
-  return v;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -194,221 +160,6 @@ __global__ void k_build_tiles(int64_t E, int A, const int *__restrict__ y, const
   const int slot = j % TE;
   for (int a = 0; a < A; ++a) tile[a * TE + slot] = y[(int64_t)e * A + a];
   reinterpret_cast<double *>(tile + (size_t)A * TE)[slot] = entN[e];
-}
-
-// ---------------------------------------------------------------------------------------------------
-// k_link: one warp per record, dense scoring of every entity of the record's block + categorical draw.
-// v0: tiles are read straight from global/L2 (the block's table is L2 resident).
-// ---------------------------------------------------------------------------------------------------
-struct RecAttr {
-  int kind;  // 0 skip, 1 const compare, 2 non-const sparse row, 3 missing non-const (PCG-II), 4 must match
-  int x;
-  int len;
-  int pad;
-  double rmatch;
-  const int *col;
-  const double *val;
-  const double *tab;  // invnorm (kind 3) / norm (kind 2 of PCG-I)
-};
-
-struct LinkParams {
-  int A, F, P, sampler;
-  uint64_t seed;
-  uint32_t iter;
-  const AttrDev *attrs;
-  const int *x, *file, *link;
-  const unsigned *zmask;
-  const double *theta;
-  const int *ent_ptr, *tile_ptr, *rec_ptr, *cta_ptr, *ent_sorted, *rec_sorted;
-  const int *tiles;
-  int *newlink;
-  int *status;
-  unsigned long long *pairs;
-};
-
-__device__ __forceinline__ double weight_pcg2(const RecAttr *ra, int A, const int *ycol, double N) {
-  double w = N;
-  for (int a = 0; a < A; ++a) {
-    const RecAttr c = ra[a];
-    if (c.kind == 0) continue;
-    const int yv = ycol[a * TE];
-    if (c.kind == 1) {
-      if (yv == c.x) w = w * c.rmatch;
-    } else if (c.kind == 2) {
-      if (yv == c.x) {
-        w = w * c.rmatch;
-      } else {
-        int lo = 0, hi = c.len - 1;
-        while (lo <= hi) {
-          const int mid = (lo + hi) >> 1;
-          const int cv = c.col[mid];
-          if (cv == yv) { w = w * c.val[mid]; break; }
-          if (cv < yv) lo = mid + 1; else hi = mid - 1;
-        }
-      }
-    } else {  // kind 3
-      w = w * c.tab[yv];
-    }
-  }
-  return w;
-}
-
-__device__ __forceinline__ double weight_pcg1(const RecAttr *ra, int A, const int *ycol) {
-  for (int a = 0; a < A; ++a)
-    if (ra[a].kind == 4 && ycol[a * TE] != ra[a].x) return 0.0;
-  double w = 1.0;
-  for (int a = 0; a < A; ++a) {
-    const RecAttr c = ra[a];
-    if (c.kind != 2) continue;
-    const int yv = ycol[a * TE];
-    w = w * c.tab[yv];
-    int lo = 0, hi = c.len - 1;
-    while (lo <= hi) {
-      const int mid = (lo + hi) >> 1;
-      const int cv = c.col[mid];
-      if (cv == yv) { w = w * c.val[mid]; break; }
-      if (cv < yv) lo = mid + 1; else hi = mid - 1;
-    }
-  }
-  return w;
-}
-
-__global__ void __launch_bounds__(LINK_WARPS * 32) k_link(LinkParams p) {
-  __shared__ RecAttr s_ra[LINK_WARPS][DBL_MAX_ATTRS];
-  const int cta = blockIdx.x;
-  if (cta >= p.cta_ptr[p.P]) return;
-  int lo = 0, hi = p.P;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (p.cta_ptr[mid] <= cta) lo = mid; else hi = mid;
-  }
-  const int b = lo;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ridx = p.rec_ptr[b] + (cta - p.cta_ptr[b]) * LINK_WARPS + warp;
-  if (ridx >= p.rec_ptr[b + 1]) return;
-  const int r = p.rec_sorted[ridx];
-  const int A = p.A;
-  const bool pcg2 = (p.sampler == DBL_PCG_II);
-
-  // per-record constants, lane a prepares attribute a
-  RecAttr *ra = s_ra[warp];
-  if (lane < A) {
-    const AttrDev &at = p.attrs[lane];
-    const int xv = p.x[(int64_t)r * A + lane];
-    RecAttr c;
-    c.kind = 0; c.x = xv; c.len = 0; c.pad = 0; c.rmatch = 1.0; c.col = nullptr; c.val = nullptr; c.tab = nullptr;
-    if (pcg2) {
-      if (xv < 0) {
-        if (!at.is_const) { c.kind = 3; c.tab = at.invnorm; }
-      } else {
-        const double th = p.theta[lane * p.F + p.file[r]];
-        double d = th * at.phi[xv];
-        if (at.is_const) {
-          c.kind = 1;
-          c.rmatch = 1.0 + (1.0 - th) / d;
-        } else {
-          d = d * at.norm[xv];
-          double ediag = 1.0;
-          row_find(at, xv, xv, ediag);
-          c.kind = 2;
-          c.rmatch = ediag + (1.0 - th) / d;
-          c.col = at.col + at.rowptr[xv];
-          c.val = at.expsim + at.rowptr[xv];
-          c.len = at.rowptr[xv + 1] - at.rowptr[xv];
-        }
-      }
-    } else if (xv >= 0) {
-      const bool dist = (p.zmask[r] >> lane) & 1u;
-      if (!dist) c.kind = 4;
-      else if (!at.is_const) {
-        c.kind = 2;
-        c.tab = at.norm;
-        c.col = at.col + at.rowptr[xv];
-        c.val = at.expsim + at.rowptr[xv];
-        c.len = at.rowptr[xv + 1] - at.rowptr[xv];
-      }
-    }
-    ra[lane] = c;
-  }
-  __syncwarp();
-
-  const int n = p.ent_ptr[b + 1] - p.ent_ptr[b];
-  const int nsteps = (n + 31) >> 5;
-  int spc = (nsteps + 31) >> 5;
-  if (spc < 1) spc = 1;
-  const int nchunks = (nsteps + spc - 1) / spc;
-  const size_t tw = tile_words(A);
-  const int *tiles = p.tiles + (size_t)p.tile_ptr[b] * tw;
-
-  auto weight_at = [&](int step) -> double {
-    const int j = (step << 5) + lane;
-    if (j >= n) return 0.0;
-    const int *tile = tiles + (size_t)(j / TE) * tw;
-    const int slot = j % TE;
-    if (pcg2) {
-      const double N = reinterpret_cast<const double *>(tile + (size_t)A * TE)[slot];
-      return weight_pcg2(ra, A, tile + slot, N);
-    }
-    return weight_pcg1(ra, A, tile + slot);
-  };
-
-  // pass 1: step totals accumulated sequentially, lane c keeps the running total at the end of chunk c
-  double run = 0.0, Q = 0.0;
-  {
-    int next_mark = spc, chunk = 0;
-    for (int s = 0; s < nsteps; ++s) {
-      const double c = butterfly_sum(weight_at(s));
-      run = run + c;
-      if (s + 1 == next_mark || s + 1 == nsteps) {
-        if (lane == chunk) Q = run;
-        ++chunk;
-        next_mark += spc;
-      }
-    }
-  }
-  const double total = run;
-  if (!(total > 0.0) || isinf(total)) {  // reference: IllegalArgumentException("zero probability mass")
-    if (lane == 0) { atomicOr(p.status, 1); p.newlink[r] = p.link[r]; }
-    return;
-  }
-  const U2 u = uniform2(p.seed, PH_LINK, p.iter, (uint32_t)r, 0u);
-  const double t = u.u0 * total;
-
-  unsigned m = __ballot_sync(0xffffffffu, lane < nchunks && Q > t);
-  const int chunk = m ? (__ffs(m) - 1) : (nchunks - 1);
-  double rsum = shfl_d(Q, chunk > 0 ? chunk - 1 : 0);
-  if (chunk == 0) rsum = 0.0;
-
-  // pass 2: locate the step inside the chunk (same operations in the same order as pass 1)
-  const int s0 = chunk * spc, s1 = min(s0 + spc, nsteps);
-  int step = s1 - 1;
-  double wl = 0.0;
-  for (int s = s0; s < s1; ++s) {
-    wl = weight_at(s);
-    const double c = butterfly_sum(wl);
-    if (rsum + c > t) { step = s; break; }
-    if (s + 1 < s1) rsum = rsum + c;
-  }
-  // inside the step: Kogge-Stone inclusive scan over lanes
-  double P = wl;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const double o = shfl_up_d(P, d);
-    if (lane >= d) P = P + o;
-  }
-  m = __ballot_sync(0xffffffffu, rsum + P > t);
-  int pick;
-  if (m) pick = __ffs(m) - 1;
-  else {
-    const unsigned pos = __ballot_sync(0xffffffffu, wl > 0.0);
-    pick = pos ? (31 - __clz(pos)) : 0;
-  }
-  if (lane == 0) {
-    int j = (step << 5) + pick;
-    if (j >= n) j = n - 1;
-    p.newlink[r] = p.ent_sorted[p.ent_ptr[b] + j];
-    atomicAdd(p.pairs, (unsigned long long)n);
-  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -757,6 +508,7 @@ struct dbl_ctx {
 
   int64_t launches = 0;
   double link_ms = 0.0;
+  int link_mode = 0;  // 0 auto (TMA kernels), 1 force the generic kernel (tests)
   double last_sweep_ms = 0.0;
   int64_t link_launches = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_events;
@@ -801,8 +553,8 @@ static int upload_tree(dbl_ctx *ctx, const dbl_kdtree *t) {
 static int upload_model(dbl_ctx *ctx, const dbl_model_desc *d) {
   const int A = d->num_attrs;
   ctx->h_attrs.resize(A);
-  ctx->dtab.resize((size_t)A * 9);
-  ctx->itab.resize((size_t)A * 2);
+  ctx->dtab.resize((size_t)A * 10);
+  ctx->itab.resize((size_t)A * 4);
   auto up_d = [&](DevBuf<double> &b, const std::vector<double> &v) -> cudaError_t {
     cudaError_t e = b.alloc(v.size());
     if (e != cudaSuccess) return e;
@@ -817,8 +569,8 @@ static int upload_model(dbl_ctx *ctx, const dbl_model_desc *d) {
   };
   for (int a = 0; a < A; ++a) {
     const dbl_index *ix = d->indexes[a];
-    DevBuf<double> *t = &ctx->dtab[(size_t)a * 9];
-    DevBuf<int> *ti = &ctx->itab[(size_t)a * 2];
+    DevBuf<double> *t = &ctx->dtab[(size_t)a * 10];
+    DevBuf<int> *ti = &ctx->itab[(size_t)a * 4];
     CUDA_TRY(up_d(t[0], ix->phi));
     CUDA_TRY(up_d(t[1], ix->probs));
     CUDA_TRY(up_d(t[2], ix->norm));
@@ -830,8 +582,16 @@ static int upload_model(dbl_ctx *ctx, const dbl_model_desc *d) {
     CUDA_TRY(up_d(t[8], ix->expsim));
     CUDA_TRY(up_i(ti[0], ix->rowptr));
     CUDA_TRY(up_i(ti[1], ix->col));
+    CUDA_TRY(up_d(t[9], ix->hvals));
+    CUDA_TRY(up_i(ti[2], ix->hkeys));
+    {
+      std::vector<int32_t> hm(ix->hmult.begin(), ix->hmult.end());
+      CUDA_TRY(up_i(ti[3], hm));
+    }
     AttrDev &h = ctx->h_attrs[a];
-    h.V = ix->V; h.is_const = ix->is_const ? 1 : 0; h.kmax = ix->kmax; h.pad = 0;
+    h.V = ix->V; h.is_const = ix->is_const ? 1 : 0; h.kmax = ix->kmax; h.hsize = ix->hsize;
+    h.hshift = ix->hshift; h.pad0 = h.pad1 = h.pad2 = 0;
+    h.hvals = t[9].p; h.hkeys = ti[2].p; h.hmult = reinterpret_cast<const unsigned *>(ti[3].p);
     h.phi = t[0].p; h.probs = t[1].p; h.norm = t[2].p; h.invnorm = t[3].p; h.pk = t[4].p; h.cdf = t[5].p;
     h.logphi = t[6].p; h.lognorm = t[7].p; h.expsim = t[8].p;
     h.rowptr = ti[0].p; h.col = ti[1].p;
@@ -1173,6 +933,67 @@ static void drain_link_events(dbl_ctx *ctx) {
   ctx->pending_events.clear();
 }
 
+// ---------------------------------------------------------------------------------------------------
+// link kernel dispatch
+// ---------------------------------------------------------------------------------------------------
+template <int A>
+static int launch_pcg2(dbl_ctx *ctx, const LinkParams &lp, size_t smem) {
+  static bool configured = false;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(k_link_pcg2<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  k_link_pcg2<A><<<ctx->max_ctas, (LINK_WARPS + 1) * 32, smem, ctx->stream>>>(lp);
+  return DBL_OK;
+}
+
+static int launch_link(dbl_ctx *ctx, int sampler, uint32_t it) {
+  const int A = ctx->A;
+  LinkParams lp;
+  memset(&lp, 0, sizeof(lp));
+  lp.A = A; lp.F = ctx->F; lp.P = ctx->P; lp.sampler = sampler; lp.seed = ctx->seed; lp.iter = it;
+  lp.attrs = ctx->attrs.p; lp.x = ctx->x.p; lp.file = ctx->file.p; lp.link = ctx->link.p; lp.zmask = ctx->zmask.p;
+  lp.theta = ctx->theta.p; lp.ent_ptr = ctx->ent_ptr.p; lp.tile_ptr = ctx->tile_ptr.p; lp.rec_ptr = ctx->rec_ptr.p;
+  lp.cta_ptr = ctx->cta_ptr.p; lp.ent_sorted = ctx->ent_sorted.p; lp.rec_sorted = ctx->rec_sorted.p;
+  lp.tiles = ctx->tiles.p; lp.newlink = ctx->newlink.p; lp.status = ctx->status.p; lp.pairs = ctx->pairs.p;
+  // shared-memory layout of the per-warp hash tables (128-byte aligned so a 32-slot key table is one word per bank)
+  bool hash_ok = true;
+  int off = 0;
+  for (int a = 0; a < A; ++a) {
+    const AttrDev &h = ctx->h_attrs[a];
+    lp.hshift[a] = h.hshift;
+    if (h.is_const) continue;
+    if (h.hsize <= 0) { hash_ok = false; continue; }
+    lp.key_off[a] = off; off += ((h.hsize * 4 + 127) / 128) * 128;
+    lp.val_off[a] = off; off += ((h.hsize * 8 + 127) / 128) * 128;
+  }
+  lp.tab_bytes_per_warp = off;
+  const size_t ring = (size_t)LINK_STAGES * tile_words(A) * 4 + 128;
+  const int mode = ctx->link_mode;  // 0 auto, 1 force generic
+  if (mode != 1 && sampler == DBL_PCG_II && hash_ok && A <= LINK_MAX_UNROLL_A) {
+    const size_t smem = ring + (size_t)LINK_WARPS * off;
+    if (smem <= 200 * 1024) {
+      switch (A) {
+#define DBL_CASE(N) case N: return launch_pcg2<N>(ctx, lp, smem);
+        DBL_CASE(1) DBL_CASE(2) DBL_CASE(3) DBL_CASE(4) DBL_CASE(5) DBL_CASE(6) DBL_CASE(7) DBL_CASE(8)
+        DBL_CASE(9) DBL_CASE(10) DBL_CASE(11) DBL_CASE(12) DBL_CASE(13) DBL_CASE(14) DBL_CASE(15) DBL_CASE(16)
+#undef DBL_CASE
+      }
+    }
+  }
+  if (mode != 1 && sampler != DBL_PCG_II && ring <= 200 * 1024) {
+    static bool configured = false;
+    if (!configured) {
+      CUDA_TRY(cudaFuncSetAttribute(k_link_match, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = true;
+    }
+    k_link_match<<<ctx->max_ctas, (LINK_WARPS + 1) * 32, ring, ctx->stream>>>(lp);
+    return DBL_OK;
+  }
+  k_link_generic<<<ctx->max_ctas, LINK_WARPS * 32, 0, ctx->stream>>>(lp);
+  return DBL_OK;
+}
+
 extern "C" int dbl_sweep(dbl_ctx *ctx, int sampler, int32_t n_sweeps) {
   if (!ctx) return DBL_ERR_INVALID;
   if (sampler < 0 || sampler > 3 || n_sweeps < 0) { ctx->set_error("bad sampler / n_sweeps"); return DBL_ERR_INVALID; }
@@ -1192,17 +1013,14 @@ extern "C" int dbl_sweep(dbl_ctx *ctx, int sampler, int32_t n_sweeps) {
                                ctx->stream));
     }
     // (2) links
-    LinkParams lp;
-    lp.A = A; lp.F = F; lp.P = ctx->P; lp.sampler = sampler; lp.seed = ctx->seed; lp.iter = it;
-    lp.attrs = ctx->attrs.p; lp.x = ctx->x.p; lp.file = ctx->file.p; lp.link = ctx->link.p; lp.zmask = ctx->zmask.p;
-    lp.theta = ctx->theta.p; lp.ent_ptr = ctx->ent_ptr.p; lp.tile_ptr = ctx->tile_ptr.p; lp.rec_ptr = ctx->rec_ptr.p;
-    lp.cta_ptr = ctx->cta_ptr.p; lp.ent_sorted = ctx->ent_sorted.p; lp.rec_sorted = ctx->rec_sorted.p;
-    lp.tiles = ctx->tiles.p; lp.newlink = ctx->newlink.p; lp.status = ctx->status.p; lp.pairs = ctx->pairs.p;
     cudaEvent_t e0, e1;
     CUDA_TRY(cudaEventCreate(&e0));
     CUDA_TRY(cudaEventCreate(&e1));
     CUDA_TRY(cudaEventRecord(e0, ctx->stream));
-    k_link<<<ctx->max_ctas, LINK_WARPS * 32, 0, ctx->stream>>>(lp);
+    {
+      int rc = launch_link(ctx, sampler, it);
+      if (rc) return rc;
+    }
     CUDA_TRY(cudaEventRecord(e1, ctx->stream));
     ctx->pending_events.emplace_back(e0, e1);
     ctx->launches += 1;
@@ -1233,6 +1051,12 @@ extern "C" int dbl_sweep(dbl_ctx *ctx, int sampler, int32_t n_sweeps) {
   CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   ctx->last_sweep_ms = ms;
   drain_link_events(ctx);
+  return DBL_OK;
+}
+
+extern "C" int dbl_set_link_mode(dbl_ctx *ctx, int mode) {
+  if (!ctx || mode < 0 || mode > 1) return DBL_ERR_INVALID;
+  ctx->link_mode = mode;
   return DBL_OK;
 }
 

@@ -100,6 +100,58 @@ void dbl_index::finish() {
     logphi[v] = std::log(phi[v]);
     lognorm[v] = std::log(norm[v]);
   }
+  build_hash();
+}
+
+// Per-row perfect hash tables for expSimOf(x, y), y != x (AttributeIndex.scala:183-186): the link kernel
+// answers "is y similar to x, and how much" with one shared-memory probe.  All rows of an attribute share the
+// table size (a power of two <= 256); each row has its own multiplier found by search.
+void dbl_index::build_hash() {
+  hsize = 0;
+  hshift = 32;
+  hmult.clear(); hkeys.clear(); hvals.clear();
+  if (is_const) return;
+  int maxlen = 0;
+  for (int v = 0; v < V; ++v) maxlen = std::max(maxlen, rowptr[v + 1] - rowptr[v] - 1);
+  int H = 32;
+  while (H < 2 * maxlen) H <<= 1;
+  for (; H <= 256; H <<= 1) {
+    int lg = 0;
+    while ((1 << lg) < H) ++lg;
+    const int shift = 32 - lg;
+    std::vector<uint32_t> mult(V, 0);
+    std::vector<int32_t> keys((size_t)V * H, -1);
+    std::vector<double> vals((size_t)V * H, 1.0);
+    bool ok = true;
+    std::vector<int> used(H);
+    for (int v = 0; v < V && ok; ++v) {
+      bool found = false;
+      for (uint32_t k = 0; k < 2048 && !found; ++k) {
+        const uint32_t m = 2654435761u * (2 * k + 1);
+        std::fill(used.begin(), used.end(), 0);
+        bool clash = false;
+        for (int p = rowptr[v]; p < rowptr[v + 1] && !clash; ++p) {
+          if (col[p] == v) continue;
+          const uint32_t s = ((uint32_t)col[p] * m) >> shift;
+          if (used[s]) clash = true;
+          used[s] = 1;
+        }
+        if (!clash) { mult[v] = m; found = true; }
+      }
+      if (!found) { ok = false; break; }
+      for (int p = rowptr[v]; p < rowptr[v + 1]; ++p) {
+        if (col[p] == v) continue;
+        const uint32_t s = ((uint32_t)col[p] * mult[v]) >> shift;
+        keys[(size_t)v * H + s] = col[p];
+        vals[(size_t)v * H + s] = expsim[p];
+      }
+    }
+    if (ok) {
+      hsize = H; hshift = shift;
+      hmult.swap(mult); hkeys.swap(keys); hvals.swap(vals);
+      return;
+    }
+  }
 }
 
 extern "C" int dbl_index_build(dbl_index **out, const char *const *values, const double *weights, int32_t V,

@@ -69,7 +69,13 @@ struct dbl_index {
   std::vector<double> expsim;
   std::vector<double> pk, cdf;      // (kmax+1) x V
   std::vector<double> logphi, lognorm;
+  // per-row perfect hash of the off-diagonal similar values (link kernel): slot = (uint32(v) * hmult[x]) >> hshift
+  int32_t hsize = 0, hshift = 32;  // hsize == 0: no table (constant attribute, or rows too long)
+  std::vector<uint32_t> hmult;     // V
+  std::vector<int32_t> hkeys;      // V x hsize, -1 = empty
+  std::vector<double> hvals;       // V x hsize
   void finish();
+  void build_hash();
 };
 
 struct dbl_kdtree {

@@ -1,0 +1,636 @@
+// Link-update kernels: one warp per record scores every entity of the record's block and draws the new link.
+//
+// Reference: updateEntityIdCollapsed GU:363-395 (PCG-II), updateEntityId / updateEntityIdSeq GU:399-466
+// (PCG-I, Gibbs; dense form), DiscreteDist(weights).sample() GU:394,427,465.  Protocol: DESIGN.md section 4.
+//
+//   k_link_pcg2<A>  PCG-II, attributes fully unrolled (A = 1..16): the block's entity table streams through
+//                   shared memory in TE-entity tiles moved by TMA bulk copies (cp.async.bulk + mbarrier ring,
+//                   one producer warp); per-record constants live in registers; the sparse similarity row of
+//                   each record attribute is a perfect-hash table in shared memory (one bank-conflict-free
+//                   probe per candidate and attribute).
+//   k_link_match    PCG-I / Gibbs: same tile pipeline; candidates must agree on every observed non-distorted
+//                   attribute, checked most-selective-first with a warp-wide early out.
+//   k_link_generic  any A <= 32 / any row length; tiles read through L1/L2.  Fallback only.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "dbl_internal.h"
+
+constexpr int TE = 128;          // entities per tile of the block-sorted entity table
+constexpr int LINK_WARPS = 8;    // consumer warps (= records) per CTA
+constexpr int LINK_STAGES = 4;   // tile ring depth
+constexpr int LINK_MAX_UNROLL_A = 16;
+constexpr unsigned FULL = 0xffffffffu;
+
+__host__ __device__ inline size_t tile_words(int A) { return (size_t)A * TE + 2 * TE; }  // int32 words per tile
+
+struct AttrDev {
+  int V, is_const, kmax, hsize;
+  int hshift, pad0, pad1, pad2;
+  const double *phi, *probs, *norm, *invnorm, *pk, *cdf, *logphi, *lognorm, *expsim, *hvals;
+  const int *rowptr, *col, *hkeys;
+  const unsigned *hmult;
+};
+
+struct LinkParams {
+  int A, F, P, sampler;
+  uint64_t seed;
+  uint32_t iter;
+  const AttrDev *attrs;
+  const int *x, *file, *link;
+  const unsigned *zmask;
+  const double *theta;
+  const int *ent_ptr, *tile_ptr, *rec_ptr, *cta_ptr, *ent_sorted, *rec_sorted;
+  const int *tiles;
+  int *newlink;
+  int *status;
+  unsigned long long *pairs;
+  // fast kernels: shared-memory layout of the per-warp hash tables (bytes from the warp's table base)
+  int tab_bytes_per_warp;
+  int key_off[DBL_MAX_ATTRS];
+  int val_off[DBL_MAX_ATTRS];
+  int hshift[DBL_MAX_ATTRS];
+};
+
+// ---------------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double shfl_xor_d(double v, int d) { return __shfl_xor_sync(FULL, v, d); }
+__device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(FULL, v, d); }
+__device__ __forceinline__ double shfl_d(double v, int l) { return __shfl_sync(FULL, v, l); }
+
+// 5-level xor butterfly: every lane ends with the same sum
+__device__ __forceinline__ double butterfly_sum(double v) {
+  v = v + shfl_xor_d(v, 16);
+  v = v + shfl_xor_d(v, 8);
+  v = v + shfl_xor_d(v, 4);
+  v = v + shfl_xor_d(v, 2);
+  v = v + shfl_xor_d(v, 1);
+  return v;
+}
+
+__device__ __forceinline__ bool row_find(const AttrDev &at, int v1, int v2, double &e) {
+  int lo = at.rowptr[v1], hi = at.rowptr[v1 + 1] - 1;
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1;
+    const int c = at.col[mid];
+    if (c == v2) { e = at.expsim[mid]; return true; }
+    if (c < v2) lo = mid + 1; else hi = mid - 1;
+  }
+  return false;
+}
+
+// CTA -> (block, first record) mapping shared by all link kernels
+__device__ __forceinline__ int find_block(const LinkParams &p, int cta) {
+  int lo = 0, hi = p.P;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (p.cta_ptr[mid] <= cta) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// Second half of the draw: given the check-pointed running totals Q (lane c = end of
+// chunk c) locate u*total: chunk -> lane (Kogge-Stone scan of the chunk's lane sums) -> step.  wf(j) must
+// reproduce the pass-1 weight of candidate j bit for bit (0 for j >= n).
+template <class WeightFn>
+__device__ __forceinline__ int finish_draw(int lane, int n, int nsteps, int spc, int nchunks, double Q, double total,
+                                           double u, WeightFn wf) {
+  const double t = u * total;
+  unsigned m = __ballot_sync(FULL, lane < nchunks && Q > t);
+  const int chunk = m ? (__ffs(m) - 1) : (nchunks - 1);
+  double r = shfl_d(Q, chunk > 0 ? chunk - 1 : 0);
+  if (chunk == 0) r = 0.0;
+  const int s0 = chunk * spc, s1 = min(s0 + spc, nsteps);
+  double ls = 0.0;
+  for (int s = s0; s < s1; ++s) ls = ls + wf((s << 5) + lane);
+  double P = ls;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const double o = shfl_up_d(P, d);
+    if (lane >= d) P = P + o;
+  }
+  m = __ballot_sync(FULL, r + P > t);
+  int L;
+  if (m) L = __ffs(m) - 1;
+  else {
+    const unsigned pos = __ballot_sync(FULL, ls > 0.0);
+    L = pos ? (31 - __clz(pos)) : 0;
+  }
+  const double Pprev = shfl_up_d(P, 1);
+  const double base_l = lane ? r + Pprev : r;
+  const double base = shfl_d(base_l, L);
+  double cum = 0.0;
+  int step = -1, last_pos = -1;
+  for (int g = s0; g < s1 && step < 0; g += 32) {
+    const int s = g + lane;
+    const double wi = (s < s1) ? wf((s << 5) + L) : 0.0;
+    const int cnt = min(32, s1 - g);
+    for (int i = 0; i < cnt; ++i) {
+      const double wv = shfl_d(wi, i);
+      cum = cum + wv;
+      if (wv > 0.0) last_pos = g + i;
+      if (base + cum > t) { step = g + i; break; }
+    }
+  }
+  if (step < 0) step = last_pos >= 0 ? last_pos : s0;
+  int j = (step << 5) + L;
+  if (j >= n) j = n - 1;
+  return j;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// generic kernel (fallback)
+// ---------------------------------------------------------------------------------------------------
+struct RecAttr {
+  int kind;  // 0 skip, 1 const compare, 2 non-const sparse row, 3 missing non-const (PCG-II), 4 must match
+  int x;
+  int len;
+  int pad;
+  double rmatch;
+  const int *col;
+  const double *val;
+  const double *tab;  // invnorm (kind 3) / norm (kind 2 of PCG-I)
+};
+
+__device__ __forceinline__ void prep_rec_attr(const LinkParams &p, int r, int a, RecAttr &c) {
+  const AttrDev &at = p.attrs[a];
+  const int xv = p.x[(int64_t)r * p.A + a];
+  c.kind = 0; c.x = xv; c.len = 0; c.pad = 0; c.rmatch = 1.0; c.col = nullptr; c.val = nullptr; c.tab = nullptr;
+  if (p.sampler == DBL_PCG_II) {
+    if (xv < 0) {
+      if (!at.is_const) { c.kind = 3; c.tab = at.invnorm; }
+    } else {
+      const double th = p.theta[a * p.F + p.file[r]];
+      double d = th * at.phi[xv];
+      if (at.is_const) {
+        c.kind = 1;
+        c.rmatch = 1.0 + (1.0 - th) / d;
+      } else {
+        d = d * at.norm[xv];
+        double ediag = 1.0;
+        row_find(at, xv, xv, ediag);
+        c.kind = 2;
+        c.rmatch = ediag + (1.0 - th) / d;
+        c.col = at.col + at.rowptr[xv];
+        c.val = at.expsim + at.rowptr[xv];
+        c.len = at.rowptr[xv + 1] - at.rowptr[xv];
+      }
+    }
+  } else if (xv >= 0) {
+    const bool dist = (p.zmask[r] >> a) & 1u;
+    if (!dist) c.kind = 4;
+    else if (!at.is_const) {
+      c.kind = 2;
+      c.tab = at.norm;
+      c.col = at.col + at.rowptr[xv];
+      c.val = at.expsim + at.rowptr[xv];
+      c.len = at.rowptr[xv + 1] - at.rowptr[xv];
+    }
+  }
+}
+
+__device__ __forceinline__ bool rec_row_find(const RecAttr &c, int yv, double &e) {
+  int lo = 0, hi = c.len - 1;
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1;
+    const int cv = c.col[mid];
+    if (cv == yv) { e = c.val[mid]; return true; }
+    if (cv < yv) lo = mid + 1; else hi = mid - 1;
+  }
+  return false;
+}
+
+// protocol weight of one candidate; ycol points at attribute 0 of the candidate inside its tile (stride TE)
+__device__ __forceinline__ double generic_weight(const RecAttr *ra, int A, bool pcg2, const int *ycol, double N) {
+  double w;
+  if (pcg2) {
+    w = N;
+    for (int a = 0; a < A; ++a) {
+      const int k = ra[a].kind;
+      if ((k == 1 || k == 2) && ycol[a * TE] == ra[a].x) w = w * ra[a].rmatch;
+    }
+    for (int a = 0; a < A; ++a) {
+      if (ra[a].kind != 2) continue;
+      const int yv = ycol[a * TE];
+      double e;
+      if (yv != ra[a].x && rec_row_find(ra[a], yv, e)) w = w * e;
+    }
+    for (int a = 0; a < A; ++a)
+      if (ra[a].kind == 3) w = w * ra[a].tab[ycol[a * TE]];
+  } else {
+    for (int a = 0; a < A; ++a)
+      if (ra[a].kind == 4 && ycol[a * TE] != ra[a].x) return 0.0;
+    w = 1.0;
+    for (int a = 0; a < A; ++a)
+      if (ra[a].kind == 2) w = w * ra[a].tab[ycol[a * TE]];
+    for (int a = 0; a < A; ++a) {
+      double e;
+      if (ra[a].kind == 2 && rec_row_find(ra[a], ycol[a * TE], e)) w = w * e;
+    }
+  }
+  return w;
+}
+
+__device__ __forceinline__ void store_link(const LinkParams &p, int lane, int r, int b, int n, int j) {
+  if (lane == 0) {
+    p.newlink[r] = p.ent_sorted[p.ent_ptr[b] + j];
+    atomicAdd(p.pairs, (unsigned long long)n);
+  }
+}
+__device__ __forceinline__ void fail_link(const LinkParams &p, int lane, int r) {
+  if (lane == 0) {  // reference: IllegalArgumentException("zero probability mass")
+    atomicOr(p.status, 1);
+    p.newlink[r] = p.link[r];
+  }
+}
+
+__global__ void __launch_bounds__(LINK_WARPS * 32) k_link_generic(LinkParams p) {
+  __shared__ RecAttr s_ra[LINK_WARPS][DBL_MAX_ATTRS];
+  const int cta = blockIdx.x;
+  if (cta >= p.cta_ptr[p.P]) return;
+  const int b = find_block(p, cta);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ridx = p.rec_ptr[b] + (cta - p.cta_ptr[b]) * LINK_WARPS + warp;
+  if (ridx >= p.rec_ptr[b + 1]) return;
+  const int r = p.rec_sorted[ridx];
+  const int A = p.A;
+  const bool pcg2 = (p.sampler == DBL_PCG_II);
+  RecAttr *ra = s_ra[warp];
+  if (lane < A) {
+    RecAttr c;
+    prep_rec_attr(p, r, lane, c);
+    ra[lane] = c;
+  }
+  __syncwarp();
+  const int n = p.ent_ptr[b + 1] - p.ent_ptr[b];
+  const int nsteps = (n + 31) >> 5;
+  const int spc = max(1, (nsteps + 31) >> 5);
+  const int nchunks = (nsteps + spc - 1) / spc;
+  const size_t tw = tile_words(A);
+  const int *tiles = p.tiles + (size_t)p.tile_ptr[b] * tw;
+  auto wf = [&](int j) -> double {
+    if (j >= n) return 0.0;
+    const int *tile = tiles + (size_t)(j / TE) * tw;
+    const int slot = j % TE;
+    const double N = reinterpret_cast<const double *>(tile + (size_t)A * TE)[slot];
+    return generic_weight(ra, A, pcg2, tile + slot, N);
+  };
+  double run = 0.0, Q = 0.0, acc = 0.0;
+  int mark = min(spc, nsteps), chunk = 0;
+  for (int s = 0; s < nsteps; ++s) {
+    acc = acc + wf((s << 5) + lane);
+    if (s + 1 == mark) {
+      run = run + butterfly_sum(acc);
+      if (lane == chunk) Q = run;
+      ++chunk;
+      acc = 0.0;
+      mark = min(mark + spc, nsteps);
+    }
+  }
+  if (!(run > 0.0) || isinf(run)) { fail_link(p, lane, r); return; }
+  const U2 u = uniform2(p.seed, PH_LINK, p.iter, (uint32_t)r, 0u);
+  const int j = finish_draw(lane, n, nsteps, spc, nchunks, Q, run, u.u0, wf);
+  store_link(p, lane, r, b, n, j);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// TMA / mbarrier plumbing (sm_90+ PTX; SASS: UBLKCP, SYNCS)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, unsigned bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// Shared-memory ring of entity tiles filled by one producer warp; every consumer warp of the CTA reads every tile.
+struct TileRing {
+  int *tiles;          // LINK_STAGES * tile_words
+  uint64_t *full;      // LINK_STAGES
+  uint64_t *empty;     // LINK_STAGES
+  int tw;              // words per tile
+};
+
+__device__ __forceinline__ void ring_init(const TileRing &rg, int consumers) {
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < LINK_STAGES; ++s) { mbar_init(&rg.full[s], 1); mbar_init(&rg.empty[s], consumers); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+}
+// producer: one lane streams ntiles tiles from global
+__device__ __forceinline__ void ring_produce(const TileRing &rg, const int *gsrc, int ntiles) {
+  const unsigned bytes = (unsigned)rg.tw * 4u;
+  for (int t = 0; t < ntiles; ++t) {
+    const int s = t % LINK_STAGES;
+    if (t >= LINK_STAGES) mbar_wait(&rg.empty[s], ((t / LINK_STAGES) - 1) & 1);
+    mbar_arrive_expect_tx(&rg.full[s], bytes);
+    tma_load_1d(rg.tiles + (size_t)s * rg.tw, gsrc + (size_t)t * rg.tw, bytes, &rg.full[s]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_link_pcg2<A>
+// ---------------------------------------------------------------------------------------------------
+template <int A>
+struct Pcg2Rec {
+  int x[A];            // record value id; -1 = missing (never equals an entity value)
+  double rm[A];        // multiplier on an exact match
+  unsigned hm[A];      // hash multiplier (non-constant attributes)
+  unsigned smask;      // observed non-constant attributes (similar-value probe)
+  unsigned mmask;      // missing non-constant attributes (invnorm factor)
+};
+
+// CONVERGED: every lane of the warp executes the call (main loop) -> the rare similar-value multiply is skipped
+// warp-wide with a vote; pass 2 calls it under divergence and must not vote.
+template <int A, bool CONVERGED>
+__device__ __forceinline__ double pcg2_weight(const Pcg2Rec<A> &rc, const LinkParams &p, const char *tab, const int *y,
+                                              double N) {
+  double w = N;
+#pragma unroll
+  for (int a = 0; a < A; ++a)
+    if (y[a] == rc.x[a]) w = w * rc.rm[a];
+#pragma unroll
+  for (int a = 0; a < A; ++a) {
+    if ((rc.smask >> a) & 1u) {
+      const unsigned slot = ((unsigned)y[a] * rc.hm[a]) >> p.hshift[a];
+      const int key = reinterpret_cast<const int *>(tab + p.key_off[a])[slot];
+      const bool hit = (key == y[a]);
+      if (CONVERGED) {
+        if (__any_sync(FULL, hit)) {
+          if (hit) w = w * reinterpret_cast<const double *>(tab + p.val_off[a])[slot];
+        }
+      } else {
+        if (hit) w = w * reinterpret_cast<const double *>(tab + p.val_off[a])[slot];
+      }
+    }
+  }
+  if (rc.mmask) {
+#pragma unroll
+    for (int a = 0; a < A; ++a)
+      if ((rc.mmask >> a) & 1u) w = w * p.attrs[a].invnorm[y[a]];
+  }
+  return w;
+}
+
+template <int A>
+__global__ void __launch_bounds__((LINK_WARPS + 1) * 32) k_link_pcg2(LinkParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int cta = blockIdx.x;
+  if (cta >= p.cta_ptr[p.P]) return;
+  const int b = find_block(p, cta);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = p.ent_ptr[b + 1] - p.ent_ptr[b];
+  const int ntiles = p.tile_ptr[b + 1] - p.tile_ptr[b];
+  constexpr int TW = A * TE + 2 * TE;
+  TileRing rg;
+  rg.tiles = reinterpret_cast<int *>(smem);
+  rg.full = reinterpret_cast<uint64_t *>(smem + (size_t)LINK_STAGES * TW * 4);
+  rg.empty = rg.full + LINK_STAGES;
+  rg.tw = TW;
+  static_assert(2 * LINK_STAGES * 8 <= 128, "barrier area");
+  char *tab_base = reinterpret_cast<char *>(smem) + (size_t)LINK_STAGES * TW * 4 + 128;
+  const int *gtiles = p.tiles + (size_t)p.tile_ptr[b] * TW;
+  ring_init(rg, LINK_WARPS);
+
+  if (warp == LINK_WARPS) {  // producer warp
+    if (lane == 0) ring_produce(rg, gtiles, ntiles);
+    return;
+  }
+  const int ridx = p.rec_ptr[b] + (cta - p.cta_ptr[b]) * LINK_WARPS + warp;
+  const bool active = ridx < p.rec_ptr[b + 1];
+  const int r = active ? p.rec_sorted[ridx] : -1;
+  char *tab = tab_base + (size_t)warp * p.tab_bytes_per_warp;
+
+  // ---- per-record constants: lane a prepares attribute a, then everything is broadcast into registers
+  Pcg2Rec<A> rc;
+  rc.smask = 0; rc.mmask = 0;
+  {
+    int xv = -1;
+    double rmv = 1.0;
+    unsigned hmv = 0;
+    bool is_s = false, is_m = false;
+    if (active && lane < A) {
+      const AttrDev &at = p.attrs[lane];
+      xv = p.x[(int64_t)r * A + lane];
+      if (xv < 0) {
+        is_m = !at.is_const;
+      } else {
+        const double th = p.theta[lane * p.F + p.file[r]];
+        double d = th * at.phi[xv];
+        if (at.is_const) {
+          rmv = 1.0 + (1.0 - th) / d;
+        } else {
+          d = d * at.norm[xv];
+          double ediag = 1.0;
+          row_find(at, xv, xv, ediag);
+          rmv = ediag + (1.0 - th) / d;
+          hmv = at.hmult[xv];
+          is_s = true;
+        }
+      }
+    }
+    rc.smask = __ballot_sync(FULL, is_s);
+    rc.mmask = __ballot_sync(FULL, is_m);
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      rc.x[a] = __shfl_sync(FULL, xv, a);
+      rc.rm[a] = shfl_d(rmv, a);
+      rc.hm[a] = __shfl_sync(FULL, hmv, a);
+    }
+    // hash tables of the record's similarity rows -> shared memory
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      if ((rc.smask >> a) & 1u) {
+        const AttrDev &at = p.attrs[a];
+        const int H = at.hsize;
+        int *kd = reinterpret_cast<int *>(tab + p.key_off[a]);
+        double *vd = reinterpret_cast<double *>(tab + p.val_off[a]);
+        const int *ks = at.hkeys + (size_t)rc.x[a] * H;
+        const double *vs = at.hvals + (size_t)rc.x[a] * H;
+        for (int i = lane; i < H; i += 32) { kd[i] = ks[i]; vd[i] = vs[i]; }
+      }
+    }
+    __syncwarp();
+  }
+
+  const int nsteps = (n + 31) >> 5;
+  const int spc = max(1, (nsteps + 31) >> 5);
+  const int nchunks = (nsteps + spc - 1) / spc;
+
+  // ---- pass 1 over the TMA-staged tiles
+  double run = 0.0, Q = 0.0, acc = 0.0;
+  int mark = min(spc, nsteps), chunk = 0, gstep = 0;
+  for (int t = 0; t < ntiles; ++t) {
+    const int s = t % LINK_STAGES;
+    mbar_wait(&rg.full[s], (t / LINK_STAGES) & 1);
+    if (active) {
+      const int *tile = rg.tiles + (size_t)s * TW;
+      const double *tileN = reinterpret_cast<const double *>(tile + A * TE);
+#pragma unroll
+      for (int q = 0; q < TE / 32; ++q) {
+        const int slot = q * 32 + lane;
+        int y[A];
+#pragma unroll
+        for (int a = 0; a < A; ++a) y[a] = tile[a * TE + slot];
+        acc = acc + pcg2_weight<A, true>(rc, p, tab, y, tileN[slot]);
+        ++gstep;
+        if (gstep == mark) {
+          run = run + butterfly_sum(acc);
+          if (lane == chunk) Q = run;
+          ++chunk;
+          acc = 0.0;
+          mark = min(mark + spc, nsteps);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&rg.empty[s]);
+  }
+  if (!active) return;
+  if (!(run > 0.0) || isinf(run)) { fail_link(p, lane, r); return; }
+
+  // ---- pass 2 from the L2-resident copy of the tiles
+  auto wf = [&](int j) -> double {
+    if (j >= n) return 0.0;
+    const int *tile = gtiles + (size_t)(j / TE) * TW;
+    const int slot = j % TE;
+    int y[A];
+#pragma unroll
+    for (int a = 0; a < A; ++a) y[a] = tile[a * TE + slot];
+    return pcg2_weight<A, false>(rc, p, tab, y, reinterpret_cast<const double *>(tile + A * TE)[slot]);
+  };
+  const U2 u = uniform2(p.seed, PH_LINK, p.iter, (uint32_t)r, 0u);
+  const int j = finish_draw(lane, n, nsteps, spc, nchunks, Q, run, u.u0, wf);
+  store_link(p, lane, r, b, n, j);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_link_match: PCG-I / Gibbs (GU:399-466).  A candidate has weight 0 unless it agrees with the record on every
+// observed, non-distorted attribute; the agreeing few are scored with the generic weight function.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__((LINK_WARPS + 1) * 32) k_link_match(LinkParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ RecAttr s_ra[LINK_WARPS][DBL_MAX_ATTRS];
+  __shared__ int s_mm_attr[LINK_WARPS][DBL_MAX_ATTRS];  // must-match attributes, most selective first
+  __shared__ int s_mm_x[LINK_WARPS][DBL_MAX_ATTRS];
+  const int cta = blockIdx.x;
+  if (cta >= p.cta_ptr[p.P]) return;
+  const int b = find_block(p, cta);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int A = p.A;
+  const int n = p.ent_ptr[b + 1] - p.ent_ptr[b];
+  const int ntiles = p.tile_ptr[b + 1] - p.tile_ptr[b];
+  const int TW = (int)tile_words(A);
+  TileRing rg;
+  rg.tiles = reinterpret_cast<int *>(smem);
+  rg.full = reinterpret_cast<uint64_t *>(smem + (size_t)LINK_STAGES * TW * 4);
+  rg.empty = rg.full + LINK_STAGES;
+  rg.tw = TW;
+  const int *gtiles = p.tiles + (size_t)p.tile_ptr[b] * TW;
+  ring_init(rg, LINK_WARPS);
+  if (warp == LINK_WARPS) {
+    if (lane == 0) ring_produce(rg, gtiles, ntiles);
+    return;
+  }
+  const int ridx = p.rec_ptr[b] + (cta - p.cta_ptr[b]) * LINK_WARPS + warp;
+  const bool active = ridx < p.rec_ptr[b + 1];
+  const int r = active ? p.rec_sorted[ridx] : -1;
+  RecAttr *ra = s_ra[warp];
+  int nmm = 0;
+  if (active) {
+    double sel = 2.0;  // selectivity key: phi(x) of a must-match attribute
+    bool mm = false;
+    if (lane < A) {
+      RecAttr c;
+      prep_rec_attr(p, r, lane, c);
+      ra[lane] = c;
+      mm = (c.kind == 4);
+      if (mm) sel = p.attrs[lane].phi[c.x];
+    }
+    // rank must-match attributes by (phi, attribute id): tiny all-pairs rank via shuffles
+    int rank = 0;
+    for (int o = 0; o < A; ++o) {
+      const double so = shfl_d(sel, o);
+      const bool mo = __shfl_sync(FULL, (int)mm, o);
+      if (mo && (so < sel || (so == sel && o < lane))) ++rank;
+    }
+    if (mm) { s_mm_attr[warp][rank] = lane; s_mm_x[warp][rank] = ra[lane].x; }
+    nmm = __popc(__ballot_sync(FULL, mm));
+    __syncwarp();
+  }
+  const int nsteps = (n + 31) >> 5;
+  const int spc = max(1, (nsteps + 31) >> 5);
+  const int nchunks = (nsteps + spc - 1) / spc;
+  const int *mma = s_mm_attr[warp];
+  const int *mmx = s_mm_x[warp];
+
+  double run = 0.0, Q = 0.0, acc = 0.0;
+  int mark = min(spc, nsteps), chunk = 0, gstep = 0;
+  for (int t = 0; t < ntiles; ++t) {
+    const int s = t % LINK_STAGES;
+    mbar_wait(&rg.full[s], (t / LINK_STAGES) & 1);
+    if (active) {
+      const int *tile = rg.tiles + (size_t)s * TW;
+      const double *tileN = reinterpret_cast<const double *>(tile + A * TE);
+#pragma unroll
+      for (int q = 0; q < TE / 32; ++q) {
+        const int slot = q * 32 + lane;
+        bool ok = (t * TE + slot) < n;
+        for (int k = 0; k < nmm; ++k) {
+          ok = ok && (tile[mma[k] * TE + slot] == mmx[k]);
+          if (!__any_sync(FULL, ok)) break;
+        }
+        if (__any_sync(FULL, ok)) {
+          if (ok) acc = acc + generic_weight(ra, A, false, tile + slot, tileN[slot]);
+        }
+        ++gstep;
+        if (gstep == mark) {
+          run = run + butterfly_sum(acc);
+          if (lane == chunk) Q = run;
+          ++chunk;
+          acc = 0.0;
+          mark = min(mark + spc, nsteps);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&rg.empty[s]);
+  }
+  if (!active) return;
+  if (!(run > 0.0) || isinf(run)) { fail_link(p, lane, r); return; }
+  auto wf = [&](int j) -> double {
+    if (j >= n) return 0.0;
+    const int *tile = gtiles + (size_t)(j / TE) * TW;
+    const int slot = j % TE;
+    return generic_weight(ra, A, false, tile + slot, reinterpret_cast<const double *>(tile + (size_t)A * TE)[slot]);
+  };
+  const U2 u = uniform2(p.seed, PH_LINK, p.iter, (uint32_t)r, 0u);
+  const int j = finish_draw(lane, n, nsteps, spc, nchunks, Q, run, u.u0, wf);
+  store_link(p, lane, r, b, n, j);
+}

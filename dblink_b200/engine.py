@@ -333,6 +333,10 @@ class GibbsEngine:
     def kernel_launches(self):
         return _lib.load().dbl_kernel_launches(self._h)
 
+    def set_link_mode(self, mode):
+        """0 = automatic kernel choice, 1 = force the generic fallback link kernel (same draws)."""
+        _check(_lib.load().dbl_set_link_mode(self._h, int(mode)), "set_link_mode", self._h)
+
     def last_sweep_ms(self):
         return _lib.load().dbl_last_sweep_ms(self._h)
 

@@ -144,6 +144,9 @@ int dbl_summary(dbl_ctx *, dbl_summary_head *head, int64_t *agg_dist /*A*F*/, in
 
 /* count of kernels launched by this context since creation (bench.py's gpu_launches) */
 int64_t dbl_kernel_launches(const dbl_ctx *);
+/* Link-kernel selection: 0 = automatic (TMA-staged kernels when the model fits them), 1 = always the generic
+ * fallback kernel.  Both produce identical draws; this exists so tests can cover the fallback. */
+int dbl_set_link_mode(dbl_ctx *, int mode);
 /* CUDA-event time (ms) of the last dbl_sweep call, first operation to last operation on the context's stream */
 double dbl_last_sweep_ms(const dbl_ctx *);
 /* CUDA-event time (ms) spent in the link-scoring kernel since the last call; resets the accumulator */

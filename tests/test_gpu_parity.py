@@ -39,11 +39,14 @@ def test_initial_state(oracle, levels, attr_ids):
     assert_same_state(eng, st)
 
 
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("sampler", SAMPLERS)
 @pytest.mark.parametrize("levels,attr_ids", [(0, ()), (2, (2, 3))])
-def test_chain_from_init(oracle, sampler, levels, attr_ids):
+def test_chain_from_init(oracle, sampler, levels, attr_ids, mode):
+    """mode 0 = TMA-staged link kernels, mode 1 = generic fallback kernel: identical draws"""
     g = synth_problem(seed=5, R=900, n_files=2)
     eng, rc, x, file = product_setup(g, 99, levels, attr_ids)
+    eng.set_link_mode(mode)
     m, st, tree, ox, ofile = oracle_setup(oracle, g, 99, levels, attr_ids)
     for it in range(6):
         eng.sweep(sampler, 1)
