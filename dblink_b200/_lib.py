@@ -92,14 +92,14 @@ def load(build_if_missing=True):
     global _LIB
     if _LIB is not None:
         return _LIB
-    if build_if_missing:
+    if build_if_missing and (not os.path.exists(SO_PATH) or os.environ.get("DBL_REBUILD") == "1"):
+        # the in-tree library travels to the GPU box prebuilt; rebuild only when it is absent (or on request)
         from . import build as _build
 
         try:
-            _build.build()
-        except Exception as e:  # stale-but-present library is still usable on a box without nvcc
-            if not os.path.exists(SO_PATH):
-                raise RuntimeError(f"libdblink_b200.so is missing and could not be built: {e}") from e
+            _build.build(force=True)
+        except Exception as e:
+            raise RuntimeError(f"libdblink_b200.so is missing and could not be built: {e}") from e
     if not os.path.exists(SO_PATH):
         raise RuntimeError(
             "libdblink_b200.so not found: build it with `python -m dblink_b200.build` (needs nvcc). "

@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "dbl_internal.h"
+#define DBL_ENGINE_TU 1
 #include "dbl_link.cuh"
 
 #define CUDA_TRY(expr)                                                                          \
@@ -150,7 +151,7 @@ __global__ void k_block_scan(int P, const int *__restrict__ ent_cnt, const int *
 __global__ void k_build_tiles(int64_t E, int A, const int *__restrict__ y, const double *__restrict__ entN,
                               const int *__restrict__ blk_sorted, const int *__restrict__ ent_sorted,
                               const int *__restrict__ ent_ptr, const int *__restrict__ tile_ptr,
-                              int *__restrict__ tiles) {
+                              int *__restrict__ tiles, const int *__restrict__ perm) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= E) return;
   const int b = blk_sorted[i];
@@ -158,7 +159,7 @@ __global__ void k_build_tiles(int64_t E, int A, const int *__restrict__ y, const
   const int j = (int)(i - ent_ptr[b]);
   int *tile = tiles + (size_t)(tile_ptr[b] + j / TE) * tile_words(A);
   const int slot = j % TE;
-  for (int a = 0; a < A; ++a) tile[a * TE + slot] = y[(int64_t)e * A + a];
+  for (int k = 0; k < A; ++k) tile[k * TE + slot] = y[(int64_t)e * A + perm[k]];  // kernel order
   reinterpret_cast<double *>(tile + (size_t)A * TE)[slot] = entN[e];
 }
 
@@ -476,6 +477,10 @@ struct dbl_ctx {
   std::vector<DevBuf<double>> dtab;  // per-attr double tables
   std::vector<DevBuf<int>> itab;
   DevBuf<AttrDev> attrs;
+  DevBuf<int> perm_dev;
+  int perm[DBL_MAX_ATTRS] = {0};
+  int n_str = 0;       // non-constant attributes
+  bool hash32 = true;  // every non-constant attribute has a 32-slot perfect-hash table
   std::vector<AttrDev> h_attrs;
   DevBuf<int> tree_buf;
   TreeDev tree{};
@@ -598,6 +603,14 @@ static int upload_model(dbl_ctx *ctx, const dbl_model_desc *d) {
   }
   CUDA_TRY(ctx->attrs.alloc(A));
   CUDA_TRY(cudaMemcpy(ctx->attrs.p, ctx->h_attrs.data(), sizeof(AttrDev) * A, cudaMemcpyHostToDevice));
+  {
+    int k = 0;
+    for (int a = 0; a < A; ++a) if (ctx->h_attrs[a].is_const) ctx->perm[k++] = a;
+    ctx->n_str = A - k;
+    for (int a = 0; a < A; ++a) if (!ctx->h_attrs[a].is_const) { ctx->perm[k++] = a; if (ctx->h_attrs[a].hsize != 32) ctx->hash32 = false; }
+    CUDA_TRY(ctx->perm_dev.alloc(A));
+    CUDA_TRY(cudaMemcpy(ctx->perm_dev.p, ctx->perm, sizeof(int) * A, cudaMemcpyHostToDevice));
+  }
   return upload_tree(ctx, d->tree);
 }
 
@@ -744,7 +757,7 @@ static int relayout(dbl_ctx *ctx) {
   CUDA_TRY(cudaMemsetAsync(ctx->tiles.p, 0, ctx->tiles.n * sizeof(int), ctx->stream));
   k_build_tiles<<<grid_for(E, 256), 256, 0, ctx->stream>>>(E, A, ctx->y.p, ctx->entN.p, ctx->blk_sorted.p,
                                                            ctx->ent_sorted.p, ctx->ent_ptr.p, ctx->tile_ptr.p,
-                                                           ctx->tiles.p);
+                                                           ctx->tiles.p, ctx->perm_dev.p);
   ctx->launches += 10;
   CUDA_TRY(cudaGetLastError());
   return DBL_OK;
@@ -936,16 +949,10 @@ static void drain_link_events(dbl_ctx *ctx) {
 // ---------------------------------------------------------------------------------------------------
 // link kernel dispatch
 // ---------------------------------------------------------------------------------------------------
-template <int A>
-static int launch_pcg2(dbl_ctx *ctx, const LinkParams &lp, size_t smem) {
-  static bool configured = false;
-  if (!configured) {
-    CUDA_TRY(cudaFuncSetAttribute(k_link_pcg2<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
-  }
-  k_link_pcg2<A><<<ctx->max_ctas, (LINK_WARPS + 1) * 32, smem, ctx->stream>>>(lp);
-  return DBL_OK;
-}
+#define DBL_DECL(N) int dbl_launch_pcg2_a##N(int ns, int grid, cudaStream_t stream, const LinkParams &lp);
+DBL_DECL(1) DBL_DECL(2) DBL_DECL(3) DBL_DECL(4) DBL_DECL(5) DBL_DECL(6) DBL_DECL(7) DBL_DECL(8)
+DBL_DECL(9) DBL_DECL(10) DBL_DECL(11) DBL_DECL(12) DBL_DECL(13) DBL_DECL(14) DBL_DECL(15) DBL_DECL(16)
+#undef DBL_DECL
 
 static int launch_link(dbl_ctx *ctx, int sampler, uint32_t it) {
   const int A = ctx->A;
@@ -956,30 +963,19 @@ static int launch_link(dbl_ctx *ctx, int sampler, uint32_t it) {
   lp.theta = ctx->theta.p; lp.ent_ptr = ctx->ent_ptr.p; lp.tile_ptr = ctx->tile_ptr.p; lp.rec_ptr = ctx->rec_ptr.p;
   lp.cta_ptr = ctx->cta_ptr.p; lp.ent_sorted = ctx->ent_sorted.p; lp.rec_sorted = ctx->rec_sorted.p;
   lp.tiles = ctx->tiles.p; lp.newlink = ctx->newlink.p; lp.status = ctx->status.p; lp.pairs = ctx->pairs.p;
-  // shared-memory layout of the per-warp hash tables (128-byte aligned so a 32-slot key table is one word per bank)
-  bool hash_ok = true;
-  int off = 0;
-  for (int a = 0; a < A; ++a) {
-    const AttrDev &h = ctx->h_attrs[a];
-    lp.hshift[a] = h.hshift;
-    if (h.is_const) continue;
-    if (h.hsize <= 0) { hash_ok = false; continue; }
-    lp.key_off[a] = off; off += ((h.hsize * 4 + 127) / 128) * 128;
-    lp.val_off[a] = off; off += ((h.hsize * 8 + 127) / 128) * 128;
-  }
-  lp.tab_bytes_per_warp = off;
+  for (int k = 0; k < A; ++k) lp.perm[k] = ctx->perm[k];
   const size_t ring = (size_t)LINK_STAGES * tile_words(A) * 4 + 128;
   const int mode = ctx->link_mode;  // 0 auto, 1 force generic
-  if (mode != 1 && sampler == DBL_PCG_II && hash_ok && A <= LINK_MAX_UNROLL_A) {
-    const size_t smem = ring + (size_t)LINK_WARPS * off;
-    if (smem <= 200 * 1024) {
-      switch (A) {
-#define DBL_CASE(N) case N: return launch_pcg2<N>(ctx, lp, smem);
-        DBL_CASE(1) DBL_CASE(2) DBL_CASE(3) DBL_CASE(4) DBL_CASE(5) DBL_CASE(6) DBL_CASE(7) DBL_CASE(8)
-        DBL_CASE(9) DBL_CASE(10) DBL_CASE(11) DBL_CASE(12) DBL_CASE(13) DBL_CASE(14) DBL_CASE(15) DBL_CASE(16)
+  if (mode != 1 && sampler == DBL_PCG_II && ctx->hash32 && A <= LINK_MAX_UNROLL_A) {
+    int rc = -1;
+    switch (A) {
+#define DBL_CASE(N) case N: rc = dbl_launch_pcg2_a##N(ctx->n_str, ctx->max_ctas, ctx->stream, lp); break;
+      DBL_CASE(1) DBL_CASE(2) DBL_CASE(3) DBL_CASE(4) DBL_CASE(5) DBL_CASE(6) DBL_CASE(7) DBL_CASE(8)
+      DBL_CASE(9) DBL_CASE(10) DBL_CASE(11) DBL_CASE(12) DBL_CASE(13) DBL_CASE(14) DBL_CASE(15) DBL_CASE(16)
 #undef DBL_CASE
-      }
     }
+    if (rc != 0) { ctx->set_error(std::string("k_link_pcg2 launch: ") + cudaGetErrorString((cudaError_t)rc)); return DBL_ERR_CUDA; }
+    return DBL_OK;
   }
   if (mode != 1 && sampler != DBL_PCG_II && ring <= 200 * 1024) {
     static bool configured = false;

@@ -3,7 +3,7 @@
 // Reference: updateEntityIdCollapsed GU:363-395 (PCG-II), updateEntityId / updateEntityIdSeq GU:399-466
 // (PCG-I, Gibbs; dense form), DiscreteDist(weights).sample() GU:394,427,465.  Protocol: DESIGN.md section 4.
 //
-//   k_link_pcg2<A>  PCG-II, attributes fully unrolled (A = 1..16): the block's entity table streams through
+//   k_link_pcg2<A,NS> (dbl_link_pcg2.cuh) PCG-II, attributes fully unrolled (A = 1..16, NS non-constant): the block's entity table streams through
 //                   shared memory in TE-entity tiles moved by TMA bulk copies (cp.async.bulk + mbarrier ring,
 //                   one producer warp); per-record constants live in registers; the sparse similarity row of
 //                   each record attribute is a perfect-hash table in shared memory (one bank-conflict-free
@@ -47,11 +47,9 @@ struct LinkParams {
   int *newlink;
   int *status;
   unsigned long long *pairs;
-  // fast kernels: shared-memory layout of the per-warp hash tables (bytes from the warp's table base)
-  int tab_bytes_per_warp;
-  int key_off[DBL_MAX_ATTRS];
-  int val_off[DBL_MAX_ATTRS];
-  int hshift[DBL_MAX_ATTRS];
+  // "kernel order" of the attributes: constant attributes first, then the others, each group in ascending
+  // attribute id.  Tiles, per-record constants and the multiplication order of the protocol use this order.
+  int perm[DBL_MAX_ATTRS];
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -155,7 +153,9 @@ struct RecAttr {
   const double *tab;  // invnorm (kind 3) / norm (kind 2 of PCG-I)
 };
 
-__device__ __forceinline__ void prep_rec_attr(const LinkParams &p, int r, int a, RecAttr &c) {
+// k = position in kernel order
+__device__ __forceinline__ void prep_rec_attr(const LinkParams &p, int r, int k, RecAttr &c) {
+  const int a = p.perm[k];
   const AttrDev &at = p.attrs[a];
   const int xv = p.x[(int64_t)r * p.A + a];
   c.kind = 0; c.x = xv; c.len = 0; c.pad = 0; c.rmatch = 1.0; c.col = nullptr; c.val = nullptr; c.tab = nullptr;
@@ -247,6 +247,7 @@ __device__ __forceinline__ void fail_link(const LinkParams &p, int lane, int r) 
   }
 }
 
+#ifdef DBL_ENGINE_TU  // non-template kernels live in exactly one translation unit (dbl_engine.cu)
 __global__ void __launch_bounds__(LINK_WARPS * 32) k_link_generic(LinkParams p) {
   __shared__ RecAttr s_ra[LINK_WARPS][DBL_MAX_ATTRS];
   const int cta = blockIdx.x;
@@ -296,6 +297,8 @@ __global__ void __launch_bounds__(LINK_WARPS * 32) k_link_generic(LinkParams p) 
   store_link(p, lane, r, b, n, j);
 }
 
+#endif  // DBL_ENGINE_TU
+
 // ---------------------------------------------------------------------------------------------------
 // TMA / mbarrier plumbing (sm_90+ PTX; SASS: UBLKCP, SYNCS)
 // ---------------------------------------------------------------------------------------------------
@@ -315,9 +318,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
   uint32_t ok = 0;
   while (!ok) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware instead of spinning
         : "memory");
   }
 }
@@ -355,185 +358,10 @@ __device__ __forceinline__ void ring_produce(const TileRing &rg, const int *gsrc
 }
 
 // ---------------------------------------------------------------------------------------------------
-// k_link_pcg2<A>
-// ---------------------------------------------------------------------------------------------------
-template <int A>
-struct Pcg2Rec {
-  int x[A];            // record value id; -1 = missing (never equals an entity value)
-  double rm[A];        // multiplier on an exact match
-  unsigned hm[A];      // hash multiplier (non-constant attributes)
-  unsigned smask;      // observed non-constant attributes (similar-value probe)
-  unsigned mmask;      // missing non-constant attributes (invnorm factor)
-};
-
-// CONVERGED: every lane of the warp executes the call (main loop) -> the rare similar-value multiply is skipped
-// warp-wide with a vote; pass 2 calls it under divergence and must not vote.
-template <int A, bool CONVERGED>
-__device__ __forceinline__ double pcg2_weight(const Pcg2Rec<A> &rc, const LinkParams &p, const char *tab, const int *y,
-                                              double N) {
-  double w = N;
-#pragma unroll
-  for (int a = 0; a < A; ++a)
-    if (y[a] == rc.x[a]) w = w * rc.rm[a];
-#pragma unroll
-  for (int a = 0; a < A; ++a) {
-    if ((rc.smask >> a) & 1u) {
-      const unsigned slot = ((unsigned)y[a] * rc.hm[a]) >> p.hshift[a];
-      const int key = reinterpret_cast<const int *>(tab + p.key_off[a])[slot];
-      const bool hit = (key == y[a]);
-      if (CONVERGED) {
-        if (__any_sync(FULL, hit)) {
-          if (hit) w = w * reinterpret_cast<const double *>(tab + p.val_off[a])[slot];
-        }
-      } else {
-        if (hit) w = w * reinterpret_cast<const double *>(tab + p.val_off[a])[slot];
-      }
-    }
-  }
-  if (rc.mmask) {
-#pragma unroll
-    for (int a = 0; a < A; ++a)
-      if ((rc.mmask >> a) & 1u) w = w * p.attrs[a].invnorm[y[a]];
-  }
-  return w;
-}
-
-template <int A>
-__global__ void __launch_bounds__((LINK_WARPS + 1) * 32) k_link_pcg2(LinkParams p) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int cta = blockIdx.x;
-  if (cta >= p.cta_ptr[p.P]) return;
-  const int b = find_block(p, cta);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = p.ent_ptr[b + 1] - p.ent_ptr[b];
-  const int ntiles = p.tile_ptr[b + 1] - p.tile_ptr[b];
-  constexpr int TW = A * TE + 2 * TE;
-  TileRing rg;
-  rg.tiles = reinterpret_cast<int *>(smem);
-  rg.full = reinterpret_cast<uint64_t *>(smem + (size_t)LINK_STAGES * TW * 4);
-  rg.empty = rg.full + LINK_STAGES;
-  rg.tw = TW;
-  static_assert(2 * LINK_STAGES * 8 <= 128, "barrier area");
-  char *tab_base = reinterpret_cast<char *>(smem) + (size_t)LINK_STAGES * TW * 4 + 128;
-  const int *gtiles = p.tiles + (size_t)p.tile_ptr[b] * TW;
-  ring_init(rg, LINK_WARPS);
-
-  if (warp == LINK_WARPS) {  // producer warp
-    if (lane == 0) ring_produce(rg, gtiles, ntiles);
-    return;
-  }
-  const int ridx = p.rec_ptr[b] + (cta - p.cta_ptr[b]) * LINK_WARPS + warp;
-  const bool active = ridx < p.rec_ptr[b + 1];
-  const int r = active ? p.rec_sorted[ridx] : -1;
-  char *tab = tab_base + (size_t)warp * p.tab_bytes_per_warp;
-
-  // ---- per-record constants: lane a prepares attribute a, then everything is broadcast into registers
-  Pcg2Rec<A> rc;
-  rc.smask = 0; rc.mmask = 0;
-  {
-    int xv = -1;
-    double rmv = 1.0;
-    unsigned hmv = 0;
-    bool is_s = false, is_m = false;
-    if (active && lane < A) {
-      const AttrDev &at = p.attrs[lane];
-      xv = p.x[(int64_t)r * A + lane];
-      if (xv < 0) {
-        is_m = !at.is_const;
-      } else {
-        const double th = p.theta[lane * p.F + p.file[r]];
-        double d = th * at.phi[xv];
-        if (at.is_const) {
-          rmv = 1.0 + (1.0 - th) / d;
-        } else {
-          d = d * at.norm[xv];
-          double ediag = 1.0;
-          row_find(at, xv, xv, ediag);
-          rmv = ediag + (1.0 - th) / d;
-          hmv = at.hmult[xv];
-          is_s = true;
-        }
-      }
-    }
-    rc.smask = __ballot_sync(FULL, is_s);
-    rc.mmask = __ballot_sync(FULL, is_m);
-#pragma unroll
-    for (int a = 0; a < A; ++a) {
-      rc.x[a] = __shfl_sync(FULL, xv, a);
-      rc.rm[a] = shfl_d(rmv, a);
-      rc.hm[a] = __shfl_sync(FULL, hmv, a);
-    }
-    // hash tables of the record's similarity rows -> shared memory
-#pragma unroll
-    for (int a = 0; a < A; ++a) {
-      if ((rc.smask >> a) & 1u) {
-        const AttrDev &at = p.attrs[a];
-        const int H = at.hsize;
-        int *kd = reinterpret_cast<int *>(tab + p.key_off[a]);
-        double *vd = reinterpret_cast<double *>(tab + p.val_off[a]);
-        const int *ks = at.hkeys + (size_t)rc.x[a] * H;
-        const double *vs = at.hvals + (size_t)rc.x[a] * H;
-        for (int i = lane; i < H; i += 32) { kd[i] = ks[i]; vd[i] = vs[i]; }
-      }
-    }
-    __syncwarp();
-  }
-
-  const int nsteps = (n + 31) >> 5;
-  const int spc = max(1, (nsteps + 31) >> 5);
-  const int nchunks = (nsteps + spc - 1) / spc;
-
-  // ---- pass 1 over the TMA-staged tiles
-  double run = 0.0, Q = 0.0, acc = 0.0;
-  int mark = min(spc, nsteps), chunk = 0, gstep = 0;
-  for (int t = 0; t < ntiles; ++t) {
-    const int s = t % LINK_STAGES;
-    mbar_wait(&rg.full[s], (t / LINK_STAGES) & 1);
-    if (active) {
-      const int *tile = rg.tiles + (size_t)s * TW;
-      const double *tileN = reinterpret_cast<const double *>(tile + A * TE);
-#pragma unroll
-      for (int q = 0; q < TE / 32; ++q) {
-        const int slot = q * 32 + lane;
-        int y[A];
-#pragma unroll
-        for (int a = 0; a < A; ++a) y[a] = tile[a * TE + slot];
-        acc = acc + pcg2_weight<A, true>(rc, p, tab, y, tileN[slot]);
-        ++gstep;
-        if (gstep == mark) {
-          run = run + butterfly_sum(acc);
-          if (lane == chunk) Q = run;
-          ++chunk;
-          acc = 0.0;
-          mark = min(mark + spc, nsteps);
-        }
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&rg.empty[s]);
-  }
-  if (!active) return;
-  if (!(run > 0.0) || isinf(run)) { fail_link(p, lane, r); return; }
-
-  // ---- pass 2 from the L2-resident copy of the tiles
-  auto wf = [&](int j) -> double {
-    if (j >= n) return 0.0;
-    const int *tile = gtiles + (size_t)(j / TE) * TW;
-    const int slot = j % TE;
-    int y[A];
-#pragma unroll
-    for (int a = 0; a < A; ++a) y[a] = tile[a * TE + slot];
-    return pcg2_weight<A, false>(rc, p, tab, y, reinterpret_cast<const double *>(tile + A * TE)[slot]);
-  };
-  const U2 u = uniform2(p.seed, PH_LINK, p.iter, (uint32_t)r, 0u);
-  const int j = finish_draw(lane, n, nsteps, spc, nchunks, Q, run, u.u0, wf);
-  store_link(p, lane, r, b, n, j);
-}
-
-// ---------------------------------------------------------------------------------------------------
 // k_link_match: PCG-I / Gibbs (GU:399-466).  A candidate has weight 0 unless it agrees with the record on every
 // observed, non-distorted attribute; the agreeing few are scored with the generic weight function.
 // ---------------------------------------------------------------------------------------------------
+#ifdef DBL_ENGINE_TU
 __global__ void __launch_bounds__((LINK_WARPS + 1) * 32) k_link_match(LinkParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ RecAttr s_ra[LINK_WARPS][DBL_MAX_ATTRS];
@@ -571,7 +399,7 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32) k_link_match(LinkParams
       prep_rec_attr(p, r, lane, c);
       ra[lane] = c;
       mm = (c.kind == 4);
-      if (mm) sel = p.attrs[lane].phi[c.x];
+      if (mm) sel = p.attrs[p.perm[lane]].phi[c.x];
     }
     // rank must-match attributes by (phi, attribute id): tiny all-pairs rank via shuffles
     int rank = 0;
@@ -634,3 +462,4 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32) k_link_match(LinkParams
   const int j = finish_draw(lane, n, nsteps, spc, nchunks, Q, run, u.u0, wf);
   store_link(p, lane, r, b, n, j);
 }
+#endif  // DBL_ENGINE_TU

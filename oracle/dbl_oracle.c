@@ -902,8 +902,10 @@ static double protocol_weight(const orc_state *s, int sampler, const rec_attr_t 
   /* multiplication order of the protocol: three passes over the attributes, each in attribute order */
   if (sampler == ORC_PCG_II) {
     w = nprod;
-    for (int a = 0; a < A; ++a) /* (i) exact matches */
-      if ((ra[a].kind == 1 || ra[a].kind == 2) && ye[a] == ra[a].x) w = w * ra[a].rmatch;
+    for (int a = 0; a < A; ++a) /* (i) exact matches: constant attributes first, then the others */
+      if (ra[a].kind == 1 && ye[a] == ra[a].x) w = w * ra[a].rmatch;
+    for (int a = 0; a < A; ++a)
+      if (ra[a].kind == 2 && ye[a] == ra[a].x) w = w * ra[a].rmatch;
     for (int a = 0; a < A; ++a) { /* (ii) similar but different values */
       double e;
       if (ra[a].kind == 2 && ye[a] != ra[a].x && row_find(m->idx[a], ra[a].x, ye[a], &e)) w = w * e;
