@@ -77,6 +77,15 @@ SIGNATURES = {
     "dbl_sweep": (C.c_int, [vp, C.c_int, C.c_int32]),
     "dbl_links_download": (C.c_int, [vp, i32p, i32p]),
     "dbl_summary": (C.c_int, [vp, C.POINTER(SummaryHead), i64p, i64p, f64p]),
+    "dbl_set_block_owners": (C.c_int, [vp, i32p]),
+    "dbl_sweep_begin": (C.c_int, [vp, C.c_int, i64p, i64p]),
+    "dbl_exchange_pack": (C.c_int, [vp, vp, vp]),
+    "dbl_exchange_unpack": (C.c_int, [vp, vp, C.c_int64, vp, C.c_int64]),
+    "dbl_sweep_end": (C.c_int, [vp]),
+    "dbl_summary_words": (C.c_int32, [vp]),
+    "dbl_partial_summary": (C.c_int, [vp, i64p, f64p]),
+    "dbl_set_global_summary": (C.c_int, [vp, i64p, C.c_double]),
+    "dbl_owned_masks": (C.c_int, [vp, u8p, u8p]),
     "dbl_kernel_launches": (C.c_int64, [vp]),
     "dbl_set_link_mode": (C.c_int, [vp, C.c_int]),
     "dbl_last_sweep_ms": (C.c_double, [vp]),

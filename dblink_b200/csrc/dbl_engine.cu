@@ -84,11 +84,11 @@ __device__ __forceinline__ int tree_leaf(const TreeDev &t, const int *yrow) {
 __global__ void k_entity_post(int64_t E, int A, const int *__restrict__ y, const AttrDev *__restrict__ attrs,
                               TreeDev tree, double *__restrict__ entN, int *__restrict__ blk,
                               const int *__restrict__ ent_rec_ptr, long long *__restrict__ counts, int iso_slot,
-                              double *__restrict__ loglik) {
+                              double *__restrict__ loglik, const unsigned char *__restrict__ ent_owned) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double ll = 0.0;
   int iso = 0;
-  if (e < E) {
+  if (e < E && ent_owned[e]) {
     const int *ye = y + e * A;
     double n = 1.0;
     for (int a = 0; a < A; ++a) {
@@ -126,10 +126,21 @@ __global__ void k_hist(int64_t n, const int *__restrict__ key, int *__restrict__
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) atomicAdd(&cnt[key[i]], 1);
 }
+// sort keys; entities / records this rank does not own go to the dummy slot (block P, entity E)
 __global__ void k_rec_block_keys(int64_t R, const int *__restrict__ link, const int *__restrict__ blk,
-                                 int *__restrict__ key) {
+                                 const unsigned char *__restrict__ rec_owned, int P, int *__restrict__ key) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < R) key[r] = blk[link[r]];
+  if (r < R) key[r] = rec_owned[r] ? blk[link[r]] : P;
+}
+__global__ void k_ent_block_keys(int64_t E, const int *__restrict__ blk, const unsigned char *__restrict__ ent_owned,
+                                 int P, int *__restrict__ key) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < E) key[e] = ent_owned[e] ? blk[e] : P;
+}
+__global__ void k_rec_link_keys(int64_t R, const int *__restrict__ link, const unsigned char *__restrict__ rec_owned,
+                                int E, int *__restrict__ key) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < R) key[r] = rec_owned[r] ? link[r] : E;
 }
 // prefix sums over the P blocks (P is 2^numLevels: small) -- one CTA, Hillis-Steele over chunks
 __global__ void k_block_scan(int P, const int *__restrict__ ent_cnt, const int *__restrict__ rec_cnt,
@@ -151,10 +162,11 @@ __global__ void k_block_scan(int P, const int *__restrict__ ent_cnt, const int *
 __global__ void k_build_tiles(int64_t E, int A, const int *__restrict__ y, const double *__restrict__ entN,
                               const int *__restrict__ blk_sorted, const int *__restrict__ ent_sorted,
                               const int *__restrict__ ent_ptr, const int *__restrict__ tile_ptr,
-                              int *__restrict__ tiles, const int *__restrict__ perm) {
+                              int *__restrict__ tiles, const int *__restrict__ perm, int P) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= E) return;
   const int b = blk_sorted[i];
+  if (b >= P) return;  // not owned by this rank
   const int e = ent_sorted[i];
   const int j = (int)(i - ent_ptr[b]);
   int *tile = tiles + (size_t)(tile_ptr[b] + j / TE) * tile_words(A);
@@ -177,6 +189,7 @@ struct ValParams {
   const unsigned *zmask;
   const double *theta;
   const int *ent_rec_ptr, *rec_by_ent;
+  const unsigned char *ent_owned;
   int *y;
 };
 
@@ -251,6 +264,7 @@ __global__ void k_values(ValParams p) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= p.E * p.A) return;
   const int64_t e = tid / p.A;
+  if (!p.ent_owned[e]) return;
   const int a = (int)(tid % p.A);
   const AttrDev &at = p.attrs[a];
   const bool collapsed = (p.sampler == DBL_PCG_I || p.sampler == DBL_PCG_II);
@@ -342,12 +356,13 @@ struct DistParams {
   const double *theta;
   long long *counts;  // [A*F] aggDist, then [A+1] recDist
   double *loglik;
+  const unsigned char *rec_owned;
 };
 
 __global__ void k_dist(DistParams p) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double ll = 0.0;
-  if (r < p.R) {
+  if (r < p.R && p.rec_owned[r]) {
     const int f = p.file[r];
     const int *ye = p.y + (int64_t)p.link[r] * p.A;
     unsigned zm = p.zmask[r];
@@ -449,6 +464,97 @@ __global__ void k_unpack_z(int64_t R, int A, const unsigned *__restrict__ zmask,
 }
 
 // ---------------------------------------------------------------------------------------------------
+// multi-GPU: ownership and the exchange of clusters whose new block belongs to another rank (replaces the
+// shuffle `.partitionBy(partitioner)`, GU:144).  Messages: entity = [e, y_0..y_{A-1}], record = [r, e, zmask].
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_mark_ent_owned(int64_t E, const int *__restrict__ blk, const int *__restrict__ owner, int rank,
+                                 unsigned char *__restrict__ ent_owned) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < E) ent_owned[e] = (owner[blk[e]] == rank);
+}
+__global__ void k_mark_rec_owned(int64_t R, const int *__restrict__ link, const unsigned char *__restrict__ ent_owned,
+                                 unsigned char *__restrict__ rec_owned) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < R) rec_owned[r] = ent_owned[link[r]];
+}
+__global__ void k_move_count_ent(int64_t E, const int *__restrict__ blk, const int *__restrict__ owner, int rank,
+                                 const unsigned char *__restrict__ ent_owned, int *__restrict__ ent_dest,
+                                 unsigned long long *__restrict__ cnt) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int d = -1;
+  if (ent_owned[e]) {
+    const int o = owner[blk[e]];
+    if (o != rank) { d = o; atomicAdd(&cnt[o], 1ull); }
+  }
+  ent_dest[e] = d;
+}
+__global__ void k_move_count_rec(int64_t R, const int *__restrict__ link, const unsigned char *__restrict__ rec_owned,
+                                 const int *__restrict__ ent_dest, unsigned long long *__restrict__ cnt) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R || !rec_owned[r]) return;
+  const int d = ent_dest[link[r]];
+  if (d >= 0) atomicAdd(&cnt[d], 1ull);
+}
+__global__ void k_move_pack_ent(int64_t E, int A, const int *__restrict__ y, const int *__restrict__ ent_dest,
+                                unsigned char *__restrict__ ent_owned, unsigned long long *__restrict__ cursor,
+                                int *__restrict__ buf) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int d = ent_dest[e];
+  if (d < 0) return;
+  const unsigned long long slot = atomicAdd(&cursor[d], 1ull);
+  int *m = buf + slot * (A + 1);
+  m[0] = (int)e;
+  for (int a = 0; a < A; ++a) m[1 + a] = y[e * A + a];
+  ent_owned[e] = 0;
+}
+__global__ void k_move_pack_rec(int64_t R, const int *__restrict__ link, const unsigned *__restrict__ zmask,
+                                const int *__restrict__ ent_dest, unsigned char *__restrict__ rec_owned,
+                                unsigned long long *__restrict__ cursor, int *__restrict__ buf) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R || !rec_owned[r]) return;
+  const int d = ent_dest[link[r]];
+  if (d < 0) return;
+  const unsigned long long slot = atomicAdd(&cursor[d], 1ull);
+  int *m = buf + slot * 3;
+  m[0] = (int)r; m[1] = link[r]; m[2] = (int)zmask[r];
+  rec_owned[r] = 0;
+}
+__global__ void k_merge_links(int64_t R, const unsigned char *__restrict__ rec_owned, const int *__restrict__ old_link,
+                              int *__restrict__ new_link) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < R && !rec_owned[r]) new_link[r] = old_link[r];
+}
+__global__ void k_unpack_ent(int64_t n, int A, const int *__restrict__ buf, const AttrDev *__restrict__ attrs,
+                             TreeDev tree, int *__restrict__ y, double *__restrict__ entN, int *__restrict__ blk,
+                             unsigned char *__restrict__ ent_owned) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int *m = buf + i * (A + 1);
+  const int64_t e = m[0];
+  double nn = 1.0;
+  for (int a = 0; a < A; ++a) {
+    const int v = m[1 + a];
+    y[e * A + a] = v;
+    if (!attrs[a].is_const) nn = nn * attrs[a].norm[v];
+  }
+  entN[e] = nn;
+  blk[e] = tree.n_nodes > 0 ? tree_leaf(tree, m + 1) : 0;
+  ent_owned[e] = 1;
+}
+__global__ void k_unpack_rec(int64_t n, const int *__restrict__ buf, int *__restrict__ link,
+                             unsigned *__restrict__ zmask, unsigned char *__restrict__ rec_owned) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int *m = buf + i * 3;
+  const int64_t r = m[0];
+  link[r] = m[1];
+  zmask[r] = (unsigned)m[2];
+  rec_owned[r] = 1;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host-side context
 // ---------------------------------------------------------------------------------------------------
 template <typename T>
@@ -493,6 +599,14 @@ struct dbl_ctx {
   DevBuf<double> entN, theta;
   std::vector<double> h_theta;
   std::vector<int64_t> file_sizes;
+
+  // ownership (multi-GPU sharding by block)
+  std::vector<int> owner_h;  // P entries; default: everything owned by this rank
+  DevBuf<int> owner, ent_dest, ent_key, link_key;
+  DevBuf<unsigned char> ent_owned, rec_owned;
+  DevBuf<unsigned long long> move_cnt;  // [2*world] counts then [2*world] cursors
+  std::vector<int64_t> h_move_ent, h_move_rec;
+  bool in_sweep = false;
 
   // layout
   DevBuf<int> iota, blk_sorted, ent_sorted, rec_key, rec_key_sorted, rec_sorted, ent_cnt, rec_cnt;
@@ -668,8 +782,11 @@ extern "C" const char *dbl_version(void) { return "dblink_b200 0.1 (sm_100a)"; }
 
 static int alloc_blocks(dbl_ctx *ctx) {
   const int P = ctx->P;
-  CUDA_TRY(ctx->ent_cnt.alloc(P));
-  CUDA_TRY(ctx->rec_cnt.alloc(P));
+  if ((int)ctx->owner_h.size() != P) ctx->owner_h.assign(P, ctx->rank);
+  CUDA_TRY(ctx->owner.alloc(P));
+  CUDA_TRY(cudaMemcpy(ctx->owner.p, ctx->owner_h.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
+  CUDA_TRY(ctx->ent_cnt.alloc(P + 1));
+  CUDA_TRY(ctx->rec_cnt.alloc(P + 1));
   CUDA_TRY(ctx->ent_ptr.alloc(P + 1));
   CUDA_TRY(ctx->tile_ptr.alloc(P + 1));
   CUDA_TRY(ctx->rec_ptr.alloc(P + 1));
@@ -692,6 +809,14 @@ static int alloc_state(dbl_ctx *ctx, int64_t R, int64_t E) {
   CUDA_TRY(ctx->y.alloc((size_t)E * A));
   CUDA_TRY(ctx->blk.alloc(E));
   CUDA_TRY(ctx->entN.alloc(E));
+  CUDA_TRY(ctx->ent_owned.alloc(E));
+  CUDA_TRY(ctx->rec_owned.alloc(R));
+  CUDA_TRY(cudaMemsetAsync(ctx->ent_owned.p, 1, E, ctx->stream));
+  CUDA_TRY(cudaMemsetAsync(ctx->rec_owned.p, 1, R, ctx->stream));
+  CUDA_TRY(ctx->ent_dest.alloc(E));
+  CUDA_TRY(ctx->ent_key.alloc(E));
+  CUDA_TRY(ctx->link_key.alloc(R));
+  CUDA_TRY(ctx->move_cnt.alloc(4 * (size_t)ctx->world));
   const int64_t M = std::max(R, E);
   CUDA_TRY(ctx->iota.alloc(M));
   k_iota<<<grid_for(M, 256), 256, 0, ctx->stream>>>(M, ctx->iota.p);
@@ -724,11 +849,12 @@ static int bits_for(int64_t n) {
 static int build_links_csr(dbl_ctx *ctx) {
   const int64_t R = ctx->R, E = ctx->E;
   size_t tb = ctx->cub_bytes;
-  CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, (const int *)ctx->link.p, ctx->link_sorted.p,
-                                           (const int *)ctx->iota.p, ctx->rec_by_ent.p, (int)R, 0, bits_for(E),
+  k_rec_link_keys<<<grid_for(R, 256), 256, 0, ctx->stream>>>(R, ctx->link.p, ctx->rec_owned.p, (int)E, ctx->link_key.p);
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, (const int *)ctx->link_key.p, ctx->link_sorted.p,
+                                           (const int *)ctx->iota.p, ctx->rec_by_ent.p, (int)R, 0, bits_for(E + 1),
                                            ctx->stream));
   CUDA_TRY(cudaMemsetAsync(ctx->ent_rec_cnt.p, 0, sizeof(int) * (E + 1), ctx->stream));
-  k_hist<<<grid_for(R, 256), 256, 0, ctx->stream>>>(R, ctx->link.p, ctx->ent_rec_cnt.p);
+  k_hist<<<grid_for(R, 256), 256, 0, ctx->stream>>>(R, ctx->link_key.p, ctx->ent_rec_cnt.p);
   tb = ctx->cub_bytes;
   CUDA_TRY(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tb, (const int *)ctx->ent_rec_cnt.p, ctx->ent_rec_ptr.p,
                                          (int)(E + 1), ctx->stream));
@@ -740,25 +866,27 @@ static int build_links_csr(dbl_ctx *ctx) {
 static int relayout(dbl_ctx *ctx) {
   const int64_t R = ctx->R, E = ctx->E;
   const int A = ctx->A, P = ctx->P;
-  const int pb = bits_for(P);
+  const int pb = bits_for(P + 1);
   size_t tb = ctx->cub_bytes;
-  CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, (const int *)ctx->blk.p, ctx->blk_sorted.p,
+  k_ent_block_keys<<<grid_for(E, 256), 256, 0, ctx->stream>>>(E, ctx->blk.p, ctx->ent_owned.p, P, ctx->ent_key.p);
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, (const int *)ctx->ent_key.p, ctx->blk_sorted.p,
                                            (const int *)ctx->iota.p, ctx->ent_sorted.p, (int)E, 0, pb, ctx->stream));
-  k_rec_block_keys<<<grid_for(R, 256), 256, 0, ctx->stream>>>(R, ctx->link.p, ctx->blk.p, ctx->rec_key.p);
+  k_rec_block_keys<<<grid_for(R, 256), 256, 0, ctx->stream>>>(R, ctx->link.p, ctx->blk.p, ctx->rec_owned.p, P,
+                                                              ctx->rec_key.p);
   tb = ctx->cub_bytes;
   CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, (const int *)ctx->rec_key.p, ctx->rec_key_sorted.p,
                                            (const int *)ctx->iota.p, ctx->rec_sorted.p, (int)R, 0, pb, ctx->stream));
-  CUDA_TRY(cudaMemsetAsync(ctx->ent_cnt.p, 0, sizeof(int) * P, ctx->stream));
-  CUDA_TRY(cudaMemsetAsync(ctx->rec_cnt.p, 0, sizeof(int) * P, ctx->stream));
-  k_hist<<<grid_for(E, 256), 256, 0, ctx->stream>>>(E, ctx->blk.p, ctx->ent_cnt.p);
+  CUDA_TRY(cudaMemsetAsync(ctx->ent_cnt.p, 0, sizeof(int) * (P + 1), ctx->stream));
+  CUDA_TRY(cudaMemsetAsync(ctx->rec_cnt.p, 0, sizeof(int) * (P + 1), ctx->stream));
+  k_hist<<<grid_for(E, 256), 256, 0, ctx->stream>>>(E, ctx->ent_key.p, ctx->ent_cnt.p);
   k_hist<<<grid_for(R, 256), 256, 0, ctx->stream>>>(R, ctx->rec_key.p, ctx->rec_cnt.p);
   k_block_scan<<<1, 32, 0, ctx->stream>>>(P, ctx->ent_cnt.p, ctx->rec_cnt.p, ctx->ent_ptr.p, ctx->tile_ptr.p,
                                           ctx->rec_ptr.p, ctx->cta_ptr.p, LINK_WARPS);
   CUDA_TRY(cudaMemsetAsync(ctx->tiles.p, 0, ctx->tiles.n * sizeof(int), ctx->stream));
   k_build_tiles<<<grid_for(E, 256), 256, 0, ctx->stream>>>(E, A, ctx->y.p, ctx->entN.p, ctx->blk_sorted.p,
                                                            ctx->ent_sorted.p, ctx->ent_ptr.p, ctx->tile_ptr.p,
-                                                           ctx->tiles.p, ctx->perm_dev.p);
-  ctx->launches += 10;
+                                                           ctx->tiles.p, ctx->perm_dev.p, P);
+  ctx->launches += 11;
   CUDA_TRY(cudaGetLastError());
   return DBL_OK;
 }
@@ -771,12 +899,13 @@ static int refresh_summary(dbl_ctx *ctx, bool draw_z, int sampler) {
   CUDA_TRY(cudaMemsetAsync(ctx->loglik.p, 0, sizeof(double), ctx->stream));
   k_entity_post<<<grid_for(ctx->E, 256), 256, 0, ctx->stream>>>(ctx->E, A, ctx->y.p, ctx->attrs.p, ctx->tree,
                                                                ctx->entN.p, ctx->blk.p, ctx->ent_rec_ptr.p,
-                                                               ctx->counts.p, ctx->iso_slot(), ctx->loglik.p);
+                                                               ctx->counts.p, ctx->iso_slot(), ctx->loglik.p, ctx->ent_owned.p);
   DistParams dp;
   dp.A = A; dp.F = F; dp.draw = draw_z ? 1 : 0; dp.seed = ctx->seed; dp.iter = (uint32_t)(ctx->iteration + 1);
   dp.R = ctx->R; dp.attrs = ctx->attrs.p; dp.x = ctx->x.p; dp.file = ctx->file.p; dp.link = ctx->link.p;
   dp.y = ctx->y.p; dp.zmask = ctx->zmask.p; dp.theta = ctx->theta.p; dp.counts = ctx->counts.p;
   dp.loglik = ctx->loglik.p;
+  dp.rec_owned = ctx->rec_owned.p;
   k_dist<<<grid_for(ctx->R, 256), 256, 0, ctx->stream>>>(dp);
   ctx->launches += 4;
   CUDA_TRY(cudaGetLastError());
@@ -990,55 +1119,70 @@ static int launch_link(dbl_ctx *ctx, int sampler, uint32_t it) {
   return DBL_OK;
 }
 
+// theta | summary -> links -> entity values -> N/blocks/distortions/summary of the shard owned by this rank
+static int sweep_local(dbl_ctx *ctx, int sampler) {
+  const int A = ctx->A, F = ctx->F;
+  const uint32_t it = (uint32_t)(ctx->iteration + 1);
+  // (1) theta | summary of the previous state (State.scala:83, GU:305-320) -- A*F scalars on the host
+  {
+    std::vector<int64_t> agg((size_t)A * F);
+    for (int i = 0; i < A * F; ++i) agg[i] = ctx->h_counts[i];
+    host_draw_theta(A, F, ctx->alpha.data(), ctx->beta.data(), ctx->seed, agg.data(), ctx->file_sizes.data(), it,
+                    ctx->h_theta.data());
+    CUDA_TRY(cudaMemcpyAsync(ctx->theta.p, ctx->h_theta.data(), sizeof(double) * A * F, cudaMemcpyHostToDevice,
+                             ctx->stream));
+  }
+  // (2) links
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  CUDA_TRY(cudaEventRecord(e0, ctx->stream));
+  {
+    int rc = launch_link(ctx, sampler, it);
+    if (rc) return rc;
+  }
+  CUDA_TRY(cudaEventRecord(e1, ctx->stream));
+  ctx->pending_events.emplace_back(e0, e1);
+  ctx->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  if (ctx->world > 1) {  // the link kernel only writes records of owned blocks: keep the others as they were
+    k_merge_links<<<grid_for(ctx->R, 256), 256, 0, ctx->stream>>>(ctx->R, ctx->rec_owned.p, ctx->link.p, ctx->newlink.p);
+    ctx->launches += 1;
+  }
+  std::swap(ctx->link.p, ctx->newlink.p);
+  // (3) entity values
+  int rc = build_links_csr(ctx);
+  if (rc) return rc;
+  ValParams vp;
+  vp.A = A; vp.F = F; vp.sampler = sampler; vp.seed = ctx->seed; vp.iter = it; vp.E = ctx->E;
+  vp.attrs = ctx->attrs.p; vp.x = ctx->x.p; vp.file = ctx->file.p; vp.zmask = ctx->zmask.p; vp.theta = ctx->theta.p;
+  vp.ent_rec_ptr = ctx->ent_rec_ptr.p; vp.rec_by_ent = ctx->rec_by_ent.p; vp.y = ctx->y.p;
+  vp.ent_owned = ctx->ent_owned.p;
+  k_values<<<grid_for(ctx->E * A, 128), 128, 0, ctx->stream>>>(vp);
+  ctx->launches += 1;
+  // (4) N(e), new block ids, distortions, summary
+  return refresh_summary(ctx, true, sampler);
+}
+
+// (5) re-partition + summary fetch (also the sync point that bounds the sweep)
+static int sweep_finish(dbl_ctx *ctx) {
+  int rc = relayout(ctx);
+  if (rc) return rc;
+  ctx->iteration += 1;
+  return fetch_summary(ctx);
+}
+
 extern "C" int dbl_sweep(dbl_ctx *ctx, int sampler, int32_t n_sweeps) {
   if (!ctx) return DBL_ERR_INVALID;
   if (sampler < 0 || sampler > 3 || n_sweeps < 0) { ctx->set_error("bad sampler / n_sweeps"); return DBL_ERR_INVALID; }
   if (!ctx->has_state) { ctx->set_error("dbl_sweep before dbl_state_init/upload"); return DBL_ERR_STATE; }
+  if (ctx->world > 1) { ctx->set_error("dbl_sweep on a sharded context: use dbl_sweep_begin/exchange/end"); return DBL_ERR_STATE; }
   CUDA_TRY(cudaSetDevice(ctx->device));
-  const int A = ctx->A, F = ctx->F;
   CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
   for (int s = 0; s < n_sweeps; ++s) {
-    const uint32_t it = (uint32_t)(ctx->iteration + 1);
-    // (1) theta | summary of the previous state (State.scala:83, GU:305-320) -- A*F scalars on the host
-    {
-      std::vector<int64_t> agg((size_t)A * F);
-      for (int i = 0; i < A * F; ++i) agg[i] = ctx->h_counts[i];
-      host_draw_theta(A, F, ctx->alpha.data(), ctx->beta.data(), ctx->seed, agg.data(), ctx->file_sizes.data(), it,
-                      ctx->h_theta.data());
-      CUDA_TRY(cudaMemcpyAsync(ctx->theta.p, ctx->h_theta.data(), sizeof(double) * A * F, cudaMemcpyHostToDevice,
-                               ctx->stream));
-    }
-    // (2) links
-    cudaEvent_t e0, e1;
-    CUDA_TRY(cudaEventCreate(&e0));
-    CUDA_TRY(cudaEventCreate(&e1));
-    CUDA_TRY(cudaEventRecord(e0, ctx->stream));
-    {
-      int rc = launch_link(ctx, sampler, it);
-      if (rc) return rc;
-    }
-    CUDA_TRY(cudaEventRecord(e1, ctx->stream));
-    ctx->pending_events.emplace_back(e0, e1);
-    ctx->launches += 1;
-    CUDA_TRY(cudaGetLastError());
-    std::swap(ctx->link.p, ctx->newlink.p);
-    // (3) entity values
-    int rc = build_links_csr(ctx);
+    int rc = sweep_local(ctx, sampler);
     if (rc) return rc;
-    ValParams vp;
-    vp.A = A; vp.F = F; vp.sampler = sampler; vp.seed = ctx->seed; vp.iter = it; vp.E = ctx->E;
-    vp.attrs = ctx->attrs.p; vp.x = ctx->x.p; vp.file = ctx->file.p; vp.zmask = ctx->zmask.p; vp.theta = ctx->theta.p;
-    vp.ent_rec_ptr = ctx->ent_rec_ptr.p; vp.rec_by_ent = ctx->rec_by_ent.p; vp.y = ctx->y.p;
-    k_values<<<grid_for(ctx->E * A, 128), 128, 0, ctx->stream>>>(vp);
-    ctx->launches += 1;
-    // (4) N(e), new block ids, distortions, summary
-    rc = refresh_summary(ctx, true, sampler);
-    if (rc) return rc;
-    // (5) re-partition
-    rc = relayout(ctx);
-    if (rc) return rc;
-    ctx->iteration += 1;
-    rc = fetch_summary(ctx);  // also the sync point that bounds the sweep
+    rc = sweep_finish(ctx);
     if (rc) return rc;
   }
   CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -1047,6 +1191,152 @@ extern "C" int dbl_sweep(dbl_ctx *ctx, int sampler, int32_t n_sweeps) {
   CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   ctx->last_sweep_ms = ms;
   drain_link_events(ctx);
+  return DBL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// multi-GPU entry points: blocks are sharded over ranks; one exchange of moved clusters per sweep
+// ---------------------------------------------------------------------------------------------------
+static int apply_ownership(dbl_ctx *ctx) {
+  k_mark_ent_owned<<<grid_for(ctx->E, 256), 256, 0, ctx->stream>>>(ctx->E, ctx->blk.p, ctx->owner.p, ctx->rank,
+                                                                  ctx->ent_owned.p);
+  k_mark_rec_owned<<<grid_for(ctx->R, 256), 256, 0, ctx->stream>>>(ctx->R, ctx->link.p, ctx->ent_owned.p,
+                                                                  ctx->rec_owned.p);
+  ctx->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  return DBL_OK;
+}
+
+extern "C" int dbl_set_block_owners(dbl_ctx *ctx, const int32_t *owner_of_block) {
+  if (!ctx || !owner_of_block) return DBL_ERR_INVALID;
+  if (!ctx->has_state) { ctx->set_error("set_block_owners needs a (replicated) state"); return DBL_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  for (int b = 0; b < ctx->P; ++b)
+    if (owner_of_block[b] < 0 || owner_of_block[b] >= ctx->world) { ctx->set_error("owner out of range"); return DBL_ERR_INVALID; }
+  ctx->owner_h.assign(owner_of_block, owner_of_block + ctx->P);
+  CUDA_TRY(cudaMemcpyAsync(ctx->owner.p, ctx->owner_h.data(), sizeof(int) * ctx->P, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = apply_ownership(ctx);
+  if (rc) return rc;
+  rc = build_links_csr(ctx);
+  if (rc) return rc;
+  rc = refresh_summary(ctx, false, 0);
+  if (rc) return rc;
+  rc = relayout(ctx);
+  if (rc) return rc;
+  return fetch_summary(ctx);
+}
+
+extern "C" int dbl_sweep_begin(dbl_ctx *ctx, int sampler, int64_t *ent_counts, int64_t *rec_counts) {
+  if (!ctx || !ent_counts || !rec_counts) return DBL_ERR_INVALID;
+  if (sampler < 0 || sampler > 3) { ctx->set_error("bad sampler"); return DBL_ERR_INVALID; }
+  if (!ctx->has_state) { ctx->set_error("no state"); return DBL_ERR_STATE; }
+  if (ctx->in_sweep) { ctx->set_error("dbl_sweep_begin twice"); return DBL_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+  int rc = sweep_local(ctx, sampler);
+  if (rc) return rc;
+  const int W = ctx->world;
+  CUDA_TRY(cudaMemsetAsync(ctx->move_cnt.p, 0, sizeof(unsigned long long) * 4 * W, ctx->stream));
+  k_move_count_ent<<<grid_for(ctx->E, 256), 256, 0, ctx->stream>>>(ctx->E, ctx->blk.p, ctx->owner.p, ctx->rank,
+                                                                  ctx->ent_owned.p, ctx->ent_dest.p, ctx->move_cnt.p);
+  k_move_count_rec<<<grid_for(ctx->R, 256), 256, 0, ctx->stream>>>(ctx->R, ctx->link.p, ctx->rec_owned.p,
+                                                                  ctx->ent_dest.p, ctx->move_cnt.p + W);
+  ctx->launches += 2;
+  std::vector<unsigned long long> h(2 * W);
+  CUDA_TRY(cudaMemcpyAsync(h.data(), ctx->move_cnt.p, sizeof(unsigned long long) * 2 * W, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->h_move_ent.assign(W, 0);
+  ctx->h_move_rec.assign(W, 0);
+  for (int d = 0; d < W; ++d) {
+    ent_counts[d] = ctx->h_move_ent[d] = (int64_t)h[d];
+    rec_counts[d] = ctx->h_move_rec[d] = (int64_t)h[W + d];
+  }
+  ctx->in_sweep = true;
+  return DBL_OK;
+}
+
+extern "C" int dbl_exchange_pack(dbl_ctx *ctx, void *ent_buf_dev, void *rec_buf_dev) {
+  if (!ctx) return DBL_ERR_INVALID;
+  if (!ctx->in_sweep) { ctx->set_error("dbl_exchange_pack outside a sweep"); return DBL_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const int W = ctx->world;
+  std::vector<unsigned long long> cur(2 * W);
+  unsigned long long oe = 0, orc = 0;
+  for (int d = 0; d < W; ++d) { cur[d] = oe; oe += ctx->h_move_ent[d]; cur[W + d] = orc; orc += ctx->h_move_rec[d]; }
+  CUDA_TRY(cudaMemcpyAsync(ctx->move_cnt.p + 2 * W, cur.data(), sizeof(unsigned long long) * 2 * W, cudaMemcpyHostToDevice,
+                           ctx->stream));
+  if (orc > 0) {
+    if (!rec_buf_dev) return DBL_ERR_INVALID;
+    k_move_pack_rec<<<grid_for(ctx->R, 256), 256, 0, ctx->stream>>>(ctx->R, ctx->link.p, ctx->zmask.p, ctx->ent_dest.p,
+                                                                   ctx->rec_owned.p, ctx->move_cnt.p + 3 * W,
+                                                                   (int *)rec_buf_dev);
+  }
+  if (oe > 0) {
+    if (!ent_buf_dev) return DBL_ERR_INVALID;
+    k_move_pack_ent<<<grid_for(ctx->E, 256), 256, 0, ctx->stream>>>(ctx->E, ctx->A, ctx->y.p, ctx->ent_dest.p,
+                                                                   ctx->ent_owned.p, ctx->move_cnt.p + 2 * W,
+                                                                   (int *)ent_buf_dev);
+  }
+  ctx->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // the host moves the buffers with NCCL on its own stream
+  return DBL_OK;
+}
+
+extern "C" int dbl_exchange_unpack(dbl_ctx *ctx, const void *ent_buf_dev, int64_t n_ent, const void *rec_buf_dev,
+                                   int64_t n_rec) {
+  if (!ctx || n_ent < 0 || n_rec < 0) return DBL_ERR_INVALID;
+  if (!ctx->in_sweep) { ctx->set_error("dbl_exchange_unpack outside a sweep"); return DBL_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (n_ent > 0)
+    k_unpack_ent<<<grid_for(n_ent, 256), 256, 0, ctx->stream>>>(n_ent, ctx->A, (const int *)ent_buf_dev, ctx->attrs.p,
+                                                                ctx->tree, ctx->y.p, ctx->entN.p, ctx->blk.p,
+                                                                ctx->ent_owned.p);
+  if (n_rec > 0)
+    k_unpack_rec<<<grid_for(n_rec, 256), 256, 0, ctx->stream>>>(n_rec, (const int *)rec_buf_dev, ctx->link.p,
+                                                                ctx->zmask.p, ctx->rec_owned.p);
+  ctx->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return DBL_OK;
+}
+
+extern "C" int dbl_sweep_end(dbl_ctx *ctx) {
+  if (!ctx) return DBL_ERR_INVALID;
+  if (!ctx->in_sweep) { ctx->set_error("dbl_sweep_end without dbl_sweep_begin"); return DBL_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  ctx->in_sweep = false;
+  int rc = sweep_finish(ctx);
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+  CUDA_TRY(cudaEventSynchronize(ctx->ev1));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  ctx->last_sweep_ms = ms;
+  drain_link_events(ctx);
+  return DBL_OK;
+}
+
+extern "C" int dbl_partial_summary(dbl_ctx *ctx, int64_t *counts, double *loglik) {
+  if (!ctx || !counts || !loglik) return DBL_ERR_INVALID;
+  for (int i = 0; i < ctx->n_counts(); ++i) counts[i] = ctx->h_counts[i];
+  *loglik = ctx->h_loglik_part;
+  return DBL_OK;
+}
+extern "C" int dbl_set_global_summary(dbl_ctx *ctx, const int64_t *counts, double loglik) {
+  if (!ctx || !counts) return DBL_ERR_INVALID;
+  for (int i = 0; i < ctx->n_counts(); ++i) ctx->h_counts[i] = counts[i];
+  ctx->h_loglik_part = loglik;
+  return DBL_OK;
+}
+extern "C" int32_t dbl_summary_words(const dbl_ctx *ctx) { return ctx ? ctx->n_counts() : 0; }
+extern "C" int dbl_owned_masks(dbl_ctx *ctx, uint8_t *ent_owned, uint8_t *rec_owned) {
+  if (!ctx) return DBL_ERR_INVALID;
+  if (!ctx->has_state) { ctx->set_error("no state"); return DBL_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (ent_owned) CUDA_TRY(cudaMemcpyAsync(ent_owned, ctx->ent_owned.p, ctx->E, cudaMemcpyDeviceToHost, ctx->stream));
+  if (rec_owned) CUDA_TRY(cudaMemcpyAsync(rec_owned, ctx->rec_owned.p, ctx->R, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return DBL_OK;
 }
 

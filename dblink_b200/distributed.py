@@ -1,0 +1,174 @@
+"""Multi-GPU Gibbs sweep: k-d-tree blocks sharded over ranks, one process per GPU (torch.distributed).
+
+Replaces, for the sweep, what Spark does in the reference:
+  - one task per partition (GibbsUpdates.scala:137)            -> blocks placed on ranks by LPT on R_b * E_b
+  - the shuffle `.partitionBy(partitioner)` (GU:144)           -> one all-to-all of the clusters whose new block is
+                                                                  owned by another rank (NCCL over NVLink; gloo in
+                                                                  the CPU tests of this host logic)
+  - accumulators (SummaryAccumulators.scala:54-63)             -> all-reduce of A*F + A + 3 int64 words + 1 double
+  - broadcast of theta (State.scala:84)                        -> nothing: every rank draws the same theta from the
+                                                                  same counter-based stream
+
+The compute engine is duck-typed (`begin/pack/unpack/end/...`), so the exchange logic below is exercised on CPU
+with the gloo backend by tests/test_distributed_cpu.py; on GPUs it drives dblink_b200.GibbsEngine.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .engine import GibbsEngine, KDTreePartitioner, SAMPLERS, _check, _p
+
+
+def lpt_assign(costs, world):
+    """Longest-processing-time placement of blocks on ranks (the reference ships the same heuristic in
+    partitioning/LPTScheduler.scala:57-76).  Deterministic: ties by block id, then lowest rank."""
+    costs = np.asarray(costs, dtype=np.float64)
+    order = sorted(range(len(costs)), key=lambda b: (-costs[b], b))
+    load = np.zeros(world)
+    owner = np.zeros(len(costs), np.int32)
+    for b in order:
+        r = int(np.argmin(load))
+        owner[b] = r
+        load[r] += costs[b]
+    return owner
+
+
+def exchange(dist, send_ent, ent_counts, send_rec, rec_counts, ent_words, device, torch):
+    """All-to-all of the packed messages.  send_* are int32 tensors concatenated by destination rank;
+    *_counts are per-destination MESSAGE counts.  Returns (recv_ent, n_ent_msgs, recv_rec, n_rec_msgs)."""
+    world = dist.get_world_size()
+    mine = torch.tensor(np.stack([ent_counts, rec_counts], axis=1).reshape(-1), dtype=torch.int64, device=device)
+    theirs = torch.empty_like(mine)
+    dist.all_to_all_single(theirs, mine)  # counts first
+    theirs_h = theirs.cpu().numpy().reshape(world, 2)
+    in_ent, in_rec = theirs_h[:, 0], theirs_h[:, 1]
+    recv_ent = torch.empty(int(in_ent.sum()) * ent_words, dtype=torch.int32, device=device)
+    recv_rec = torch.empty(int(in_rec.sum()) * 3, dtype=torch.int32, device=device)
+    dist.all_to_all_single(recv_ent, send_ent, output_split_sizes=[int(c) * ent_words for c in in_ent],
+                           input_split_sizes=[int(c) * ent_words for c in ent_counts])
+    dist.all_to_all_single(recv_rec, send_rec, output_split_sizes=[int(c) * 3 for c in in_rec],
+                           input_split_sizes=[int(c) * 3 for c in rec_counts])
+    return recv_ent, int(in_ent.sum()), recv_rec, int(in_rec.sum())
+
+
+def allreduce_summary(dist, counts, loglik, device, torch):
+    t = torch.tensor(counts, dtype=torch.int64, device=device)
+    dist.all_reduce(t)
+    ll = torch.tensor([loglik], dtype=torch.float64, device=device)
+    dist.all_reduce(ll)
+    return t.cpu().numpy(), float(ll[0])
+
+
+class ShardedGibbs:
+    """Same surface as GibbsEngine (init_state / sweep / summary / download_state), block-sharded over the ranks of
+    the default process group."""
+
+    def __init__(self, indexes, alpha, beta, seed=0, num_files=1, levels=0, split_attrs=()):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.levels, self.split_attrs = levels, list(split_attrs)
+        self.eng = GibbsEngine(indexes, alpha, beta, None, seed, num_files, rank=self.rank, world_size=self.world)
+        self.A, self.F = self.eng.A, self.eng.F
+        self.owner = None
+        self._ms = 0.0
+
+    # ---- state ---------------------------------------------------------------------------------------
+    def init_state(self, x, file_ids=None, population_size=0):
+        """Every rank builds the same replicated initial state (State.deterministic), fits the same k-d tree on it,
+        then keeps only the blocks LPT assigns to it."""
+        e = self.eng
+        e.init_state(x, file_ids, population_size)
+        part = KDTreePartitioner(self.levels, self.split_attrs).fit(e.download_state()["y"])
+        e.set_partitioner(part)
+        self.partitioner = part
+        link, blk = e.links()
+        P = e.num_partitions
+        ent = np.bincount(blk, minlength=P).astype(np.float64)
+        rec = np.bincount(blk[link], minlength=P).astype(np.float64)
+        self.set_owners(lpt_assign(ent * rec, self.world))
+
+    def set_owners(self, owner):
+        owner = np.ascontiguousarray(owner, dtype=np.int32)
+        self.owner = owner
+        _check(_lib.load().dbl_set_block_owners(self.eng._h, _p(owner, _lib.i32p)), "set_block_owners", self.eng._h)
+        self._sync_summary()
+
+    def _sync_summary(self):
+        L = _lib.load()
+        n = L.dbl_summary_words(self.eng._h)
+        counts = np.zeros(n, np.int64)
+        ll = C.c_double(0.0)
+        _check(L.dbl_partial_summary(self.eng._h, _p(counts, _lib.i64p), C.byref(ll)), "partial_summary", self.eng._h)
+        g, gll = allreduce_summary(self.dist, counts, ll.value, self.device, self.torch)
+        g = np.ascontiguousarray(g, dtype=np.int64)
+        _check(L.dbl_set_global_summary(self.eng._h, _p(g, _lib.i64p), gll), "set_global_summary", self.eng._h)
+
+    # ---- transition ----------------------------------------------------------------------------------
+    def sweep(self, sampler="PCG-I", n=1):
+        torch, dist, L, h = self.torch, self.dist, _lib.load(), self.eng._h
+        s = SAMPLERS[sampler] if isinstance(sampler, str) else int(sampler)
+        W, ew = self.world, self.A + 1
+        total_ms = 0.0
+        for _ in range(n):
+            ec = np.zeros(W, np.int64)
+            rc = np.zeros(W, np.int64)
+            _check(L.dbl_sweep_begin(h, s, _p(ec, _lib.i64p), _p(rc, _lib.i64p)), "sweep_begin", h)
+            send_ent = torch.empty(int(ec.sum()) * ew, dtype=torch.int32, device=self.device)
+            send_rec = torch.empty(int(rc.sum()) * 3, dtype=torch.int32, device=self.device)
+            _check(L.dbl_exchange_pack(h, send_ent.data_ptr() if send_ent.numel() else None,
+                                       send_rec.data_ptr() if send_rec.numel() else None), "exchange_pack", h)
+            recv_ent, ne, recv_rec, nr = exchange(dist, send_ent, ec, send_rec, rc, ew, self.device, torch)
+            torch.cuda.synchronize()
+            _check(L.dbl_exchange_unpack(h, recv_ent.data_ptr() if ne else None, ne,
+                                         recv_rec.data_ptr() if nr else None, nr), "exchange_unpack", h)
+            _check(L.dbl_sweep_end(h), "sweep_end", h)
+            total_ms += self.eng.last_sweep_ms()
+            self._sync_summary()
+            self.last_exchange = (int(ec.sum()), int(rc.sum()))
+        self._ms = total_ms
+
+    def last_sweep_ms(self):
+        return self._ms
+
+    # ---- read-out ------------------------------------------------------------------------------------
+    def summary(self):
+        return self.eng.summary()
+
+    def kernel_launches(self):
+        return self.eng.kernel_launches()
+
+    def link_kernel_ms(self):
+        return self.eng.link_kernel_ms()
+
+    @property
+    def iteration(self):
+        return self.eng.iteration
+
+    def owned_masks(self):
+        e = self.eng
+        em = np.zeros(e.num_entities, np.uint8)
+        rm = np.zeros(e.num_records, np.uint8)
+        _check(_lib.load().dbl_owned_masks(e._h, _p(em, _lib.u8p), _p(rm, _lib.u8p)), "owned_masks", e._h)
+        return em.astype(bool), rm.astype(bool)
+
+    def download_state(self):
+        """Gather the full state on every rank (each entity / record taken from the rank that owns it)."""
+        torch, dist = self.torch, self.dist
+        st = self.eng.download_state()
+        em, rm = self.owned_masks()
+        out = {"theta": st["theta"]}
+        for key, mask in (("y", em), ("block", em), ("link", rm), ("z", rm)):
+            a = st[key].astype(np.int64)
+            m = mask.reshape((-1,) + (1,) * (a.ndim - 1))
+            t = torch.tensor(np.where(m, a, 0), device=self.device)
+            dist.all_reduce(t)  # exactly one rank owns each row
+            out[key] = t.cpu().numpy().astype(st[key].dtype)
+        cnt = torch.tensor(em.astype(np.int64), device=self.device)
+        dist.all_reduce(cnt)
+        assert int(cnt.min()) == 1 and int(cnt.max()) == 1, "every entity must be owned by exactly one rank"
+        return out

@@ -142,6 +142,33 @@ typedef struct {
 int dbl_summary(dbl_ctx *, dbl_summary_head *head, int64_t *agg_dist /*A*F*/, int64_t *rec_dist /*A+1*/,
                 double *theta /*A*F*/);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Multi-GPU: one context per rank/GPU (dbl_model_desc.rank / world_size), blocks sharded over ranks.  Replaces
+ * the shuffle `.partitionBy(partitioner)` (GU:144), the broadcast of theta (State.scala:84) and the summary
+ * accumulators (SummaryAccumulators.scala:54-63).  Every rank initialises the same replicated state
+ * (dbl_state_init / dbl_set_partitioner), then dbl_set_block_owners marks which blocks it owns.  One sweep is
+ *   dbl_sweep_begin        theta | global summary, links, entity values, distortions of the owned shard; counts of
+ *                          entity / record messages for every destination rank
+ *   dbl_exchange_pack      messages into caller-provided DEVICE buffers, concatenated by destination rank:
+ *                          entity message = 1 + A int32 words [e, y_0..y_{A-1}], record message = 3 words
+ *                          [r, e, z bit mask]; the host moves them with one all-to-all (NCCL) each
+ *   dbl_exchange_unpack    apply what was received
+ *   dbl_sweep_end          re-partition the shard, partial summary
+ *   dbl_partial_summary -> all-reduce on the host -> dbl_set_global_summary (drives the next theta draw)
+ * Draws are keyed by global ids, so the chain is identical for any number of ranks.
+ * ------------------------------------------------------------------------------------------------- */
+int dbl_set_block_owners(dbl_ctx *, const int32_t *owner_of_block /* numPartitions entries in [0, world) */);
+int dbl_sweep_begin(dbl_ctx *, int sampler, int64_t *ent_msgs_per_dest /*world*/, int64_t *rec_msgs_per_dest /*world*/);
+int dbl_exchange_pack(dbl_ctx *, void *ent_buf_dev, void *rec_buf_dev);
+int dbl_exchange_unpack(dbl_ctx *, const void *ent_buf_dev, int64_t n_ent_msgs, const void *rec_buf_dev,
+                        int64_t n_rec_msgs);
+int dbl_sweep_end(dbl_ctx *);
+int32_t dbl_summary_words(const dbl_ctx *); /* A*F + (A+1) + 2 */
+int dbl_partial_summary(dbl_ctx *, int64_t *counts /*dbl_summary_words*/, double *loglik_without_prior);
+int dbl_set_global_summary(dbl_ctx *, const int64_t *counts, double loglik_without_prior);
+/* which entities / records this rank currently owns (host byte arrays of E and R entries) */
+int dbl_owned_masks(dbl_ctx *, uint8_t *ent_owned, uint8_t *rec_owned);
+
 /* count of kernels launched by this context since creation (bench.py's gpu_launches) */
 int64_t dbl_kernel_launches(const dbl_ctx *);
 /* Link-kernel selection: 0 = automatic (TMA-staged kernels when the model fits them), 1 = always the generic

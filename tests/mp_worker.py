@@ -1,0 +1,102 @@
+"""Worker launched by the multi-process tests: `python -m torch.distributed.run ... tests/mp_worker.py MODE`.
+
+MODE cpu : gloo, world_size 2 -- the host-side exchange logic of dblink_b200.distributed on CPU tensors.
+MODE gpu : nccl, one rank per GPU -- the sharded chain must equal the oracle chain bit for bit.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def cpu_mode():
+    import torch
+    import torch.distributed as dist
+
+    from dblink_b200.distributed import allreduce_summary, exchange, lpt_assign
+
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device("cpu")
+    A = 3
+    ew = A + 1
+    # rank r sends (r + d + 1) entity messages and 2*(r+d) record messages to rank d; payload encodes (src, dst, i)
+    ec = np.array([rank + d + 1 for d in range(world)], np.int64)
+    rc = np.array([2 * (rank + d) for d in range(world)], np.int64)
+    ent = [[rank * 1000 + d * 100 + i] + [rank, d, i] for d in range(world) for i in range(ec[d])]
+    rec = [[rank * 1000 + d * 100 + i, d, rank] for d in range(world) for i in range(rc[d])]
+    send_ent = torch.tensor(np.array(ent, np.int32).reshape(-1), dtype=torch.int32)
+    send_rec = torch.tensor(np.array(rec, np.int32).reshape(-1) if rec else np.zeros(0, np.int32), dtype=torch.int32)
+    recv_ent, ne, recv_rec, nr = exchange(dist, send_ent, ec, send_rec, rc, ew, dev, torch)
+    assert ne == sum(s + rank + 1 for s in range(world)) and nr == sum(2 * (s + rank) for s in range(world))
+    got = recv_ent.numpy().reshape(-1, ew)
+    exp = [[s * 1000 + rank * 100 + i, s, rank, i] for s in range(world) for i in range(s + rank + 1)]
+    assert got.tolist() == exp, (got.tolist(), exp)
+    gotr = recv_rec.numpy().reshape(-1, 3)
+    expr = [[s * 1000 + rank * 100 + i, rank, s] for s in range(world) for i in range(2 * (s + rank))]
+    assert gotr.tolist() == expr
+    counts, ll = allreduce_summary(dist, np.arange(5, dtype=np.int64) * (rank + 1), 1.5 * (rank + 1), dev, torch)
+    tot = sum(r + 1 for r in range(world))
+    assert counts.tolist() == (np.arange(5) * tot).tolist() and abs(ll - 1.5 * tot) < 1e-12
+    owner = lpt_assign([9, 1, 8, 2, 7, 3, 3, 3], world)
+    loads = np.bincount(owner, weights=[9, 1, 8, 2, 7, 3, 3, 3], minlength=world)
+    assert loads.max() - loads.min() <= 3 and set(owner.tolist()) == set(range(world))
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("cpu exchange ok")
+
+
+def gpu_mode():
+    import torch
+    import torch.distributed as dist
+
+    from helpers import oracle_setup, synth_problem
+    from oracle import oracle as O
+    from dblink_b200 import synth
+    from dblink_b200.distributed import ShardedGibbs
+
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    g = synth_problem(seed=5, R=1500, n_files=2)
+    import dblink_b200 as D
+
+    rc = D.RecordsCache.build(g["values"], g["files"], g["attributes"])
+    x, file = rc.transform_records(g["values"], g["files"])
+    alpha = [a.alpha for a in g["attributes"]]
+    beta = [a.beta for a in g["attributes"]]
+    for sampler in ("PCG-II", "PCG-I", "Gibbs"):
+        eng = ShardedGibbs(rc.indexes, alpha, beta, seed=99, num_files=len(rc.file_ids), levels=3, split_attrs=(2, 3))
+        eng.init_state(x, file)
+        m, st, tree, ox, ofile = oracle_setup(O, g, 99, 3, (2, 3))
+        moved = 0
+        for it in range(5):
+            eng.sweep(sampler, 1)
+            moved += eng.last_exchange[0]
+            st.sweep(O.SAMPLERS[sampler])
+            d = eng.download_state()
+            for k in ("theta", "link", "y", "z"):
+                assert np.array_equal(d[k], getattr(st, k)), (sampler, it, k, rank)
+            ps, os_ = eng.summary(), st.summary()
+            assert ps["num_isolates"] == os_["num_isolates"]
+            assert np.array_equal(ps["agg_dist"], os_["agg_dist"]) and np.array_equal(ps["rec_dist"], os_["rec_dist"])
+            assert abs(ps["log_likelihood"] - os_["log_likelihood"]) <= 1e-9 * abs(os_["log_likelihood"])
+        t = torch.tensor([moved], device="cuda")
+        dist.all_reduce(t)
+        if world > 1:
+            assert int(t[0]) > 0, "the test should move clusters between ranks"
+        eng.eng.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print(f"gpu sharded chain == oracle chain on {world} ranks")
+
+
+if __name__ == "__main__":
+    {"cpu": cpu_mode, "gpu": gpu_mode}[sys.argv[1]]()
