@@ -267,8 +267,9 @@ __global__ void __launch_bounds__(LINK_WARPS * 32) k_link_generic(LinkParams p) 
   }
   __syncwarp();
   const int n = p.ent_ptr[b + 1] - p.ent_ptr[b];
-  const int nsteps = (n + 31) >> 5;
-  const int spc = max(1, (nsteps + 31) >> 5);
+  const int ntiles = (n + TE - 1) / TE;
+  const int nsteps = ntiles * (TE / 32);                       // steps beyond the last candidate add zeros
+  const int spc = (TE / 32) * max(1, (ntiles + 31) >> 5);      // a chunk is a whole number of tiles
   const int nchunks = (nsteps + spc - 1) / spc;
   const size_t tw = tile_words(A);
   const int *tiles = p.tiles + (size_t)p.tile_ptr[b] * tw;
@@ -412,39 +413,40 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32) k_link_match(LinkParams
     nmm = __popc(__ballot_sync(FULL, mm));
     __syncwarp();
   }
-  const int nsteps = (n + 31) >> 5;
-  const int spc = max(1, (nsteps + 31) >> 5);
+  const int nsteps = ntiles * (TE / 32);
+  const int tpc = max(1, (ntiles + 31) >> 5);
+  const int spc = (TE / 32) * tpc;
   const int nchunks = (nsteps + spc - 1) / spc;
   const int *mma = s_mm_attr[warp];
   const int *mmx = s_mm_x[warp];
+  const int off0 = nmm ? mma[0] * TE : 0;
+  const int x0 = nmm ? mmx[0] : 0;
 
   double run = 0.0, Q = 0.0, acc = 0.0;
-  int mark = min(spc, nsteps), chunk = 0, gstep = 0;
+  int chunk = 0, tile_in_chunk = 0;
   for (int t = 0; t < ntiles; ++t) {
     const int s = t % LINK_STAGES;
     mbar_wait(&rg.full[s], (t / LINK_STAGES) & 1);
     if (active) {
       const int *tile = rg.tiles + (size_t)s * TW;
       const double *tileN = reinterpret_cast<const double *>(tile + A * TE);
+      const int valid = min(TE, n - t * TE);  // candidates in this tile (the last tile is zero padded)
 #pragma unroll
       for (int q = 0; q < TE / 32; ++q) {
         const int slot = q * 32 + lane;
-        bool ok = (t * TE + slot) < n;
-        for (int k = 0; k < nmm; ++k) {
-          ok = ok && (tile[mma[k] * TE + slot] == mmx[k]);
-          if (!__any_sync(FULL, ok)) break;
-        }
+        // the most selective must-match attribute decides almost every candidate: one load, one compare, one vote
+        bool ok = (slot < valid) && (nmm == 0 || tile[off0 + slot] == x0);
         if (__any_sync(FULL, ok)) {
+          for (int k = 1; k < nmm; ++k) ok = ok && (tile[mma[k] * TE + slot] == mmx[k]);
           if (ok) acc = acc + generic_weight(ra, A, false, tile + slot, tileN[slot]);
         }
-        ++gstep;
-        if (gstep == mark) {
-          run = run + butterfly_sum(acc);
-          if (lane == chunk) Q = run;
-          ++chunk;
-          acc = 0.0;
-          mark = min(mark + spc, nsteps);
-        }
+      }
+      if (++tile_in_chunk == tpc || t + 1 == ntiles) {
+        run = run + butterfly_sum(acc);
+        if (lane == chunk) Q = run;
+        ++chunk;
+        acc = 0.0;
+        tile_in_chunk = 0;
       }
     }
     __syncwarp();

@@ -13,9 +13,9 @@
 constexpr int PCG2_H = 32;                           // hash slots per (record, attribute)
 constexpr int PCG2_TAB_BYTES = PCG2_H * 4 + PCG2_H * 8;  // keys then values
 
-// w *= r when y == x, as ISETP + predicated DMUL (the compiler's select form costs twice the issue slots)
+// w *= r when y == x (ptxas turns any predicated form into DMUL + 2 FSEL; plain C avoids extra moves)
 __device__ __forceinline__ void mul_if_eq(double &w, int y, int x, double r) {
-  asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, %2;\n\t@p mul.rn.f64 %0, %0, %3;\n\t}" : "+d"(w) : "r"(y), "r"(x), "d"(r));
+  if (y == x) w = w * r;
 }
 
 template <int A, int NS>
@@ -133,13 +133,14 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32) k_link_pcg2(LinkParams 
     __syncwarp();
   }
 
-  const int nsteps = (n + 31) >> 5;
-  const int spc = max(1, (nsteps + 31) >> 5);
+  const int nsteps = ntiles * (TE / 32);          // steps beyond the last candidate add zeros
+  const int tpc = max(1, (ntiles + 31) >> 5);     // a chunk is a whole number of tiles
+  const int spc = (TE / 32) * tpc;
   const int nchunks = (nsteps + spc - 1) / spc;
 
   // ---- pass 1 over the TMA-staged tiles
   double run = 0.0, Q = 0.0, acc = 0.0;
-  int mark = min(spc, nsteps), chunk = 0, gstep = 0;
+  int chunk = 0, tile_in_chunk = 0;
   for (int t = 0; t < ntiles; ++t) {
     const int s = t % LINK_STAGES;
     mbar_wait(&rg.full[s], (t / LINK_STAGES) & 1);
@@ -153,14 +154,13 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32) k_link_pcg2(LinkParams 
 #pragma unroll
         for (int k = 0; k < A; ++k) y[k] = tile[k * TE + slot];
         acc = acc + pcg2_weight<A, NS, true>(rc, p, tab, y, tileN[slot]);
-        ++gstep;
-        if (gstep == mark) {
-          run = run + butterfly_sum(acc);
-          if (lane == chunk) Q = run;
-          ++chunk;
-          acc = 0.0;
-          mark = min(mark + spc, nsteps);
-        }
+      }
+      if (++tile_in_chunk == tpc || t + 1 == ntiles) {
+        run = run + butterfly_sum(acc);
+        if (lane == chunk) Q = run;
+        ++chunk;
+        acc = 0.0;
+        tile_in_chunk = 0;
       }
     }
     __syncwarp();

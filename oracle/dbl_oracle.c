@@ -726,7 +726,8 @@ void orc_draw_theta(const orc_model *m, const int64_t *agg_dist, const int64_t *
 /* Categorical draw protocol (replaces DiscreteDist(weights).sample(), GU:394,427,465, which    */
 /* builds an alias table per draw).  Candidates in canonical order, padded to a multiple of 32; */
 /* a "step" is 32 consecutive candidates (lane l owns candidate step*32+l); steps are grouped    */
-/* into at most 32 "chunks"; inside a chunk every lane sums its own candidates in step order,    */
+/* into at most 32 "chunks" of whole 128-candidate tiles; inside a chunk every lane sums its    */
+/* own candidates in step order,                                                                 */
 /* the chunk total is a 5-level xor-butterfly sum of the 32 lane sums, chunk totals accumulate   */
 /* sequentially and are check-pointed; u*total is located chunk -> lane (Kogge-Stone inclusive   */
 /* scan of the lane sums) -> step (sequential walk of that lane).                                */
@@ -752,10 +753,13 @@ static void load_step(const double *w, int64_t n, int64_t step, double out[32]) 
 /* status: 0 ok, 1 zero/non-finite total mass (reference throws, IndexNonUniformDiscreteDist.scala:71-79) */
 int orc_draw_index(const double *w, int64_t n, double u, int *status) {
   if (status) *status = 0;
-  int64_t nsteps = (n + 31) / 32;
-  if (nsteps == 0) { if (status) *status = 1; return -1; }
-  int64_t spc = (nsteps + 31) / 32; /* steps per chunk */
-  if (spc < 1) spc = 1;
+  /* candidates are laid out in tiles of 128 (= 4 steps); a chunk is a whole number of tiles */
+  int64_t ntiles = (n + 127) / 128;
+  if (ntiles == 0) { if (status) *status = 1; return -1; }
+  int64_t nsteps = 4 * ntiles;          /* steps beyond the last candidate only add zeros */
+  int64_t tpc = (ntiles + 31) / 32;     /* tiles per chunk */
+  if (tpc < 1) tpc = 1;
+  int64_t spc = 4 * tpc;                /* steps per chunk */
   int64_t nchunks = (nsteps + spc - 1) / spc;
   double Q[32];
   double run = 0.0;

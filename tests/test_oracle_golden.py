@@ -110,8 +110,9 @@ def test_draw_index_protocol(oracle):
 
     def enumeration_order(n):
         """chunk-major, then lane-major, then step: the order in which the protocol lays out the mass"""
-        nsteps = (n + 31) // 32
-        spc = max(1, (nsteps + 31) // 32)
+        ntiles = (n + 127) // 128
+        nsteps = 4 * ntiles
+        spc = 4 * max(1, (ntiles + 31) // 32)
         order = []
         for c0 in range(0, nsteps, spc):
             for lane in range(32):
