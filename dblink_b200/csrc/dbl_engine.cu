@@ -449,6 +449,28 @@ __global__ void k_init_records(int64_t E, int64_t R, int A, const int *__restric
   }
   zmask[r] = zm;
 }
+// range checks of an uploaded state (the reference would fail with ArrayIndexOutOfBounds / require):
+// bit 0 record value id, bit 1 file id, bit 2 link, bit 3 entity value id
+__global__ void k_validate(int64_t R, int64_t E, int A, int F, const AttrDev *__restrict__ attrs,
+                           const int *__restrict__ x, const int *__restrict__ file, const int *__restrict__ link,
+                           const int *__restrict__ y, int *__restrict__ flag) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int bad = 0;
+  if (i < R) {
+    for (int a = 0; a < A; ++a) {
+      const int v = x[i * A + a];
+      if (v < -1 || v >= attrs[a].V) bad |= 1;
+    }
+    if (file[i] < 0 || file[i] >= F) bad |= 2;
+    if (link && (link[i] < 0 || link[i] >= E)) bad |= 4;
+  }
+  if (y && i < E)
+    for (int a = 0; a < A; ++a) {
+      const int v = y[i * A + a];
+      if (v < 0 || v >= attrs[a].V) bad |= 8;
+    }
+  if (bad) atomicOr(flag, bad);
+}
 __global__ void k_pack_z(int64_t R, int A, const uint8_t *__restrict__ z, unsigned *__restrict__ zmask) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
@@ -595,6 +617,8 @@ struct dbl_ctx {
   int64_t R = 0, E = 0, iteration = 0;
   bool has_state = false;
   DevBuf<int> x, file, link, newlink, y, blk;
+  DevBuf<uint8_t> zbytes;  // staging for the byte-per-flag host format of z
+  DevBuf<int> vflag, file_cnt;
   DevBuf<unsigned> zmask;
   DevBuf<double> entN, theta;
   std::vector<double> h_theta;
@@ -800,7 +824,15 @@ static int alloc_blocks(dbl_ctx *ctx) {
 static int alloc_state(dbl_ctx *ctx, int64_t R, int64_t E) {
   const int A = ctx->A;
   if (R <= 0 || E <= 0 || R > 0x7fffffff || E > 0x7fffffff) { ctx->set_error("bad R/E"); return DBL_ERR_INVALID; }
+  if (ctx->R == R && ctx->E == E && ctx->x.p && ctx->tiles.p) {  // same shape as the previous state: reuse buffers
+    CUDA_TRY(cudaMemsetAsync(ctx->ent_owned.p, 1, E, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(ctx->rec_owned.p, 1, R, ctx->stream));
+    return DBL_OK;
+  }
   ctx->R = R; ctx->E = E;
+  CUDA_TRY(ctx->zbytes.alloc((size_t)R * A));
+  CUDA_TRY(ctx->vflag.alloc(1));
+  CUDA_TRY(ctx->file_cnt.alloc(ctx->F));
   CUDA_TRY(ctx->x.alloc((size_t)R * A));
   CUDA_TRY(ctx->file.alloc(R));
   CUDA_TRY(ctx->link.alloc(R));
@@ -930,16 +962,28 @@ static int fetch_summary(dbl_ctx *ctx) {
   return DBL_OK;
 }
 
-static int finish_new_state(dbl_ctx *ctx) {
-  // file sizes (RecordsCache.fileSizes)
-  std::vector<int> hf(ctx->R);
-  CUDA_TRY(cudaMemcpyAsync(hf.data(), ctx->file.p, sizeof(int) * ctx->R, cudaMemcpyDeviceToHost, ctx->stream));
+static int finish_new_state(dbl_ctx *ctx, bool check_state) {
+  // range checks on the device, then file sizes (RecordsCache.fileSizes)
+  CUDA_TRY(cudaMemsetAsync(ctx->vflag.p, 0, sizeof(int), ctx->stream));
+  k_validate<<<grid_for(std::max(ctx->R, ctx->E), 256), 256, 0, ctx->stream>>>(
+      ctx->R, ctx->E, ctx->A, ctx->F, ctx->attrs.p, ctx->x.p, ctx->file.p, check_state ? ctx->link.p : nullptr,
+      check_state ? ctx->y.p : nullptr, ctx->vflag.p);
+  int bad = 0;
+  CUDA_TRY(cudaMemcpyAsync(&bad, ctx->vflag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  ctx->file_sizes.assign(ctx->F, 0);
-  for (int64_t r = 0; r < ctx->R; ++r) {
-    if (hf[r] < 0 || hf[r] >= ctx->F) { ctx->set_error("file id out of range"); return DBL_ERR_INVALID; }
-    ctx->file_sizes[hf[r]]++;
+  if (bad) {
+    ctx->has_state = false;
+    ctx->set_error(bad & 1 ? "record value id out of range" : bad & 2 ? "file id out of range"
+                   : bad & 4 ? "link out of range" : "entity value id out of range");
+    return DBL_ERR_INVALID;
   }
+  CUDA_TRY(cudaMemsetAsync(ctx->file_cnt.p, 0, sizeof(int) * ctx->F, ctx->stream));
+  k_hist<<<grid_for(ctx->R, 256), 256, 0, ctx->stream>>>(ctx->R, ctx->file.p, ctx->file_cnt.p);
+  std::vector<int> hc(ctx->F);
+  CUDA_TRY(cudaMemcpyAsync(hc.data(), ctx->file_cnt.p, sizeof(int) * ctx->F, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->file_sizes.assign(hc.begin(), hc.end());
+  ctx->launches += 2;
   int rc = build_links_csr(ctx);
   if (rc) return rc;
   rc = refresh_summary(ctx, false, 0);
@@ -949,15 +993,6 @@ static int finish_new_state(dbl_ctx *ctx) {
   rc = fetch_summary(ctx);
   if (rc) return rc;
   ctx->has_state = true;
-  return DBL_OK;
-}
-
-static int check_ids(dbl_ctx *ctx, int64_t R, const int32_t *x) {
-  for (int64_t r = 0; r < R; ++r)
-    for (int a = 0; a < ctx->A; ++a) {
-      const int v = x[r * ctx->A + a];
-      if (v < -1 || v >= ctx->h_attrs[a].V) { ctx->set_error("record value id out of range"); return DBL_ERR_INVALID; }
-    }
   return DBL_OK;
 }
 
@@ -982,9 +1017,7 @@ extern "C" int dbl_state_init(dbl_ctx *ctx, int64_t R, const int32_t *x, const i
   if (!ctx || !x || !file) return DBL_ERR_INVALID;
   CUDA_TRY(cudaSetDevice(ctx->device));
   const int64_t E = pop > 0 ? pop : R;
-  int rc = check_ids(ctx, R, x);
-  if (rc) return rc;
-  rc = alloc_state(ctx, R, E);
+  int rc = alloc_state(ctx, R, E);
   if (rc) return rc;
   const int A = ctx->A;
   CUDA_TRY(cudaMemcpyAsync(ctx->x.p, x, sizeof(int) * R * A, cudaMemcpyHostToDevice, ctx->stream));
@@ -998,7 +1031,7 @@ extern "C" int dbl_state_init(dbl_ctx *ctx, int64_t R, const int32_t *x, const i
   CUDA_TRY(cudaMemcpyAsync(ctx->theta.p, ctx->h_theta.data(), sizeof(double) * A * ctx->F, cudaMemcpyHostToDevice,
                            ctx->stream));
   ctx->iteration = 0;
-  return finish_new_state(ctx);
+  return finish_new_state(ctx, false);
 }
 
 extern "C" int dbl_state_upload(dbl_ctx *ctx, int64_t R, int64_t E, const int32_t *x, const int32_t *file,
@@ -1006,21 +1039,10 @@ extern "C" int dbl_state_upload(dbl_ctx *ctx, int64_t R, int64_t E, const int32_
                                 int64_t iteration) {
   if (!ctx || !x || !file || !z || !link || !y || !theta) return DBL_ERR_INVALID;
   CUDA_TRY(cudaSetDevice(ctx->device));
-  int rc = check_ids(ctx, R, x);
-  if (rc) return rc;
-  for (int64_t r = 0; r < R; ++r)
-    if (link[r] < 0 || link[r] >= E) { ctx->set_error("link out of range"); return DBL_ERR_INVALID; }
-  for (int64_t e = 0; e < E; ++e)
-    for (int a = 0; a < ctx->A; ++a)
-      if (y[e * ctx->A + a] < 0 || y[e * ctx->A + a] >= ctx->h_attrs[a].V) {
-        ctx->set_error("entity value id out of range");
-        return DBL_ERR_INVALID;
-      }
-  rc = alloc_state(ctx, R, E);
+  int rc = alloc_state(ctx, R, E);
   if (rc) return rc;
   const int A = ctx->A;
-  DevBuf<uint8_t> zb;
-  CUDA_TRY(zb.alloc((size_t)R * A));
+  DevBuf<uint8_t> &zb = ctx->zbytes;
   CUDA_TRY(cudaMemcpyAsync(ctx->x.p, x, sizeof(int) * R * A, cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(cudaMemcpyAsync(ctx->file.p, file, sizeof(int) * R, cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(cudaMemcpyAsync(zb.p, z, (size_t)R * A, cudaMemcpyHostToDevice, ctx->stream));
@@ -1032,7 +1054,7 @@ extern "C" int dbl_state_upload(dbl_ctx *ctx, int64_t R, int64_t E, const int32_
   CUDA_TRY(cudaMemcpyAsync(ctx->theta.p, ctx->h_theta.data(), sizeof(double) * A * ctx->F, cudaMemcpyHostToDevice,
                            ctx->stream));
   ctx->iteration = iteration;
-  rc = finish_new_state(ctx);
+  rc = finish_new_state(ctx, true);
   return rc;
 }
 
@@ -1042,9 +1064,8 @@ extern "C" int dbl_state_download(dbl_ctx *ctx, uint8_t *z, int32_t *link, int32
   if (!ctx->has_state) { ctx->set_error("no state"); return DBL_ERR_STATE; }
   CUDA_TRY(cudaSetDevice(ctx->device));
   const int A = ctx->A;
-  DevBuf<uint8_t> zb;
+  DevBuf<uint8_t> &zb = ctx->zbytes;
   if (z) {
-    CUDA_TRY(zb.alloc((size_t)ctx->R * A));
     k_unpack_z<<<grid_for(ctx->R, 256), 256, 0, ctx->stream>>>(ctx->R, A, ctx->zmask.p, zb.p);
     ctx->launches += 1;
     CUDA_TRY(cudaMemcpyAsync(z, zb.p, (size_t)ctx->R * A, cudaMemcpyDeviceToHost, ctx->stream));

@@ -295,13 +295,17 @@ class GibbsEngine:
     def iteration(self):
         return _lib.load().dbl_iteration(self._h)
 
-    def download_state(self):
+    def download_state(self, out=None):
+        """Full state on the host (State.save, State.scala:122-150).  `out` may hold preallocated (e.g. pinned)
+        arrays under the keys z, link, y, theta, block; they are filled in place."""
         R, E, A = self.num_records, self.num_entities, self.A
-        z = np.zeros((R, A), np.uint8)
-        link = np.zeros(R, np.int32)
-        y = np.zeros((E, A), np.int32)
-        theta = np.zeros((A, self.F))
-        blk = np.zeros(E, np.int32)
+        out = out if out is not None else {}
+        z = out.get("z") if out.get("z") is not None else np.zeros((R, A), np.uint8)
+        link = out.get("link") if out.get("link") is not None else np.zeros(R, np.int32)
+        y = out.get("y") if out.get("y") is not None else np.zeros((E, A), np.int32)
+        theta = out.get("theta") if out.get("theta") is not None else np.zeros((A, self.F))
+        blk = out.get("block") if out.get("block") is not None else np.zeros(E, np.int32)
+        assert z.dtype == np.uint8 and link.dtype == np.int32 and y.dtype == np.int32 and blk.dtype == np.int32
         _check(_lib.load().dbl_state_download(self._h, _p(z, _lib.u8p), _p(link, _lib.i32p), _p(y, _lib.i32p),
                                               _p(theta, _lib.f64p), _p(blk, _lib.i32p)), "download_state", self._h)
         return {"z": z, "link": link, "y": y, "theta": theta, "block": blk}

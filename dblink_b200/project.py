@@ -1,0 +1,172 @@
+"""Project: a dblink configuration bound to its data (Project.scala:32-230, ProjectSteps.scala:53-84).
+
+Same HOCON surface as the reference (`dblink.data.*`, `dblink.partitioner`, `dblink.steps[*]`, ...); the sample
+step runs on the GPU engine, summarize / evaluate run on the host from linkage-chain.parquet.
+"""
+import os
+import shutil
+
+from . import analysis, config as hocon, sampler as chain, writers
+from .engine import GibbsEngine, KDTreePartitioner
+from .records import Attribute, RecordsCache, SimilarityFn, read_csv
+
+SUPPORTED_METRICS = ("pairwise", "cluster")  # ProjectStep.scala:36
+SUPPORTED_QUANTITIES = ("cluster-size-distribution", "partition-sizes", "shared-most-probable-clusters")  # :37
+
+
+class Project:
+    def __init__(self, cfg, base_dir="."):
+        g = cfg.get
+        self.cfg = cfg
+        self.data_path = os.path.join(base_dir, cfg.get_string("dblink.data.path"))
+        self.output_path = os.path.join(base_dir, cfg.get_string("dblink.outputPath"))
+        self.rec_id_attribute = cfg.get_string("dblink.data.recordIdentifier")
+        self.file_id_attribute = g("dblink.data.fileIdentifier", None)
+        self.ent_id_attribute = g("dblink.data.entityIdentifier", None)
+        self.null_value = cfg.get_string("dblink.data.nullValue")
+        self.random_seed = cfg.get_int("dblink.randomSeed")
+        self.population_size = g("dblink.populationSize", None)
+        self.expected_max_cluster_size = int(g("dblink.expectedMaxClusterSize", 10))
+        self.matching_attributes = []
+        for c in cfg.get_list("dblink.data.matchingAttributes"):  # Project.parseMatchingAttributes, :201-216
+            sf = c["similarityFunction"]
+            if sf["name"] == "ConstantSimilarityFn":
+                fn = SimilarityFn("ConstantSimilarityFn")
+            elif sf["name"] == "LevenshteinSimilarityFn":
+                fn = SimilarityFn("LevenshteinSimilarityFn", float(sf["parameters"]["threshold"]),
+                                  float(sf["parameters"]["maxSimilarity"]))
+            else:
+                raise hocon.ConfigError("similarityFunction.name: unsupported value")
+            self.matching_attributes.append(Attribute(c["name"], fn, float(c["distortionPrior"]["alpha"]),
+                                                      float(c["distortionPrior"]["beta"])))
+        p = cfg.get_config("dblink.partitioner")  # Project.parsePartitioner, :218-229
+        if p.get_string("name") != "KDTreePartitioner":
+            raise hocon.ConfigError("partitioner.name: unsupported value")
+        names = [a.name for a in self.matching_attributes]
+        self.num_levels = p.get_int("parameters.numLevels")
+        self.partition_attribute_ids = [names.index(n) for n in p.get_list("parameters.matchingAttributes")]
+        self._loaded = None
+
+    @classmethod
+    def from_file(cls, path):
+        base = os.getcwd()
+        return cls(hocon.parse_file(path), base)
+
+    # ---- data ------------------------------------------------------------------------------------
+    def load(self):
+        if self._loaded is None:
+            names = [a.name for a in self.matching_attributes]
+            rec_ids, files, values, ent_ids = read_csv(self.data_path, self.rec_id_attribute, names,
+                                                       self.file_id_attribute, self.ent_id_attribute, self.null_value)
+            cache = RecordsCache.build(values, files, self.matching_attributes, self.expected_max_cluster_size)
+            x, f = cache.transform_records(values, files)
+            self._loaded = {"rec_ids": rec_ids, "ent_ids": ent_ids, "cache": cache, "x": x, "file": f}
+        return self._loaded
+
+    def true_clusters(self):
+        d = self.load()
+        if d["ent_ids"] is None:
+            return None
+        return analysis.membership_to_clusters(d["rec_ids"], d["ent_ids"])
+
+    def generate_initial_state(self):
+        """Project.generateInitialState (:130-145) -> a GibbsEngine at iteration 0."""
+        d = self.load()
+        cache = d["cache"]
+        eng = GibbsEngine(cache.indexes, [a.alpha for a in self.matching_attributes],
+                          [a.beta for a in self.matching_attributes], None, self.random_seed, len(cache.file_ids))
+        eng.init_state(d["x"], d["file"], int(self.population_size or 0))
+        part = KDTreePartitioner(self.num_levels, self.partition_attribute_ids).fit(eng.download_state()["y"])
+        eng.set_partitioner(part)
+        eng._partitioner_keepalive = part
+        return eng
+
+    # ---- steps (ProjectSteps.parseSteps) -------------------------------------------------------------
+    def steps(self):
+        out = []
+        for st in self.cfg.get_list("dblink.steps"):
+            prm = st.get("parameters", {})
+            name = st["name"]
+            if name == "sample":
+                out.append(("sample", dict(sample_size=int(prm["sampleSize"]),
+                                           burnin_interval=int(prm.get("burninInterval", 0)),
+                                           thinning_interval=int(prm.get("thinningInterval", 1)),
+                                           resume=bool(prm.get("resume", True)), sampler=prm.get("sampler", "PCG-I"))))
+            elif name == "summarize":
+                q = list(prm["quantities"])
+                if not q or any(x not in SUPPORTED_QUANTITIES for x in q):
+                    raise ValueError(f"quantities must be one of {SUPPORTED_QUANTITIES}.")
+                out.append(("summarize", dict(lower_iteration_cutoff=int(prm.get("lowerIterationCutoff", 0)),
+                                              quantities=q)))
+            elif name == "evaluate":
+                m = list(prm["metrics"])
+                if not m or any(x not in SUPPORTED_METRICS for x in m):
+                    raise ValueError(f"metrics must be one of {SUPPORTED_METRICS}.")
+                out.append(("evaluate", dict(lower_iteration_cutoff=int(prm.get("lowerIterationCutoff", 0)), metrics=m,
+                                             use_existing_smpc=bool(prm.get("useExistingSMPC", False)))))
+            elif name == "copy-files":
+                out.append(("copy-files", dict(file_names=list(prm["fileNames"]),
+                                               destination_path=prm["destinationPath"],
+                                               overwrite=bool(prm.get("overwrite", False)),
+                                               delete_source=bool(prm.get("deleteSource", False)))))
+            else:
+                raise hocon.ConfigError("steps.name: unsupported step")
+        return out
+
+    def execute(self, log=print):
+        eng = None
+        results = {}
+        for name, prm in self.steps():
+            if name == "sample":
+                if eng is None or not prm["resume"]:
+                    eng = self.generate_initial_state()
+                d = self.load()
+                log(f"SampleStep: sampleSize={prm['sample_size']} burninInterval={prm['burnin_interval']} "
+                    f"thinningInterval={prm['thinning_interval']} sampler={prm['sampler']}")
+                chain.sample(eng, d["rec_ids"], [a.name for a in self.matching_attributes], prm["sample_size"],
+                             self.output_path, prm["burnin_interval"], prm["thinning_interval"], sampler=prm["sampler"])
+            elif name == "summarize":
+                ch = writers.read_linkage_chain(os.path.join(self.output_path, "linkage-chain.parquet"),
+                                                prm["lower_iteration_cutoff"])
+                for q in prm["quantities"]:
+                    if q == "cluster-size-distribution":
+                        writers.save_cluster_size_distribution(analysis.cluster_size_distribution(ch), self.output_path)
+                    elif q == "partition-sizes":
+                        writers.save_partition_sizes(analysis.partition_sizes(ch), self.output_path)
+                    else:
+                        self._save_smpc(analysis.shared_most_probable_clusters(ch))
+            elif name == "evaluate":
+                truth = self.true_clusters()
+                if truth is None:
+                    raise ValueError("Ground truth entity ids are required for evaluation")  # ProjectStep.scala:65
+                ch = writers.read_linkage_chain(os.path.join(self.output_path, "linkage-chain.parquet"),
+                                                prm["lower_iteration_cutoff"])
+                smpc = analysis.shared_most_probable_clusters(ch)
+                self._save_smpc(smpc)
+                text = []
+                for m in prm["metrics"]:
+                    if m == "pairwise":
+                        results["pairwise"] = analysis.pairwise_metrics(smpc, truth)
+                        text.append(analysis.format_pairwise(results["pairwise"]))
+                    else:
+                        results["cluster"] = analysis.adjusted_rand_index(smpc, truth)
+                        text.append(analysis.format_cluster(results["cluster"]))
+                with open(os.path.join(self.output_path, "evaluation-results.txt"), "w") as fh:
+                    fh.write("\n".join(text) + "\n")
+            elif name == "copy-files":
+                os.makedirs(prm["destination_path"], exist_ok=True)
+                for fn in prm["file_names"]:
+                    src = os.path.join(self.output_path, fn)
+                    if os.path.exists(src):
+                        dst = os.path.join(prm["destination_path"], os.path.basename(fn))
+                        if os.path.exists(dst) and not prm["overwrite"]:
+                            continue
+                        (shutil.copytree if os.path.isdir(src) else shutil.copy)(src, dst)
+                        if prm["delete_source"]:
+                            (shutil.rmtree if os.path.isdir(src) else os.remove)(src)
+        return results
+
+    def _save_smpc(self, clusters):
+        with open(os.path.join(self.output_path, "shared-most-probable-clusters.csv"), "w") as fh:
+            for c in clusters:
+                fh.write(", ".join(sorted(c)) + "\n")

@@ -118,8 +118,11 @@ class RecordsCache:
 
 def read_csv(path, rec_id_col, attribute_names, file_id_col=None, ent_id_col=None, null_value="NA"):
     """Project.scala:173-180 + State.scala:350-371: CSV with header -> record ids, file ids, string values."""
+    import gzip
+
     rec_ids, files, values, ent_ids = [], [], [], []
-    with open(path, newline="") as fh:
+    opener = (lambda: gzip.open(path, "rt", newline="")) if str(path).endswith(".gz") else (lambda: open(path, newline=""))
+    with opener() as fh:
         rd = csv.DictReader(fh)
         for row in rd:
             rec_ids.append(row[rec_id_col])

@@ -1,0 +1,196 @@
+"""CPU-only tests of the host layer around the sweep: HOCON surface, posterior summaries, output formats,
+project/step parsing.  No GPU compute."""
+import os
+
+import numpy as np
+import pytest
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+CONF = """
+dblink : {
+    // hyper-parameters (referenced below)
+    lowDistortion : {alpha : 0.5, beta : 50.0}
+    constSimFn : { name : "ConstantSimilarityFn", }
+    levSimFn : {
+        name : "LevenshteinSimilarityFn",
+        parameters : {
+            threshold : 7.0
+            maxSimilarity : 10.0
+        }
+    }
+    data : {
+        path : "%s"
+        recordIdentifier : "rec_id",
+        # fileIdentifier : null,
+        entityIdentifier : "ent_id" // optional
+        nullValue : "NA"
+        matchingAttributes : [
+            {name : "by", similarityFunction : ${dblink.constSimFn}, distortionPrior : ${dblink.lowDistortion}},
+            {name : "bm", similarityFunction : ${dblink.constSimFn}, distortionPrior : ${dblink.lowDistortion}},
+            {name : "bd", similarityFunction : ${dblink.constSimFn}, distortionPrior : ${dblink.lowDistortion}},
+            {name : "fname_c1", similarityFunction : ${dblink.levSimFn}, distortionPrior : ${dblink.lowDistortion}},
+            {name : "lname_c1", similarityFunction : ${dblink.levSimFn}, distortionPrior : ${dblink.lowDistortion}}
+        ]
+    }
+    randomSeed : 319158
+    expectedMaxClusterSize : 10
+    partitioner : {
+        name : "KDTreePartitioner",
+        parameters : {
+            numLevels : %d, // zero = no partitioning
+            matchingAttributes : %s
+        }
+    }
+    outputPath : "%s"
+    checkpointPath : "/tmp/spark_checkpoint/"
+    steps : [
+        {name : "sample", parameters : {
+            sampleSize : %d,
+            burninInterval : 0,
+            thinningInterval : %d,
+            resume : false,
+            sampler : "%s"
+        }},
+        {name : "summarize", parameters : {
+            lowerIterationCutoff : 0,
+            quantities : ["cluster-size-distribution", "partition-sizes"]
+        }},
+        {name : "evaluate", parameters : {
+            lowerIterationCutoff : %d,
+            metrics : ["pairwise", "cluster"],
+            useExistingSMPC : false
+        }}
+    ]
+}
+"""
+
+
+def make_conf(data, out, levels=0, attrs="[]", sample_size=100, thinning=10, sampler="PCG-I", cutoff=100):
+    return CONF % (data, levels, attrs, out, sample_size, thinning, sampler, cutoff)
+
+
+def test_hocon_subset():
+    from dblink_b200 import config
+
+    c = config.parse_string(make_conf("d.csv", "out/"))
+    assert c.get_string("dblink.data.path") == "d.csv"
+    assert c.get_int("dblink.randomSeed") == 319158
+    ma = c.get_list("dblink.data.matchingAttributes")
+    assert [a["name"] for a in ma] == ["by", "bm", "bd", "fname_c1", "lname_c1"]
+    assert ma[3]["similarityFunction"] == {"name": "LevenshteinSimilarityFn",
+                                           "parameters": {"threshold": 7.0, "maxSimilarity": 10.0}}
+    assert ma[0]["distortionPrior"] == {"alpha": 0.5, "beta": 50.0}
+    assert not c.has("dblink.data.fileIdentifier")      # commented out
+    assert c.get("dblink.populationSize", None) is None  # optional key (Project.scala:194)
+    assert c.get_list("dblink.steps")[0]["parameters"]["resume"] is False
+    # other HOCON features: '=' separator, object without separator, dotted keys, merge, optional substitution
+    d = config.parse_string('a { b = 1 }\na.c : "x"\nd = ${a.b}\ne = ${?nope}\nf = [1, 2,\n 3,]\n')
+    assert d.tree == {"a": {"b": 1, "c": "x"}, "d": 1, "e": None, "f": [1, 2, 3]}
+    with pytest.raises(config.ConfigError):
+        config.parse_string("a = ${missing}")
+    with pytest.raises(config.ConfigError):
+        config.parse_string("a { b : 1")
+    with pytest.raises(config.ConfigError):
+        c.get_string("dblink.nope")
+
+
+def test_project_parsing_and_data(tmp_path):
+    import dblink_b200 as D
+    from dblink_b200 import config
+    from dblink_b200.project import Project
+
+    data = os.path.join(GOLDEN, "RLdata500.csv.gz")
+    p = Project(config.parse_string(make_conf(data, str(tmp_path) + "/", 1, '["fname_c1"]')), base_dir="")
+    assert [a.name for a in p.matching_attributes] == ["by", "bm", "bd", "fname_c1", "lname_c1"]
+    assert [a.is_constant for a in p.matching_attributes] == [True, True, True, False, False]
+    assert p.num_levels == 1 and p.partition_attribute_ids == [3] and p.expected_max_cluster_size == 10
+    steps = p.steps()
+    assert [s[0] for s in steps] == ["sample", "summarize", "evaluate"]
+    assert steps[0][1] == dict(sample_size=100, burnin_interval=0, thinning_interval=10, resume=False, sampler="PCG-I")
+    d = p.load()
+    assert d["x"].shape == (500, 5) and (d["x"] >= 0).all()
+    assert [ix.num_values for ix in d["cache"].indexes] == [86, 12, 31, 146, 108]
+    assert [ix.nnz for ix in d["cache"].indexes][3:] == [236, 236]
+    truth = p.true_clusters()
+    assert len(truth) == 450 and sum(len(c) == 2 for c in truth) == 50
+    bad = make_conf(data, str(tmp_path) + "/").replace('"KDTreePartitioner"', '"SimplePartitioner"')
+    with pytest.raises(config.ConfigError):
+        Project(config.parse_string(bad), base_dir="")
+    bad = make_conf(data, str(tmp_path) + "/").replace('["pairwise", "cluster"]', '["accuracy"]')
+    with pytest.raises(ValueError):
+        Project(config.parse_string(bad), base_dir="").steps()
+
+
+def test_analysis_metrics():
+    from dblink_b200 import analysis as an
+
+    truth = [frozenset("ab"), frozenset("cd"), frozenset("e"), frozenset("fgh")]
+    pred = [frozenset("ab"), frozenset("c"), frozenset("de"), frozenset("fg"), frozenset("h")]
+    m = an.pairwise_metrics(pred, truth)
+    assert (m["TP"], m["FP"], m["FN"]) == (2, 1, 3)
+    assert m["precision"] == pytest.approx(2 / 3) and m["recall"] == pytest.approx(2 / 5)
+    assert m["f1score"] == pytest.approx(2 * (2 / 3) * (2 / 5) / (2 / 3 + 2 / 5))
+    assert an.adjusted_rand_index(truth, truth) == pytest.approx(1.0)
+    from sklearn.metrics import adjusted_rand_score
+
+    recs = sorted("abcdefgh")
+    lab = lambda cl: [next(i for i, c in enumerate(cl) if r in c) for r in recs]  # noqa: E731
+    assert an.adjusted_rand_index(pred, truth) == pytest.approx(adjusted_rand_score(lab(truth), lab(pred)))
+    chain = [(10, {0: [["a", "b"], ["c"]], 1: [["d", "e"]]}), (20, {0: [["a", "b"], ["c", "d"]], 1: [["e"]]}),
+             (30, {0: [["a", "b", "c"]], 1: [["d", "e"]]})]
+    mpc = an.most_probable_clusters(chain)
+    assert mpc["a"][0] == frozenset("ab") and mpc["a"][1] == pytest.approx(2 / 3)
+    assert mpc["d"][0] == frozenset("de")
+    assert set(an.shared_most_probable_clusters(chain)) == {frozenset("ab"), frozenset("c"), frozenset("de")}
+    assert an.cluster_size_distribution(chain)[30] == {3: 1, 2: 1}
+    assert an.partition_sizes(chain)[20] == {0: 2, 1: 1}
+
+
+def test_writers_roundtrip(tmp_path):
+    import pyarrow.parquet as pq
+
+    from dblink_b200 import analysis as an, writers as w
+
+    link = np.array([3, 0, 3, 2, 0, 4], np.int32)
+    blk = np.array([0, 1, 1, 0, 0], np.int32)  # entity 1 is isolated
+    ids = ["r%d" % i for i in range(6)]
+    parts = w.linkage_structure(link, blk, ids)
+    assert parts == {0: [["r1", "r4"], ["r0", "r2"], ["r5"]], 1: [["r3"]]}
+    path = os.path.join(tmp_path, "linkage-chain.parquet")
+    lw = w.LinkageChainWriter(path, write_buffer_size=2)
+    for it in (0, 10, 20):
+        lw.append(it, parts)
+    lw.close()
+    assert sorted(os.listdir(path)) == ["partitionId=0", "partitionId=1"]  # hive partitioning (BufferedRDDWriter:49)
+    t = pq.ParquetFile(os.path.join(path, "partitionId=0", sorted(os.listdir(os.path.join(path, "partitionId=0")))[0])).read()
+    assert t.schema.names == ["iteration", "linkageStructure"]
+    assert str(t.schema.field("iteration").type) == "int64"
+    assert str(t.schema.field("linkageStructure").type).startswith("list<") and "string" in str(t.schema.field("linkageStructure").type)
+    chain = w.read_linkage_chain(path, lower_iteration_cutoff=10)
+    assert [c[0] for c in chain] == [10, 20] and chain[0][1] == parts
+    dw = w.DiagnosticsWriter(os.path.join(tmp_path, "diagnostics.csv"), ["by", "fname_c1"])
+    dw.write_row({"iteration": 7, "num_isolates": 2, "log_likelihood": -123.456, "agg_dist": np.array([[1, 2], [3, 4]]),
+                  "rec_dist": np.array([5, 1, 0])}, 10)
+    dw.close()
+    lines = open(os.path.join(tmp_path, "diagnostics.csv")).read().splitlines()
+    assert lines[0] == ("iteration,systemTime-ms,numObservedEntities,logLikelihood,popSize,aggDist-by,aggDist-fname_c1,"
+                        "recDistortion-0,recDistortion-1,recDistortion-2")  # DiagnosticsWriter.scala:39-45
+    f = lines[1].split(",")
+    assert f[0] == "7" and f[2] == "8" and f[3] == "-1.234560000e+02" and f[4:] == ["10", "3", "7", "5", "1", "0"]
+    w.save_cluster_size_distribution(an.cluster_size_distribution(chain), str(tmp_path))
+    assert open(os.path.join(tmp_path, "cluster-size-distribution.csv")).read().splitlines()[0] == "iteration,0,1,2"
+    w.save_partition_sizes(an.partition_sizes(chain), str(tmp_path))
+    assert open(os.path.join(tmp_path, "partition-sizes.csv")).read().splitlines() == ["iteration,0,1", "10,3,1", "20,3,1"]
+
+
+def test_sampler_argument_checks():
+    from dblink_b200 import sampler
+
+    for kw in (dict(sample_size=0), dict(sample_size=1, burnin_interval=-1), dict(sample_size=1, thinning_interval=0),
+               dict(sample_size=1, sampler="Metropolis")):
+        args = dict(sample_size=1, burnin_interval=0, thinning_interval=1, sampler="PCG-I")
+        args.update(kw)
+        with pytest.raises(ValueError):
+            sampler.sample(None, [], [], args["sample_size"], "/tmp/x", args["burnin_interval"], args["thinning_interval"],
+                           sampler=args["sampler"])
