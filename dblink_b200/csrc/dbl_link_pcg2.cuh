@@ -34,18 +34,33 @@ __device__ __forceinline__ double pcg2_weight(const Pcg2Rec<A, NS> &rc, const Li
   double w = N;
 #pragma unroll
   for (int k = 0; k < A; ++k) mul_if_eq(w, y[k], rc.x[k], rc.rm[k]);
+  if (CONVERGED) {
+    // probe all NS tables first (no control flow), then ONE vote: the multiply by a similarity is rare
+    bool hit[NS > 0 ? NS : 1];
+    bool any = false;
 #pragma unroll
-  for (int q = 0; q < NS; ++q) {
-    const int yv = y[A - NS + q];
-    const unsigned slot = ((unsigned)yv * rc.hm[q]) >> 27;
-    const int key = reinterpret_cast<const int *>(tab + q * PCG2_TAB_BYTES)[slot];
-    const bool hit = (key == yv);
-    if (CONVERGED) {
-      if (__any_sync(FULL, hit)) {
-        if (hit) w = w * reinterpret_cast<const double *>(tab + q * PCG2_TAB_BYTES + PCG2_H * 4)[slot];
+    for (int q = 0; q < NS; ++q) {
+      const int yv = y[A - NS + q];
+      const unsigned slot = ((unsigned)yv * rc.hm[q]) >> 27;
+      hit[q] = (reinterpret_cast<const int *>(tab + q * PCG2_TAB_BYTES)[slot] == yv);
+      any = any || hit[q];
+    }
+    if (NS > 0 && __any_sync(FULL, any)) {
+#pragma unroll
+      for (int q = 0; q < NS; ++q) {
+        if (hit[q]) {
+          const unsigned slot = ((unsigned)y[A - NS + q] * rc.hm[q]) >> 27;
+          w = w * reinterpret_cast<const double *>(tab + q * PCG2_TAB_BYTES + PCG2_H * 4)[slot];
+        }
       }
-    } else {
-      if (hit) w = w * reinterpret_cast<const double *>(tab + q * PCG2_TAB_BYTES + PCG2_H * 4)[slot];
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < NS; ++q) {
+      const int yv = y[A - NS + q];
+      const unsigned slot = ((unsigned)yv * rc.hm[q]) >> 27;
+      if (reinterpret_cast<const int *>(tab + q * PCG2_TAB_BYTES)[slot] == yv)
+        w = w * reinterpret_cast<const double *>(tab + q * PCG2_TAB_BYTES + PCG2_H * 4)[slot];
     }
   }
   if (rc.mmask) {
@@ -57,7 +72,7 @@ __device__ __forceinline__ double pcg2_weight(const Pcg2Rec<A, NS> &rc, const Li
 }
 
 template <int A, int NS>
-__global__ void __launch_bounds__((LINK_WARPS + 1) * 32) k_link_pcg2(LinkParams p) {
+__global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int cta = blockIdx.x;
   if (cta >= p.cta_ptr[p.P]) return;
