@@ -142,20 +142,26 @@ __global__ void k_rec_link_keys(int64_t R, const int *__restrict__ link, const u
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r < R) key[r] = rec_owned[r] ? link[r] : E;
 }
+// offsets from sorted keys: ptr[k] = first position whose key is >= k, for k = 0..n_keys (keys beyond the data
+// point at n).  One pass over the sorted array; replaces an atomic histogram + scan.
+__global__ void k_segment_ptr(int64_t n, int n_keys, const int *__restrict__ sorted_key, int *__restrict__ ptr) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  const int cur = (i < n) ? min(sorted_key[i], n_keys) : n_keys;
+  const int prev = (i > 0) ? min(sorted_key[i - 1], n_keys) : -1;
+  for (int k = prev + 1; k <= cur; ++k) ptr[k] = (int)i;
+}
 // prefix sums over the P blocks (P is 2^numLevels: small) -- one CTA, Hillis-Steele over chunks
-__global__ void k_block_scan(int P, const int *__restrict__ ent_cnt, const int *__restrict__ rec_cnt,
-                             int *__restrict__ ent_ptr, int *__restrict__ tile_ptr, int *__restrict__ rec_ptr,
-                             int *__restrict__ cta_ptr, int warps_per_cta) {
+__global__ void k_block_scan(int P, const int *__restrict__ ent_ptr, const int *__restrict__ rec_ptr,
+                             int *__restrict__ tile_ptr, int *__restrict__ cta_ptr, int warps_per_cta) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    int e = 0, t = 0, r = 0, c = 0;
+    int t = 0, c = 0;
     for (int b = 0; b < P; ++b) {
-      ent_ptr[b] = e; tile_ptr[b] = t; rec_ptr[b] = r; cta_ptr[b] = c;
-      e += ent_cnt[b];
-      t += (ent_cnt[b] + TE - 1) / TE;
-      r += rec_cnt[b];
-      c += (rec_cnt[b] + warps_per_cta - 1) / warps_per_cta;
+      tile_ptr[b] = t; cta_ptr[b] = c;
+      t += (ent_ptr[b + 1] - ent_ptr[b] + TE - 1) / TE;
+      c += (rec_ptr[b + 1] - rec_ptr[b] + warps_per_cta - 1) / warps_per_cta;
     }
-    ent_ptr[P] = e; tile_ptr[P] = t; rec_ptr[P] = r; cta_ptr[P] = c;
+    tile_ptr[P] = t; cta_ptr[P] = c;
   }
 }
 // tiled, block-sorted copy of the entity table: tile = { int32 y[A][TE]; double N[TE] }
@@ -411,7 +417,10 @@ __global__ void k_dist(DistParams p) {
       }
     }
     if (p.draw) p.zmask[r] = zm;
-    atomicAdd((unsigned long long *)&p.counts[p.A * p.F + nd], 1ull);  // GU:265
+    // GU:265 -- warp-aggregated: one atomic per distinct count in the warp
+    const unsigned peers = __match_any_sync(__activemask(), nd);
+    if ((__ffs(peers) - 1) == (int)(threadIdx.x & 31))
+      atomicAdd((unsigned long long *)&p.counts[p.A * p.F + nd], (unsigned long long)__popc(peers));
   }
   typedef cub::BlockReduce<double, 256> BR;
   __shared__ typename BR::TempStorage tmp;
@@ -885,12 +894,8 @@ static int build_links_csr(dbl_ctx *ctx) {
   CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, (const int *)ctx->link_key.p, ctx->link_sorted.p,
                                            (const int *)ctx->iota.p, ctx->rec_by_ent.p, (int)R, 0, bits_for(E + 1),
                                            ctx->stream));
-  CUDA_TRY(cudaMemsetAsync(ctx->ent_rec_cnt.p, 0, sizeof(int) * (E + 1), ctx->stream));
-  k_hist<<<grid_for(R, 256), 256, 0, ctx->stream>>>(R, ctx->link_key.p, ctx->ent_rec_cnt.p);
-  tb = ctx->cub_bytes;
-  CUDA_TRY(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tb, (const int *)ctx->ent_rec_cnt.p, ctx->ent_rec_ptr.p,
-                                         (int)(E + 1), ctx->stream));
-  ctx->launches += 5;
+  k_segment_ptr<<<grid_for(R + 1, 256), 256, 0, ctx->stream>>>(R, (int)E, ctx->link_sorted.p, ctx->ent_rec_ptr.p);
+  ctx->launches += 3;
   return DBL_OK;
 }
 
@@ -908,12 +913,10 @@ static int relayout(dbl_ctx *ctx) {
   tb = ctx->cub_bytes;
   CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, (const int *)ctx->rec_key.p, ctx->rec_key_sorted.p,
                                            (const int *)ctx->iota.p, ctx->rec_sorted.p, (int)R, 0, pb, ctx->stream));
-  CUDA_TRY(cudaMemsetAsync(ctx->ent_cnt.p, 0, sizeof(int) * (P + 1), ctx->stream));
-  CUDA_TRY(cudaMemsetAsync(ctx->rec_cnt.p, 0, sizeof(int) * (P + 1), ctx->stream));
-  k_hist<<<grid_for(E, 256), 256, 0, ctx->stream>>>(E, ctx->ent_key.p, ctx->ent_cnt.p);
-  k_hist<<<grid_for(R, 256), 256, 0, ctx->stream>>>(R, ctx->rec_key.p, ctx->rec_cnt.p);
-  k_block_scan<<<1, 32, 0, ctx->stream>>>(P, ctx->ent_cnt.p, ctx->rec_cnt.p, ctx->ent_ptr.p, ctx->tile_ptr.p,
-                                          ctx->rec_ptr.p, ctx->cta_ptr.p, LINK_WARPS);
+  k_segment_ptr<<<grid_for(E + 1, 256), 256, 0, ctx->stream>>>(E, P, ctx->blk_sorted.p, ctx->ent_ptr.p);
+  k_segment_ptr<<<grid_for(R + 1, 256), 256, 0, ctx->stream>>>(R, P, ctx->rec_key_sorted.p, ctx->rec_ptr.p);
+  k_block_scan<<<1, 32, 0, ctx->stream>>>(P, ctx->ent_ptr.p, ctx->rec_ptr.p, ctx->tile_ptr.p, ctx->cta_ptr.p,
+                                          LINK_WARPS);
   CUDA_TRY(cudaMemsetAsync(ctx->tiles.p, 0, ctx->tiles.n * sizeof(int), ctx->stream));
   k_build_tiles<<<grid_for(E, 256), 256, 0, ctx->stream>>>(E, A, ctx->y.p, ctx->entN.p, ctx->blk_sorted.p,
                                                            ctx->ent_sorted.p, ctx->ent_ptr.p, ctx->tile_ptr.p,
