@@ -1,0 +1,80 @@
+"""BASELINE.json's full size (1M records / 10 attributes / 64 blocks) on the GPU, where the oracle is too slow:
+size-independent properties of a sweep -- state invariants, summary identities, determinism, and agreement of the
+two independent link-kernel implementations (TMA/hash kernels vs generic fallback), which share only the draw
+protocol."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def big():
+    import dblink_b200 as D
+    from dblink_b200 import synth
+
+    enc = synth.generate_encoded(2, 1_000_000, synth.config_attrs(4), dup=0.10, distortion=0.05, missing=0.01, n_files=2)
+    indexes, x, file, F = synth.build_encoded(enc)
+    alpha = [a.alpha for a in enc["attributes"]]
+    beta = [a.beta for a in enc["attributes"]]
+
+    def make():
+        eng = D.GibbsEngine(indexes, alpha, beta, None, 2024, F)
+        eng.init_state(x, file)
+        part = D.KDTreePartitioner(6, [4, 5, 6, 7, 8, 9]).fit(eng.download_state()["y"])
+        eng.set_partitioner(part)
+        eng._keep = part
+        return eng
+
+    return make, x, file
+
+
+def check_invariants(eng, x, prev_block_of_record=None):
+    d = eng.download_state()
+    s = eng.summary()
+    R, A = x.shape
+    y_of = d["y"][d["link"]]
+    # GU:262-263: a non-distorted observed attribute always agrees with the linked entity
+    assert not ((d["z"] == 0) & (x >= 0) & (x != y_of)).any()
+    # observed and different => distorted (GU:352-354)
+    assert (d["z"][(x >= 0) & (x != y_of)] == 1).all()
+    # summary identities (GU:219-301)
+    assert s["rec_dist"].sum() == R
+    assert (s["rec_dist"] * np.arange(A + 1)).sum() == s["agg_dist"].sum() == int(d["z"].sum())
+    assert s["num_isolates"] == eng.num_entities - len(np.unique(d["link"]))
+    assert np.isfinite(s["log_likelihood"])
+    assert ((s["theta"] > 0) & (s["theta"] < 1)).all()
+    assert d["block"].min() >= 0 and d["block"].max() < eng.num_partitions
+    return d, s
+
+
+@pytest.mark.parametrize("sampler", ["PCG-II", "PCG-I"])
+def test_full_size_properties(big, sampler):
+    make, x, file = big
+    a, b = make(), make()
+    b.set_link_mode(1)  # generic fallback kernel
+    check_invariants(a, x)
+    blk_before = a.download_state()["block"]
+    link_before = a.download_state()["link"]
+    for it in range(2):
+        a.sweep(sampler, 1)
+        b.sweep(sampler, 1)
+        da, sa = check_invariants(a, x)
+        db = b.download_state()
+        for k in ("link", "y", "z", "theta", "block"):
+            assert np.array_equal(da[k], db[k]), (sampler, it, k)  # two kernel implementations, identical draws
+        sb = b.summary()
+        assert np.array_equal(sa["agg_dist"], sb["agg_dist"]) and np.array_equal(sa["rec_dist"], sb["rec_dist"])
+        assert sa["log_likelihood"] == pytest.approx(sb["log_likelihood"], rel=1e-9)
+        if it == 0:
+            # a record can only link to an entity of the block it was in (GU:137, 192-198)
+            assert np.array_equal(blk_before[da["link"]], blk_before[link_before])
+    assert sa["pairs_scored"] == sb["pairs_scored"] > 3e10
+    # determinism: a fresh engine replays the same chain
+    c = make()
+    c.sweep(sampler, 2)
+    dc = c.download_state()
+    for k in ("link", "y", "z", "theta"):
+        assert np.array_equal(da[k], dc[k])
+    for e in (a, b, c):
+        e.close()
