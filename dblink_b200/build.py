@@ -39,7 +39,8 @@ def _deps():
 
 
 def units():
-    u = [("dbl_engine.o", "dbl_engine.cu", []), ("dbl_host.o", "dbl_host.cpp", [])]
+    u = [("dbl_engine.o", "dbl_engine.cu", []), ("dbl_host.o", "dbl_host.cpp", []),
+         ("dbl_index_gpu.o", "dbl_index_gpu.cu", [])]
     for a in range(1, MAX_A + 1):
         u.append((f"dbl_link_a{a}.o", "dbl_link_inst.cu", [f"-DDBL_INST_A={a}"]))
     return u

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
@@ -176,31 +177,53 @@ extern "C" int dbl_index_build(dbl_index **out, const char *const *values, const
   }
   ix->rowptr.assign(V + 1, 0);
   if (!ix->is_const) {
-    // all-pairs thresholded similarity (computeSimValueIndex, :219-231), rows in parallel
+    // all-pairs thresholded similarity (computeSimValueIndex, :219-231)
     std::vector<std::vector<std::pair<int32_t, double>>> rows(V);
     std::vector<int> len(V);
     for (int i = 0; i < V; ++i) len[i] = (int)ix->values[i].size();
-    std::atomic<int> next{0};
-    auto work = [&]() {
-      for (;;) {
-        const int i = next.fetch_add(16);
-        if (i >= V) break;
-        for (int r = i; r < std::min(V, i + 16); ++r) {
-          auto &row = rows[r];
-          for (int c = 0; c < V; ++c) {
-            const int d = host_levenshtein(ix->values[r].data(), len[r], ix->values[c].data(), len[c]);
-            const double e = std::exp(host_similarity_from_distance(d, len[r], len[c], threshold, max_sim));
-            if (e > 1.0) row.emplace_back(c, e);
+    bool done = false;
+    const char *env = std::getenv("DBL_INDEX_GPU");  // "0" = host only, "1" = GPU whenever possible
+    const bool want_gpu = env ? (env[0] == '1') : (V >= 2048);
+    if (want_gpu) {
+      // integer distances of the candidate pairs on the GPU, identical double arithmetic afterwards
+      std::vector<int> ci, cj, cd;
+      if (gpu_levenshtein_candidates(ix->values, threshold, max_sim, ci, cj, cd)) {
+        for (int r = 0; r < V; ++r) {  // the diagonal: distance 0
+          const double e = std::exp(host_similarity_from_distance(0, len[r], len[r], threshold, max_sim));
+          if (e > 1.0) rows[r].emplace_back(r, e);
+        }
+        for (size_t k = 0; k < ci.size(); ++k) {
+          const int i = ci[k], j = cj[k];
+          const double e = std::exp(host_similarity_from_distance(cd[k], len[i], len[j], threshold, max_sim));
+          if (e > 1.0) { rows[i].emplace_back(j, e); rows[j].emplace_back(i, e); }
+        }
+        for (int r = 0; r < V; ++r) std::sort(rows[r].begin(), rows[r].end());
+        done = true;
+      }
+    }
+    if (!done) {
+      std::atomic<int> next{0};
+      auto work = [&]() {
+        for (;;) {
+          const int i = next.fetch_add(16);
+          if (i >= V) break;
+          for (int r = i; r < std::min(V, i + 16); ++r) {
+            auto &row = rows[r];
+            for (int c = 0; c < V; ++c) {
+              const int d = host_levenshtein(ix->values[r].data(), len[r], ix->values[c].data(), len[c]);
+              const double e = std::exp(host_similarity_from_distance(d, len[r], len[c], threshold, max_sim));
+              if (e > 1.0) row.emplace_back(c, e);
+            }
           }
         }
-      }
-    };
-    unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    if (V < 512) nt = 1;
-    std::vector<std::thread> th;
-    for (unsigned t = 1; t < nt; ++t) th.emplace_back(work);
-    work();
-    for (auto &t : th) t.join();
+      };
+      unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+      if (V < 512) nt = 1;
+      std::vector<std::thread> th;
+      for (unsigned t = 1; t < nt; ++t) th.emplace_back(work);
+      work();
+      for (auto &t : th) t.join();
+    }
     for (int r = 0; r < V; ++r) ix->rowptr[r + 1] = ix->rowptr[r] + (int32_t)rows[r].size();
     ix->col.resize(ix->rowptr[V]);
     ix->expsim.resize(ix->rowptr[V]);

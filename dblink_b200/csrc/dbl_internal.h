@@ -88,4 +88,7 @@ struct dbl_kdtree {
 void host_draw_theta(int A, int F, const double *alpha, const double *beta, uint64_t seed, const int64_t *agg_dist,
                      const int64_t *file_sizes, uint32_t iter, double *theta_out);
 int host_levenshtein(const char *a, int la, const char *b, int lb);
+// GPU all-pairs candidate distances for the attribute index (dbl_index_gpu.cu); false = not applicable
+bool gpu_levenshtein_candidates(const std::vector<std::string> &values, double threshold, double max_sim,
+                                std::vector<int> &oi, std::vector<int> &oj, std::vector<int> &od);
 double host_similarity_from_distance(int dist, int la, int lb, double threshold, double max_sim);

@@ -161,3 +161,23 @@ def test_block_size_many_tiles(oracle):
         eng.sweep(sampler, 2)
         st.sweep(oracle.SAMPLERS[sampler], 2)
         assert_same_state(eng, st)
+
+
+def test_attribute_index_gpu_build_equals_host(monkeypatch):
+    """the all-pairs Levenshtein kernel (csrc/dbl_index_gpu.cu) and the host loop build identical tables"""
+    import dblink_b200 as D
+    from dblink_b200 import synth
+
+    rng = np.random.default_rng(3)
+    strings, _ = synth._string_vocab(rng, 1600)
+    strings += ["", "A", "AB", "BB", "John Smith", "Jane Smith"]
+    vw = {s: float(1 + (i * 7919) % 13) for i, s in enumerate(dict.fromkeys(strings))}
+    for thr in (7.0, 5.0, 0.0):
+        monkeypatch.setenv("DBL_INDEX_GPU", "0")
+        host = D.AttributeIndex.build(vw, "levenshtein", thr, 10.0).tables()
+        monkeypatch.setenv("DBL_INDEX_GPU", "1")
+        dev = D.AttributeIndex.build(vw, "levenshtein", thr, 10.0).tables()
+        for k in ("phi", "norm", "rowptr", "col", "expsim"):
+            np.testing.assert_array_equal(host[k], dev[k])
+        if thr == 0.0:
+            assert len(host["col"]) > 0.5 * len(vw) ** 2  # no truncation: nearly all pairs are "similar"
