@@ -168,12 +168,14 @@ __device__ __forceinline__ void prep_rec_attr(const LinkParams &p, int r, int k,
       if (at.is_const) {
         c.kind = 1;
         c.rmatch = 1.0 + (1.0 - th) / d;
+        c.rmatch = (c.rmatch - 1.0) + 1.0;  // see k_link_pcg2: the multiplier is rebuilt from (rmatch - 1)
       } else {
         d = d * at.norm[xv];
         double ediag = 1.0;
         row_find(at, xv, xv, ediag);
         c.kind = 2;
         c.rmatch = ediag + (1.0 - th) / d;
+        c.rmatch = (c.rmatch - 1.0) + 1.0;
         c.col = at.col + at.rowptr[xv];
         c.val = at.expsim + at.rowptr[xv];
         c.len = at.rowptr[xv + 1] - at.rowptr[xv];

@@ -127,6 +127,7 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkPara
         }
       }
     }
+    rmv = (rmv - 1.0) + 1.0;  // protocol: the multiplier is defined through (r - 1) (identity below ~2^53)
     rc.mmask = __ballot_sync(FULL, is_m);
 #pragma unroll
     for (int k = 0; k < A; ++k) {

@@ -873,12 +873,14 @@ static void prep_record(const orc_state *s, int64_t r, int sampler, rec_attr_t *
       if (xv < 0) { ra[a].kind = ix->is_const ? 0 : 3; continue; }
       double th = s->theta[a * F + f];
       double d = th * ix->phi[xv];
-      if (ix->is_const) { ra[a].kind = 1; ra[a].rmatch = 1.0 + (1.0 - th) / d; }
+      if (ix->is_const) { ra[a].kind = 1; ra[a].rmatch = 1.0 + (1.0 - th) / d; ra[a].rmatch = (ra[a].rmatch - 1.0) + 1.0; }
       else {
         d = d * ix->norm[xv];
         double ediag = 1.0;
         row_find(ix, xv, xv, &ediag);
         ra[a].kind = 2; ra[a].rmatch = ediag + (1.0 - th) / d;
+        /* the kernels keep (rmatch - 1) and rebuild rmatch as fl(that + 1): the identity below ~2^53 */
+        ra[a].rmatch = (ra[a].rmatch - 1.0) + 1.0;
       }
     } else {
       if (xv < 0) continue;
