@@ -153,15 +153,18 @@ __global__ void k_segment_ptr(int64_t n, int n_keys, const int *__restrict__ sor
 }
 // prefix sums over the P blocks (P is 2^numLevels: small) -- one CTA, Hillis-Steele over chunks
 __global__ void k_block_scan(int P, const int *__restrict__ ent_ptr, const int *__restrict__ rec_ptr,
-                             int *__restrict__ tile_ptr, int *__restrict__ cta_ptr, int warps_per_cta) {
+                             int *__restrict__ tile_ptr, int *__restrict__ cta_ptr, int warps_per_cta,
+                             int *__restrict__ cta_ptr2, int warps_per_cta2) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    int t = 0, c = 0;
+    int t = 0, c = 0, c2 = 0;
     for (int b = 0; b < P; ++b) {
-      tile_ptr[b] = t; cta_ptr[b] = c;
+      tile_ptr[b] = t; cta_ptr[b] = c; cta_ptr2[b] = c2;
       t += (ent_ptr[b + 1] - ent_ptr[b] + TE - 1) / TE;
-      c += (rec_ptr[b + 1] - rec_ptr[b] + warps_per_cta - 1) / warps_per_cta;
+      const int nr = rec_ptr[b + 1] - rec_ptr[b];
+      c += (nr + warps_per_cta - 1) / warps_per_cta;
+      c2 += (nr + warps_per_cta2 - 1) / warps_per_cta2;
     }
-    tile_ptr[P] = t; cta_ptr[P] = c;
+    tile_ptr[P] = t; cta_ptr[P] = c; cta_ptr2[P] = c2;
   }
 }
 // tiled, block-sorted copy of the entity table: tile = { int32 y[A][TE]; double N[TE] }
@@ -643,7 +646,7 @@ struct dbl_ctx {
 
   // layout
   DevBuf<int> iota, blk_sorted, ent_sorted, rec_key, rec_key_sorted, rec_sorted, ent_cnt, rec_cnt;
-  DevBuf<int> ent_ptr, tile_ptr, rec_ptr, cta_ptr, tiles;
+  DevBuf<int> ent_ptr, tile_ptr, rec_ptr, cta_ptr, cta_ptr2, tiles;
   DevBuf<int> link_sorted, rec_by_ent, ent_rec_cnt, ent_rec_ptr;
   DevBuf<unsigned char> cub_tmp;
   size_t cub_bytes = 0;
@@ -824,6 +827,7 @@ static int alloc_blocks(dbl_ctx *ctx) {
   CUDA_TRY(ctx->tile_ptr.alloc(P + 1));
   CUDA_TRY(ctx->rec_ptr.alloc(P + 1));
   CUDA_TRY(ctx->cta_ptr.alloc(P + 1));
+  CUDA_TRY(ctx->cta_ptr2.alloc(P + 1));
   const size_t max_tiles = (size_t)(ctx->E / TE) + (size_t)P + 1;
   CUDA_TRY(ctx->tiles.alloc(max_tiles * tile_words(ctx->A)));
   ctx->max_ctas = (int)((ctx->R + LINK_WARPS - 1) / LINK_WARPS) + P;
@@ -916,7 +920,7 @@ static int relayout(dbl_ctx *ctx) {
   k_segment_ptr<<<grid_for(E + 1, 256), 256, 0, ctx->stream>>>(E, P, ctx->blk_sorted.p, ctx->ent_ptr.p);
   k_segment_ptr<<<grid_for(R + 1, 256), 256, 0, ctx->stream>>>(R, P, ctx->rec_key_sorted.p, ctx->rec_ptr.p);
   k_block_scan<<<1, 32, 0, ctx->stream>>>(P, ctx->ent_ptr.p, ctx->rec_ptr.p, ctx->tile_ptr.p, ctx->cta_ptr.p,
-                                          LINK_WARPS);
+                                          LINK_WARPS, ctx->cta_ptr2.p, MATCH_WARPS);
   CUDA_TRY(cudaMemsetAsync(ctx->tiles.p, 0, ctx->tiles.n * sizeof(int), ctx->stream));
   k_build_tiles<<<grid_for(E, 256), 256, 0, ctx->stream>>>(E, A, ctx->y.p, ctx->entN.p, ctx->blk_sorted.p,
                                                            ctx->ent_sorted.p, ctx->ent_ptr.p, ctx->tile_ptr.p,
@@ -1130,13 +1134,15 @@ static int launch_link(dbl_ctx *ctx, int sampler, uint32_t it) {
     if (rc != 0) { ctx->set_error(std::string("k_link_pcg2 launch: ") + cudaGetErrorString((cudaError_t)rc)); return DBL_ERR_CUDA; }
     return DBL_OK;
   }
-  if (mode != 1 && sampler != DBL_PCG_II && ring <= 200 * 1024) {
-    static bool configured = false;
-    if (!configured) {
-      CUDA_TRY(cudaFuncSetAttribute(k_link_match, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      configured = true;
+  if (mode != 1 && sampler != DBL_PCG_II && ring <= 160 * 1024) {
+    static size_t configured = 0;
+    if (configured < ring) {
+      CUDA_TRY(cudaFuncSetAttribute(k_link_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring));
+      configured = ring;
     }
-    k_link_match<<<ctx->max_ctas, (LINK_WARPS + 1) * 32, ring, ctx->stream>>>(lp);
+    lp.cta_ptr = ctx->cta_ptr2.p;  // MATCH_WARPS records per CTA
+    const int grid = (int)((ctx->R + MATCH_WARPS - 1) / MATCH_WARPS) + ctx->P;
+    k_link_match<<<grid, (MATCH_WARPS + 1) * 32, ring, ctx->stream>>>(lp);
     return DBL_OK;
   }
   k_link_generic<<<ctx->max_ctas, LINK_WARPS * 32, 0, ctx->stream>>>(lp);

@@ -20,6 +20,7 @@
 
 constexpr int TE = 128;          // entities per tile of the block-sorted entity table
 constexpr int LINK_WARPS = 8;    // consumer warps (= records) per CTA
+constexpr int MATCH_WARPS = 16;  // ... of k_link_match, which is bound by L2 -> shared-memory tile traffic
 constexpr int LINK_STAGES = 4;   // tile ring depth
 constexpr int LINK_MAX_UNROLL_A = 16;
 constexpr unsigned FULL = 0xffffffffu;
@@ -316,14 +317,29 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned by
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// consumer-side wait (critical path): plain try_wait loop -- the hardware suspends the warp for a short,
+// implementation-defined time per attempt and wakes it promptly when the phase completes
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+// producer-side wait (off the critical path while the ring is full): long suspend-time hint so that the idle
+// producer lane does not steal issue slots from the consumer warps
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, unsigned parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok = 0;
   while (!ok) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(addr), "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware instead of spinning
+        : "r"(addr), "r"(parity), "r"(0x989680u)
         : "memory");
   }
 }
@@ -350,11 +366,17 @@ __device__ __forceinline__ void ring_init(const TileRing &rg, int consumers) {
   __syncthreads();
 }
 // producer: one lane streams ntiles tiles from global
+// RELAXED: the consumers are slow (PCG-II): let the producer sleep.  !RELAXED: the consumers drain tiles faster
+// than the producer can be woken (PCG-I): poll.
+template <bool RELAXED>
 __device__ __forceinline__ void ring_produce(const TileRing &rg, const int *gsrc, int ntiles) {
   const unsigned bytes = (unsigned)rg.tw * 4u;
   for (int t = 0; t < ntiles; ++t) {
     const int s = t % LINK_STAGES;
-    if (t >= LINK_STAGES) mbar_wait(&rg.empty[s], ((t / LINK_STAGES) - 1) & 1);
+    if (t >= LINK_STAGES) {
+      if (RELAXED) mbar_wait_relaxed(&rg.empty[s], ((t / LINK_STAGES) - 1) & 1);
+      else mbar_wait(&rg.empty[s], ((t / LINK_STAGES) - 1) & 1);
+    }
     mbar_arrive_expect_tx(&rg.full[s], bytes);
     tma_load_1d(rg.tiles + (size_t)s * rg.tw, gsrc + (size_t)t * rg.tw, bytes, &rg.full[s]);
   }
@@ -365,11 +387,11 @@ __device__ __forceinline__ void ring_produce(const TileRing &rg, const int *gsrc
 // observed, non-distorted attribute; the agreeing few are scored with the generic weight function.
 // ---------------------------------------------------------------------------------------------------
 #ifdef DBL_ENGINE_TU
-__global__ void __launch_bounds__((LINK_WARPS + 1) * 32) k_link_match(LinkParams p) {
+__global__ void __launch_bounds__((MATCH_WARPS + 1) * 32) k_link_match(LinkParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ RecAttr s_ra[LINK_WARPS][DBL_MAX_ATTRS];
-  __shared__ int s_mm_attr[LINK_WARPS][DBL_MAX_ATTRS];  // must-match attributes, most selective first
-  __shared__ int s_mm_x[LINK_WARPS][DBL_MAX_ATTRS];
+  __shared__ RecAttr s_ra[MATCH_WARPS][DBL_MAX_ATTRS];
+  __shared__ int s_mm_attr[MATCH_WARPS][DBL_MAX_ATTRS];  // must-match attributes, most selective first
+  __shared__ int s_mm_x[MATCH_WARPS][DBL_MAX_ATTRS];
   const int cta = blockIdx.x;
   if (cta >= p.cta_ptr[p.P]) return;
   const int b = find_block(p, cta);
@@ -384,12 +406,12 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32) k_link_match(LinkParams
   rg.empty = rg.full + LINK_STAGES;
   rg.tw = TW;
   const int *gtiles = p.tiles + (size_t)p.tile_ptr[b] * TW;
-  ring_init(rg, LINK_WARPS);
-  if (warp == LINK_WARPS) {
-    if (lane == 0) ring_produce(rg, gtiles, ntiles);
+  ring_init(rg, MATCH_WARPS);
+  if (warp == MATCH_WARPS) {
+    if (lane == 0) ring_produce<false>(rg, gtiles, ntiles);
     return;
   }
-  const int ridx = p.rec_ptr[b] + (cta - p.cta_ptr[b]) * LINK_WARPS + warp;
+  const int ridx = p.rec_ptr[b] + (cta - p.cta_ptr[b]) * MATCH_WARPS + warp;
   const bool active = ridx < p.rec_ptr[b + 1];
   const int r = active ? p.rec_sorted[ridx] : -1;
   RecAttr *ra = s_ra[warp];
@@ -439,7 +461,10 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32) k_link_match(LinkParams
         // the most selective must-match attribute decides almost every candidate: one load, one compare, one vote
         bool ok = (slot < valid) && (nmm == 0 || tile[off0 + slot] == x0);
         if (__any_sync(FULL, ok)) {
-          for (int k = 1; k < nmm; ++k) ok = ok && (tile[mma[k] * TE + slot] == mmx[k]);
+          for (int k = 1; k < nmm; ++k) {
+            ok = ok && (tile[mma[k] * TE + slot] == mmx[k]);
+            if (!__any_sync(FULL, ok)) break;  // warp-uniform: nobody left after this attribute
+          }
           if (ok) acc = acc + generic_weight(ra, A, false, tile + slot, tileN[slot]);
         }
       }

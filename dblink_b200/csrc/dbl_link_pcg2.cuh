@@ -93,7 +93,7 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkPara
   ring_init(rg, LINK_WARPS);
 
   if (warp == LINK_WARPS) {  // producer warp
-    if (lane == 0) ring_produce(rg, gtiles, ntiles);
+    if (lane == 0) ring_produce<true>(rg, gtiles, ntiles);
     return;
   }
   const int ridx = p.rec_ptr[b] + (cta - p.cta_ptr[b]) * LINK_WARPS + warp;
