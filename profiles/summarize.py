@@ -45,11 +45,21 @@ def kernel(rep, out_md, pairs=None):
     for k in KEYS:
         if k in m:
             lines.append(f"| {k} | {m[k][0]} | {m[k][1]} |")
-    stalls = [(h, float(m[h][0])) for h in hdr if "warp_issue_stalled" in h and h.endswith("per_warp_active.pct")]
+    stalls = []
+    for h in hdr:
+        if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio"):
+            try:
+                stalls.append((h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")], float(m[h][0])))
+            except ValueError:
+                pass
     stalls.sort(key=lambda t: -t[1])
-    lines += ["", "top stall reasons (% of warp-active cycles):", ""]
+    lines += ["", "warps stalled per issue-active cycle, by reason (smsp__average_warps_issue_stalled_*):", ""]
     for h, v in stalls[:8]:
-        lines.append(f"* {h.split('stalled_')[1].replace('_per_warp_active.pct', '')}: {v:.1f}")
+        lines.append(f"* {h}: {v:.2f}")
+    for k in ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+              "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"):
+        if k in m:
+            lines.append(f"* {k}: {m[k][0]} %")
     dram = to_bytes(*m["dram__bytes_read.sum"]) + to_bytes(*m["dram__bytes_write.sum"])
     dur_ms = float(m["gpu__time_duration.sum"][0]) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}[m["gpu__time_duration.sum"][1]]
     inst = float(m["smsp__inst_executed.sum"][0])
@@ -64,14 +74,19 @@ def kernel(rep, out_md, pairs=None):
     ci = {h: i for i, h in enumerate(sh)}
     body = [r for r in src[2:] if len(r) > 10]
     if body and "Instructions Executed" in ci:
-        mx = max(int(r[ci["Instructions Executed"]]) for r in body)
-        hot = [r for r in body if int(r[ci["Instructions Executed"]]) > 0.5 * mx]
+        counts = sorted(int(r[ci["Instructions Executed"]]) for r in body)
+        # the main loop = the most populated band of equal execution counts (the mbarrier spin loop has higher
+        # counts but only a handful of instructions)
+        import statistics
+        big = [c for c in counts if c > 0.02 * counts[-1]]
+        mode = statistics.median(big) if big else counts[-1]
+        hot = [r for r in body if 0.7 * mode <= int(r[ci["Instructions Executed"]]) <= 1.4 * mode]
         op = collections.Counter()
         for r in hot:
             t = r[ci["Source"]].split()
             o = (t[1] if t[0].startswith("@") else t[0]).rstrip(";").split(".")[0]
             op[o] += 1
-        lines += ["", f"hot loop ({len(hot)} SASS instructions executed > 50% of the maximum count), opcode mix:", "",
+        lines += ["", f"main loop ({len(hot)} SASS instructions with the modal execution count), opcode mix:", "",
                   ", ".join(f"{k} {v}" for k, v in op.most_common(16))]
         sass = " ".join(r[ci["Source"]] for r in body)
         lines += ["", "Blackwell/Hopper async-copy evidence in SASS: " +
