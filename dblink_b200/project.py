@@ -6,7 +6,7 @@ step runs on the GPU engine, summarize / evaluate run on the host from linkage-c
 import os
 import shutil
 
-from . import analysis, config as hocon, sampler as chain, writers
+from . import analysis, config as hocon, sampler as chain, state_io, writers
 from .engine import GibbsEngine, KDTreePartitioner
 from .records import Attribute, RecordsCache, SimilarityFn, read_csv
 
@@ -69,17 +69,42 @@ class Project:
             return None
         return analysis.membership_to_clusters(d["rec_ids"], d["ent_ids"])
 
+    def _new_engine(self):
+        d = self.load()
+        cache = d["cache"]
+        return GibbsEngine(cache.indexes, [a.alpha for a in self.matching_attributes],
+                           [a.beta for a in self.matching_attributes], None, self.random_seed, len(cache.file_ids))
+
+    def fingerprint(self):
+        d = self.load()
+        return state_io.model_fingerprint(d["cache"].indexes, d["x"], d["file"],
+                                          [a.alpha for a in self.matching_attributes],
+                                          [a.beta for a in self.matching_attributes])
+
     def generate_initial_state(self):
         """Project.generateInitialState (:130-145) -> a GibbsEngine at iteration 0."""
         d = self.load()
-        cache = d["cache"]
-        eng = GibbsEngine(cache.indexes, [a.alpha for a in self.matching_attributes],
-                          [a.beta for a in self.matching_attributes], None, self.random_seed, len(cache.file_ids))
+        eng = self._new_engine()
         eng.init_state(d["x"], d["file"], int(self.population_size or 0))
         part = KDTreePartitioner(self.num_levels, self.partition_attribute_ids).fit(eng.download_state()["y"])
         eng.set_partitioner(part)
         eng._partitioner_keepalive = part
         return eng
+
+    def saved_state(self):
+        """Project.savedState (:113-128): the engine restored from `state.npz` under outputPath, or None.  The
+        partition function is re-fitted on the deterministic initial entity values, exactly as the original run
+        fitted it, so the resumed chain continues as if it had never stopped."""
+        if not state_io.saved_state_exists(self.output_path):
+            return None
+        st = state_io.load_state(self.output_path, self.fingerprint())
+        d = self.load()
+        eng = self.generate_initial_state()
+        eng.upload_state(d["x"], d["file"], st["z"], st["link"], st["y"], st["theta"], st["iteration"])
+        return eng
+
+    def save_state(self, eng):
+        state_io.save_state(eng, self.output_path, self.fingerprint(), self.random_seed)
 
     # ---- steps (ProjectSteps.parseSteps) -------------------------------------------------------------
     def steps(self):
@@ -118,13 +143,16 @@ class Project:
         results = {}
         for name, prm in self.steps():
             if name == "sample":
-                if eng is None or not prm["resume"]:
+                if prm["resume"]:  # ProjectStep.scala:47-52
+                    eng = eng or self.saved_state() or self.generate_initial_state()
+                else:
                     eng = self.generate_initial_state()
                 d = self.load()
                 log(f"SampleStep: sampleSize={prm['sample_size']} burninInterval={prm['burnin_interval']} "
                     f"thinningInterval={prm['thinning_interval']} sampler={prm['sampler']}")
                 chain.sample(eng, d["rec_ids"], [a.name for a in self.matching_attributes], prm["sample_size"],
                              self.output_path, prm["burnin_interval"], prm["thinning_interval"], sampler=prm["sampler"])
+                self.save_state(eng)  # Sampler.scala:120
             elif name == "summarize":
                 ch = writers.read_linkage_chain(os.path.join(self.output_path, "linkage-chain.parquet"),
                                                 prm["lower_iteration_cutoff"])

@@ -95,3 +95,32 @@ def test_rldata10000_four_blocks(oracle, sampler, tmp_path):
     assert pw["TP"] >= 100 and pw["precision"] > 0.25, pw
     sizes = np.bincount(np.bincount(link, minlength=eng.num_entities))
     assert sizes[1] > 6000, sizes  # most records are singletons (8000 of 10000 in the ground truth)
+
+
+def test_save_and_resume_continues_the_same_chain(tmp_path):
+    """State.save / State.read (State.scala:122-193): a chain stopped and resumed equals the uninterrupted chain,
+    and the writers append (Sampler.scala:71,79-81)."""
+    from dblink_b200 import config, state_io
+    from dblink_b200.project import Project
+
+    data = os.path.join(GOLDEN, "RLdata500.csv.gz")
+    outa, outb = str(tmp_path) + "/a/", str(tmp_path) + "/b/"
+    def mk(out, n, resume):
+        conf = make_conf(data, out, 0, "[]", sample_size=n, thinning=5, cutoff=0)
+        return Project(config.parse_string(conf.replace("resume : false", "resume : %s" % resume)), base_dir="")
+
+    pa = mk(outa, 8, "false")
+    pa.execute(log=lambda *a: None)      # 40 sweeps in one go
+    pb = mk(outb, 4, "true")
+    pb.execute(log=lambda *a: None)      # 20 sweeps ...
+    assert state_io.saved_state_exists(outb)
+    pb2 = mk(outb, 4, "true")
+    pb2.execute(log=lambda *a: None)     # ... resumed for 20 more
+    sa, sb = state_io.load_state(outa), state_io.load_state(outb)
+    assert sa["iteration"] == sb["iteration"] == 40
+    for k in ("theta", "z", "link", "y"):
+        assert np.array_equal(sa[k], sb[k]), k
+    da = open(outa + "diagnostics.csv").read().splitlines()
+    db = open(outb + "diagnostics.csv").read().splitlines()
+    strip = lambda rows: [",".join(r.split(",")[:1] + r.split(",")[2:]) for r in rows]  # noqa: E731  (drop systemTime)
+    assert strip(da) == strip(db)

@@ -194,3 +194,20 @@ def test_sampler_argument_checks():
         with pytest.raises(ValueError):
             sampler.sample(None, [], [], args["sample_size"], "/tmp/x", args["burnin_interval"], args["thinning_interval"],
                            sampler=args["sampler"])
+
+
+def test_bench_reference_arm_runs():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) prints one JSON line"""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for sampler in ("PCG-II", "PCG-I"):
+        res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--records", "20000",
+                              "--steps", "1", "--warmup", "0", "--cpu-sample", "500", "--sampler", sampler],
+                             capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, res.stderr[-2000:]
+        line = json.loads(res.stdout.strip().splitlines()[-1])
+        assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "iterations/s"
+        assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
