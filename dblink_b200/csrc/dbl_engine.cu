@@ -25,6 +25,7 @@
 #include "dbl_internal.h"
 #define DBL_ENGINE_TU 1
 #include "dbl_link.cuh"
+#include "dbl_link_pcg2.cuh"
 
 #define CUDA_TRY(expr)                                                                          \
   do {                                                                                          \
@@ -620,7 +621,7 @@ struct dbl_ctx {
   DevBuf<int> perm_dev;
   int perm[DBL_MAX_ATTRS] = {0};
   int n_str = 0;       // non-constant attributes
-  bool hash32 = true;  // every non-constant attribute has a 32-slot perfect-hash table
+  int hslots = 32, hshift = 27;  // common hash-table size of the non-constant attributes; hslots = 0: none
   std::vector<AttrDev> h_attrs;
   DevBuf<int> tree_buf;
   TreeDev tree{};
@@ -722,8 +723,23 @@ static int upload_model(dbl_ctx *ctx, const dbl_model_desc *d) {
     if (v.empty()) return cudaSuccess;
     return cudaMemcpy(b.p, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice);
   };
+  // one hash-table size for the whole model: re-hash the smaller tables to the largest
+  int Hmax = 32;
+  bool hash_ok = true;
+  for (int a = 0; a < A; ++a) {
+    if (d->indexes[a]->is_const) continue;
+    if (d->indexes[a]->hsize <= 0) hash_ok = false;
+    Hmax = std::max(Hmax, d->indexes[a]->hsize);
+  }
+  std::vector<dbl_index> rehashed(A);
   for (int a = 0; a < A; ++a) {
     const dbl_index *ix = d->indexes[a];
+    if (hash_ok && !ix->is_const && ix->hsize != Hmax) {
+      rehashed[a] = *ix;
+      rehashed[a].build_hash(Hmax);
+      if (rehashed[a].hsize != Hmax) hash_ok = false;
+      ix = &rehashed[a];
+    }
     DevBuf<double> *t = &ctx->dtab[(size_t)a * 10];
     DevBuf<int> *ti = &ctx->itab[(size_t)a * 4];
     CUDA_TRY(up_d(t[0], ix->phi));
@@ -757,7 +773,10 @@ static int upload_model(dbl_ctx *ctx, const dbl_model_desc *d) {
     int k = 0;
     for (int a = 0; a < A; ++a) if (ctx->h_attrs[a].is_const) ctx->perm[k++] = a;
     ctx->n_str = A - k;
-    for (int a = 0; a < A; ++a) if (!ctx->h_attrs[a].is_const) { ctx->perm[k++] = a; if (ctx->h_attrs[a].hsize != 32) ctx->hash32 = false; }
+    for (int a = 0; a < A; ++a) if (!ctx->h_attrs[a].is_const) ctx->perm[k++] = a;
+    ctx->hslots = hash_ok ? Hmax : 0;
+    ctx->hshift = 32;
+    for (int h2 = 1; h2 < Hmax; h2 <<= 1) ctx->hshift -= 1;
     CUDA_TRY(ctx->perm_dev.alloc(A));
     CUDA_TRY(cudaMemcpy(ctx->perm_dev.p, ctx->perm, sizeof(int) * A, cudaMemcpyHostToDevice));
   }
@@ -1123,7 +1142,9 @@ static int launch_link(dbl_ctx *ctx, int sampler, uint32_t it) {
   for (int k = 0; k < A; ++k) lp.perm[k] = ctx->perm[k];
   const size_t ring = (size_t)LINK_STAGES * tile_words(A) * 4 + 128;
   const int mode = ctx->link_mode;  // 0 auto, 1 force generic
-  if (mode != 1 && sampler == DBL_PCG_II && ctx->hash32 && A <= LINK_MAX_UNROLL_A) {
+  lp.hslots = ctx->hslots; lp.hshift = ctx->hshift;
+  if (mode != 1 && sampler == DBL_PCG_II && ctx->hslots > 0 && A <= LINK_MAX_UNROLL_A &&
+      pcg2_smem_bytes(A, ctx->n_str, ctx->hslots) <= 100 * 1024) {
     int rc = -1;
     switch (A) {
 #define DBL_CASE(N) case N: rc = dbl_launch_pcg2_a##N(ctx->n_str, ctx->max_ctas, ctx->stream, lp); break;

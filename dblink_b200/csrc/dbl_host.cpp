@@ -107,14 +107,14 @@ void dbl_index::finish() {
 // Per-row perfect hash tables for expSimOf(x, y), y != x (AttributeIndex.scala:183-186): the link kernel
 // answers "is y similar to x, and how much" with one shared-memory probe.  All rows of an attribute share the
 // table size (a power of two <= 256); each row has its own multiplier found by search.
-void dbl_index::build_hash() {
+void dbl_index::build_hash(int min_slots) {
   hsize = 0;
   hshift = 32;
   hmult.clear(); hkeys.clear(); hvals.clear();
   if (is_const) return;
   int maxlen = 0;
   for (int v = 0; v < V; ++v) maxlen = std::max(maxlen, rowptr[v + 1] - rowptr[v] - 1);
-  int H = 32;
+  int H = std::max(32, min_slots);
   while (H < 2 * maxlen) H <<= 1;
   for (; H <= 256; H <<= 1) {
     int lg = 0;

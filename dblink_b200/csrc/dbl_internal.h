@@ -75,7 +75,7 @@ struct dbl_index {
   std::vector<int32_t> hkeys;      // V x hsize, -1 = empty
   std::vector<double> hvals;       // V x hsize
   void finish();
-  void build_hash();
+  void build_hash(int min_slots = 32);
 };
 
 struct dbl_kdtree {

@@ -51,6 +51,7 @@ struct LinkParams {
   // "kernel order" of the attributes: constant attributes first, then the others, each group in ascending
   // attribute id.  Tiles, per-record constants and the multiplication order of the protocol use this order.
   int perm[DBL_MAX_ATTRS];
+  int hslots, hshift;  // common size of the per-row similarity hash tables (k_link_pcg2); 0 = unavailable
 };
 
 // ---------------------------------------------------------------------------------------------------

@@ -10,8 +10,9 @@
 #pragma once
 #include "dbl_link.cuh"
 
-constexpr int PCG2_H = 32;                           // hash slots per (record, attribute)
-constexpr int PCG2_TAB_BYTES = PCG2_H * 4 + PCG2_H * 8;  // keys then values
+// Per (record, non-constant attribute): H key words then H f64 values, H = p.hslots (a power of two >= 32, the same
+// for every attribute of the model; 32 = one key per bank = conflict-free probes).
+__device__ __host__ __forceinline__ int pcg2_tab_bytes(int H) { return H * 12; }
 
 // w *= r when y == x (ptxas turns any predicated form into DMUL + 2 FSEL; plain C avoids extra moves)
 __device__ __forceinline__ void mul_if_eq(double &w, int y, int x, double r) {
@@ -28,9 +29,12 @@ struct Pcg2Rec {
 
 // CONVERGED: every lane of the warp executes the call (main loop), so the rare similar-value multiply is skipped
 // warp-wide with a vote; pass 2 calls it under divergence and must not vote.
-template <int A, int NS, bool CONVERGED>
+template <int A, int NS, int HC, bool CONVERGED>
 __device__ __forceinline__ double pcg2_weight(const Pcg2Rec<A, NS> &rc, const LinkParams &p, const char *tab,
                                               const int *y, double N) {
+  const int hslots = HC ? HC : p.hslots;
+  const int hshift = HC ? 27 : p.hshift;
+  const int tabb = pcg2_tab_bytes(hslots);
   double w = N;
 #pragma unroll
   for (int k = 0; k < A; ++k) mul_if_eq(w, y[k], rc.x[k], rc.rm[k]);
@@ -41,16 +45,16 @@ __device__ __forceinline__ double pcg2_weight(const Pcg2Rec<A, NS> &rc, const Li
 #pragma unroll
     for (int q = 0; q < NS; ++q) {
       const int yv = y[A - NS + q];
-      const unsigned slot = ((unsigned)yv * rc.hm[q]) >> 27;
-      hit[q] = (reinterpret_cast<const int *>(tab + q * PCG2_TAB_BYTES)[slot] == yv);
+      const unsigned slot = ((unsigned)yv * rc.hm[q]) >> hshift;
+      hit[q] = (reinterpret_cast<const int *>(tab + q * tabb)[slot] == yv);
       any = any || hit[q];
     }
     if (NS > 0 && __any_sync(FULL, any)) {
 #pragma unroll
       for (int q = 0; q < NS; ++q) {
         if (hit[q]) {
-          const unsigned slot = ((unsigned)y[A - NS + q] * rc.hm[q]) >> 27;
-          w = w * reinterpret_cast<const double *>(tab + q * PCG2_TAB_BYTES + PCG2_H * 4)[slot];
+          const unsigned slot = ((unsigned)y[A - NS + q] * rc.hm[q]) >> hshift;
+          w = w * reinterpret_cast<const double *>(tab + q * tabb + hslots * 4)[slot];
         }
       }
     }
@@ -58,9 +62,9 @@ __device__ __forceinline__ double pcg2_weight(const Pcg2Rec<A, NS> &rc, const Li
 #pragma unroll
     for (int q = 0; q < NS; ++q) {
       const int yv = y[A - NS + q];
-      const unsigned slot = ((unsigned)yv * rc.hm[q]) >> 27;
-      if (reinterpret_cast<const int *>(tab + q * PCG2_TAB_BYTES)[slot] == yv)
-        w = w * reinterpret_cast<const double *>(tab + q * PCG2_TAB_BYTES + PCG2_H * 4)[slot];
+      const unsigned slot = ((unsigned)yv * rc.hm[q]) >> hshift;
+      if (reinterpret_cast<const int *>(tab + q * tabb)[slot] == yv)
+        w = w * reinterpret_cast<const double *>(tab + q * tabb + hslots * 4)[slot];
     }
   }
   if (rc.mmask) {
@@ -71,7 +75,7 @@ __device__ __forceinline__ double pcg2_weight(const Pcg2Rec<A, NS> &rc, const Li
   return w;
 }
 
-template <int A, int NS>
+template <int A, int NS, int HC>
 __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int cta = blockIdx.x;
@@ -88,7 +92,7 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkPara
   rg.tw = TW;
   static_assert(2 * LINK_STAGES * 8 <= 128, "barrier area");
   char *tab = reinterpret_cast<char *>(smem) + (size_t)LINK_STAGES * TW * 4 + 128 +
-              (size_t)warp * (NS > 0 ? NS : 1) * PCG2_TAB_BYTES;
+              (size_t)warp * (NS > 0 ? NS : 1) * pcg2_tab_bytes(HC ? HC : p.hslots);
   const int *gtiles = p.tiles + (size_t)p.tile_ptr[b] * TW;
   ring_init(rg, LINK_WARPS);
 
@@ -140,11 +144,14 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkPara
 #pragma unroll
     for (int q = 0; q < NS; ++q) {
       const AttrDev &at = p.attrs[p.perm[A - NS + q]];
-      int *kd = reinterpret_cast<int *>(tab + q * PCG2_TAB_BYTES);
-      double *vd = reinterpret_cast<double *>(tab + q * PCG2_TAB_BYTES + PCG2_H * 4);
+      const int H = HC ? HC : p.hslots;
+      int *kd = reinterpret_cast<int *>(tab + q * pcg2_tab_bytes(H));
+      double *vd = reinterpret_cast<double *>(tab + q * pcg2_tab_bytes(H) + H * 4);
       const int xq = rc.x[A - NS + q];
-      kd[lane] = (xq >= 0) ? at.hkeys[(size_t)xq * PCG2_H + lane] : -1;
-      vd[lane] = (xq >= 0) ? at.hvals[(size_t)xq * PCG2_H + lane] : 1.0;
+      for (int i = lane; i < H; i += 32) {
+        kd[i] = (xq >= 0) ? at.hkeys[(size_t)xq * H + i] : -1;
+        vd[i] = (xq >= 0) ? at.hvals[(size_t)xq * H + i] : 1.0;
+      }
     }
     __syncwarp();
   }
@@ -169,7 +176,7 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkPara
         int y[A];
 #pragma unroll
         for (int k = 0; k < A; ++k) y[k] = tile[k * TE + slot];
-        acc = acc + pcg2_weight<A, NS, true>(rc, p, tab, y, tileN[slot]);
+        acc = acc + pcg2_weight<A, NS, HC, true>(rc, p, tab, y, tileN[slot]);
       }
       if (++tile_in_chunk == tpc || t + 1 == ntiles) {
         run = run + butterfly_sum(acc);
@@ -193,32 +200,37 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkPara
     int y[A];
 #pragma unroll
     for (int k = 0; k < A; ++k) y[k] = tile[k * TE + slot];
-    return pcg2_weight<A, NS, false>(rc, p, tab, y, reinterpret_cast<const double *>(tile + A * TE)[slot]);
+    return pcg2_weight<A, NS, HC, false>(rc, p, tab, y, reinterpret_cast<const double *>(tile + A * TE)[slot]);
   };
   const U2 u = uniform2(p.seed, PH_LINK, p.iter, (uint32_t)r, 0u);
   const int j = finish_draw(lane, n, nsteps, spc, nchunks, Q, run, u.u0, wf);
   store_link(p, lane, r, b, n, j);
 }
 
-inline size_t pcg2_smem_bytes(int A, int NS) {
-  return (size_t)LINK_STAGES * tile_words(A) * 4 + 128 + (size_t)LINK_WARPS * (NS > 0 ? NS : 1) * PCG2_TAB_BYTES;
+inline size_t pcg2_smem_bytes(int A, int NS, int H) {
+  return (size_t)LINK_STAGES * tile_words(A) * 4 + 128 + (size_t)LINK_WARPS * (NS > 0 ? NS : 1) * pcg2_tab_bytes(H);
 }
 
-// launch k_link_pcg2<A, NS> for a runtime NS in [0, A]; returns cudaError_t as int
+// launch k_link_pcg2<A, NS, HC> for a runtime NS in [0, A]; HC = 32 (compile-time table size) when the model's
+// tables have 32 slots, else 0 (size read from the parameters); returns cudaError_t as int
+template <int A, int NS, int HC>
+int pcg2_launch_one(int grid, cudaStream_t stream, const LinkParams &lp) {
+  const size_t smem = pcg2_smem_bytes(A, NS, lp.hslots);
+  static size_t configured = 0;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(k_link_pcg2<A, NS, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = smem;
+  }
+  k_link_pcg2<A, NS, HC><<<grid, (LINK_WARPS + 1) * 32, smem, stream>>>(lp);
+  return (int)cudaGetLastError();
+}
+
 template <int A, int NS>
 struct Pcg2Launch {
   static int go(int ns, int grid, cudaStream_t stream, const LinkParams &lp) {
-    if (ns == NS) {
-      const size_t smem = pcg2_smem_bytes(A, NS);
-      static bool configured = false;
-      if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_link_pcg2<A, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
-      }
-      k_link_pcg2<A, NS><<<grid, (LINK_WARPS + 1) * 32, smem, stream>>>(lp);
-      return (int)cudaGetLastError();
-    }
+    if (ns == NS)
+      return lp.hslots == 32 ? pcg2_launch_one<A, NS, 32>(grid, stream, lp) : pcg2_launch_one<A, NS, 0>(grid, stream, lp);
     if constexpr (NS > 0) return Pcg2Launch<A, NS - 1>::go(ns, grid, stream, lp);
     return (int)cudaErrorInvalidValue;
   }

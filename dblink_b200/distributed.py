@@ -10,7 +10,7 @@ Replaces, for the sweep, what Spark does in the reference:
                                                                   same counter-based stream
 
 The compute engine is duck-typed (`begin/pack/unpack/end/...`), so the exchange logic below is exercised on CPU
-with the gloo backend by tests/test_distributed_cpu.py; on GPUs it drives dblink_b200.GibbsEngine.
+with the gloo backend by tests/test_distributed.py; on GPUs it drives dblink_b200.GibbsEngine.
 """
 import ctypes as C
 
@@ -91,6 +91,11 @@ class ShardedGibbs:
         ent = np.bincount(blk, minlength=P).astype(np.float64)
         rec = np.bincount(blk[link], minlength=P).astype(np.float64)
         self.set_owners(lpt_assign(ent * rec, self.world))
+
+    def upload_state(self, x, file_ids, z, link, y, theta, iteration=0):
+        """Every rank uploads the same full state (State.read), then keeps the blocks it owns."""
+        self.eng.upload_state(x, file_ids, z, link, y, theta, iteration)
+        self.set_owners(self.owner)
 
     def set_owners(self, owner):
         owner = np.ascontiguousarray(owner, dtype=np.int32)
