@@ -85,6 +85,7 @@ SIGNATURES = {
     "dbl_summary_words": (C.c_int32, [vp]),
     "dbl_partial_summary": (C.c_int, [vp, i64p, f64p]),
     "dbl_set_global_summary": (C.c_int, [vp, i64p, C.c_double]),
+    "dbl_export_owned_dev": (C.c_int, [vp, vp, vp, vp, vp]),
     "dbl_owned_masks": (C.c_int, [vp, u8p, u8p]),
     "dbl_kernel_launches": (C.c_int64, [vp]),
     "dbl_set_link_mode": (C.c_int, [vp, C.c_int]),

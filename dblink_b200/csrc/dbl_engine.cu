@@ -589,6 +589,26 @@ __global__ void k_unpack_rec(int64_t n, const int *__restrict__ buf, int *__rest
   rec_owned[r] = 1;
 }
 
+// owned rows of the state into caller-provided device buffers, zeros elsewhere (the host sums them over ranks)
+__global__ void k_export_ent(int64_t E, int A, const unsigned char *__restrict__ owned, const int *__restrict__ y,
+                             const int *__restrict__ blk, int *__restrict__ y_out, int *__restrict__ blk_out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const bool o = owned[e];
+  for (int a = 0; a < A; ++a) y_out[e * A + a] = o ? y[e * A + a] : 0;
+  blk_out[e] = o ? blk[e] : 0;
+}
+__global__ void k_export_rec(int64_t R, int A, const unsigned char *__restrict__ owned, const int *__restrict__ link,
+                             const unsigned *__restrict__ zmask, int *__restrict__ link_out,
+                             unsigned char *__restrict__ z_out) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const bool o = owned[r];
+  link_out[r] = o ? link[r] : 0;
+  const unsigned zm = o ? zmask[r] : 0u;
+  for (int a = 0; a < A; ++a) z_out[r * A + a] = (zm >> a) & 1u;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host-side context
 // ---------------------------------------------------------------------------------------------------
@@ -1381,6 +1401,20 @@ extern "C" int dbl_set_global_summary(dbl_ctx *ctx, const int64_t *counts, doubl
   return DBL_OK;
 }
 extern "C" int32_t dbl_summary_words(const dbl_ctx *ctx) { return ctx ? ctx->n_counts() : 0; }
+extern "C" int dbl_export_owned_dev(dbl_ctx *ctx, void *y_dev, void *blk_dev, void *link_dev, void *z_dev) {
+  if (!ctx || !y_dev || !blk_dev || !link_dev || !z_dev) return DBL_ERR_INVALID;
+  if (!ctx->has_state) { ctx->set_error("no state"); return DBL_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  k_export_ent<<<grid_for(ctx->E, 256), 256, 0, ctx->stream>>>(ctx->E, ctx->A, ctx->ent_owned.p, ctx->y.p, ctx->blk.p,
+                                                              (int *)y_dev, (int *)blk_dev);
+  k_export_rec<<<grid_for(ctx->R, 256), 256, 0, ctx->stream>>>(ctx->R, ctx->A, ctx->rec_owned.p, ctx->link.p,
+                                                              ctx->zmask.p, (int *)link_dev, (unsigned char *)z_dev);
+  ctx->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return DBL_OK;
+}
+
 extern "C" int dbl_owned_masks(dbl_ctx *ctx, uint8_t *ent_owned, uint8_t *rec_owned) {
   if (!ctx) return DBL_ERR_INVALID;
   if (!ctx->has_state) { ctx->set_error("no state"); return DBL_ERR_STATE; }

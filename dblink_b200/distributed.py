@@ -162,18 +162,19 @@ class ShardedGibbs:
         return em.astype(bool), rm.astype(bool)
 
     def download_state(self):
-        """Gather the full state on every rank (each entity / record taken from the rank that owns it)."""
-        torch, dist = self.torch, self.dist
-        st = self.eng.download_state()
-        em, rm = self.owned_masks()
-        out = {"theta": st["theta"]}
-        for key, mask in (("y", em), ("block", em), ("link", rm), ("z", rm)):
-            a = st[key].astype(np.int64)
-            m = mask.reshape((-1,) + (1,) * (a.ndim - 1))
-            t = torch.tensor(np.where(m, a, 0), device=self.device)
+        """The full state on every rank: each rank exports the rows it owns into device buffers (zeros elsewhere),
+        one all-reduce (NCCL) per array sums them, one device-to-host copy brings them back."""
+        torch, dist, e = self.torch, self.dist, self.eng
+        R, E, A = e.num_records, e.num_entities, self.A
+        y = torch.empty(E * A, dtype=torch.int32, device=self.device)
+        blk = torch.empty(E, dtype=torch.int32, device=self.device)
+        link = torch.empty(R, dtype=torch.int32, device=self.device)
+        z = torch.empty(R * A, dtype=torch.uint8, device=self.device)
+        _check(_lib.load().dbl_export_owned_dev(e._h, y.data_ptr(), blk.data_ptr(), link.data_ptr(), z.data_ptr()),
+               "export_owned", e._h)
+        for t in (y, blk, link, z):
             dist.all_reduce(t)  # exactly one rank owns each row
-            out[key] = t.cpu().numpy().astype(st[key].dtype)
-        cnt = torch.tensor(em.astype(np.int64), device=self.device)
-        dist.all_reduce(cnt)
-        assert int(cnt.min()) == 1 and int(cnt.max()) == 1, "every entity must be owned by exactly one rank"
-        return out
+        theta = np.zeros((A, self.F))
+        _check(_lib.load().dbl_summary(e._h, None, None, None, _p(theta, _lib.f64p)), "summary", e._h)
+        return {"theta": theta, "y": y.cpu().numpy().reshape(E, A), "block": blk.cpu().numpy(),
+                "link": link.cpu().numpy(), "z": z.cpu().numpy().reshape(R, A)}

@@ -166,6 +166,9 @@ int dbl_sweep_end(dbl_ctx *);
 int32_t dbl_summary_words(const dbl_ctx *); /* A*F + (A+1) + 2 */
 int dbl_partial_summary(dbl_ctx *, int64_t *counts /*dbl_summary_words*/, double *loglik_without_prior);
 int dbl_set_global_summary(dbl_ctx *, const int64_t *counts, double loglik_without_prior);
+/* the rows this rank owns (zeros elsewhere) into caller-provided DEVICE buffers: y int32[E*A], block int32[E],
+ * link int32[R], z uint8[R*A]; summing them over ranks (all-reduce) gives the full state on every rank */
+int dbl_export_owned_dev(dbl_ctx *, void *y_dev, void *block_dev, void *link_dev, void *z_dev);
 /* which entities / records this rank currently owns (host byte arrays of E and R entries) */
 int dbl_owned_masks(dbl_ctx *, uint8_t *ent_owned, uint8_t *rec_owned);
 

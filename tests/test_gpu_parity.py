@@ -181,3 +181,22 @@ def test_attribute_index_gpu_build_equals_host(monkeypatch):
             np.testing.assert_array_equal(host[k], dev[k])
         if thr == 0.0:
             assert len(host["col"]) > 0.5 * len(vw) ** 2  # no truncation: nearly all pairs are "similar"
+
+
+@pytest.mark.parametrize("n_const,n_str", [(1, 0), (0, 1), (3, 0), (0, 6), (7, 5), (8, 8), (14, 3)])
+def test_model_shapes(oracle, n_const, n_str):
+    """different (A, NS) instantiations of the unrolled PCG-II kernel, and A > 16 which takes the generic kernel"""
+    from dblink_b200 import synth
+
+    attrs = [synth.SynthAttr(f"c{i}", "constant", 5 + 3 * i, 0.5) for i in range(n_const)]
+    attrs += [synth.SynthAttr(f"s{i}", "levenshtein", 60 + 10 * i, 1.0) for i in range(n_str)]
+    # interleave so that kernel order (constants first) differs from attribute order
+    attrs = attrs[::2] + attrs[1::2]
+    g = synth.generate(40 + n_const, 400, attrs, dup=0.3, distortion=0.15, missing=0.05, n_files=2)
+    levels = 1 if len(attrs) > 1 else 0
+    eng, rc, x, file = product_setup(g, 3, levels, (len(attrs) - 1,) if levels else ())
+    m, st, tree, ox, ofile = oracle_setup(oracle, g, 3, levels, (len(attrs) - 1,) if levels else ())
+    for sampler in ("PCG-II", "PCG-I", "Gibbs"):
+        eng.sweep(sampler, 2)
+        st.sweep(oracle.SAMPLERS[sampler], 2)
+        assert_same_state(eng, st)
