@@ -668,6 +668,13 @@ struct dbl_ctx {
   // layout
   DevBuf<int> iota, blk_sorted, ent_sorted, rec_key, rec_key_sorted, rec_sorted, ent_cnt, rec_cnt;
   DevBuf<int> ent_ptr, tile_ptr, rec_ptr, cta_ptr, cta_ptr2, tiles;
+  // inverted index of the block tables for the pruned PCG-I link kernel (built on demand, once per sweep)
+  DevBuf<unsigned long long> inv_key_in, inv_key;
+  DevBuf<int> inv_pos_in, inv_pos;
+  DevBuf<unsigned char> inv_tmp;
+  size_t inv_tmp_bytes = 0;
+  bool inv_valid = false;
+  int inv_vbits = 32;
   DevBuf<int> link_sorted, rec_by_ent, ent_rec_cnt, ent_rec_ptr;
   DevBuf<unsigned char> cub_tmp;
   size_t cub_bytes = 0;
@@ -684,7 +691,7 @@ struct dbl_ctx {
 
   int64_t launches = 0;
   double link_ms = 0.0;
-  int link_mode = 0;  // 0 auto (TMA kernels), 1 force the generic kernel (tests)
+  int link_mode = 0;  // 0 auto, 1 generic kernel everywhere, 2 dense TMA kernels everywhere (no pruning)
   double last_sweep_ms = 0.0;
   int64_t link_launches = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_events;
@@ -965,6 +972,7 @@ static int relayout(dbl_ctx *ctx) {
                                                            ctx->ent_sorted.p, ctx->ent_ptr.p, ctx->tile_ptr.p,
                                                            ctx->tiles.p, ctx->perm_dev.p, P);
   ctx->launches += 11;
+  ctx->inv_valid = false;
   CUDA_TRY(cudaGetLastError());
   return DBL_OK;
 }
@@ -1150,6 +1158,40 @@ DBL_DECL(1) DBL_DECL(2) DBL_DECL(3) DBL_DECL(4) DBL_DECL(5) DBL_DECL(6) DBL_DECL
 DBL_DECL(9) DBL_DECL(10) DBL_DECL(11) DBL_DECL(12) DBL_DECL(13) DBL_DECL(14) DBL_DECL(15) DBL_DECL(16)
 #undef DBL_DECL
 
+// (block, attribute, value) -> candidate positions, for k_link_pruned
+static int ensure_inverted_index(dbl_ctx *ctx) {
+  if (ctx->inv_valid) return DBL_OK;
+  const int64_t n = ctx->E * ctx->A;
+  if (n > 0x7fffffff) { ctx->set_error("inverted index too large"); return DBL_ERR_INVALID; }
+  if (ctx->inv_key.n != (size_t)n) {
+    CUDA_TRY(ctx->inv_key_in.alloc(n));
+    CUDA_TRY(ctx->inv_key.alloc(n));
+    CUDA_TRY(ctx->inv_pos_in.alloc(n));
+    CUDA_TRY(ctx->inv_pos.alloc(n));
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                    (const int *)nullptr, (int *)nullptr, (int)n, 0, 64, ctx->stream);
+    ctx->inv_tmp_bytes = tb + 256;
+    CUDA_TRY(ctx->inv_tmp.alloc(ctx->inv_tmp_bytes));
+  }
+  int vmax = 1;
+  for (int a = 0; a < ctx->A; ++a) vmax = std::max(vmax, ctx->h_attrs[a].V);
+  ctx->inv_vbits = bits_for(vmax + 1);
+  const int nbits = ctx->inv_vbits + bits_for((int64_t)(ctx->P + 1) * ctx->A);
+  k_inv_keys<<<grid_for(n, 256), 256, 0, ctx->stream>>>(ctx->E, ctx->A, ctx->P, ctx->inv_vbits, ctx->y.p,
+                                                        ctx->blk_sorted.p, ctx->ent_sorted.p, ctx->ent_ptr.p,
+                                                        ctx->perm_dev.p, ctx->inv_key_in.p, ctx->inv_pos_in.p);
+  size_t tb = ctx->inv_tmp_bytes;
+  // stable radix sort on the significant bits only: positions stay ascending inside a key
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->inv_tmp.p, tb, (const unsigned long long *)ctx->inv_key_in.p,
+                                           ctx->inv_key.p, (const int *)ctx->inv_pos_in.p, ctx->inv_pos.p, (int)n, 0,
+                                           std::min(64, nbits), ctx->stream));
+  ctx->launches += 4;
+  ctx->inv_valid = true;
+  CUDA_TRY(cudaGetLastError());
+  return DBL_OK;
+}
+
 static int launch_link(dbl_ctx *ctx, int sampler, uint32_t it) {
   const int A = ctx->A;
   LinkParams lp;
@@ -1160,6 +1202,7 @@ static int launch_link(dbl_ctx *ctx, int sampler, uint32_t it) {
   lp.cta_ptr = ctx->cta_ptr.p; lp.ent_sorted = ctx->ent_sorted.p; lp.rec_sorted = ctx->rec_sorted.p;
   lp.tiles = ctx->tiles.p; lp.newlink = ctx->newlink.p; lp.status = ctx->status.p; lp.pairs = ctx->pairs.p;
   for (int k = 0; k < A; ++k) lp.perm[k] = ctx->perm[k];
+  lp.blk_of_link = ctx->blk.p;
   const size_t ring = (size_t)LINK_STAGES * tile_words(A) * 4 + 128;
   const int mode = ctx->link_mode;  // 0 auto, 1 force generic
   lp.hslots = ctx->hslots; lp.hshift = ctx->hshift;
@@ -1173,6 +1216,19 @@ static int launch_link(dbl_ctx *ctx, int sampler, uint32_t it) {
 #undef DBL_CASE
     }
     if (rc != 0) { ctx->set_error(std::string("k_link_pcg2 launch: ") + cudaGetErrorString((cudaError_t)rc)); return DBL_ERR_CUDA; }
+    return DBL_OK;
+  }
+  if (mode == 0 && sampler != DBL_PCG_II) {  // pruned scoring through the inverted index
+    int rc = ensure_inverted_index(ctx);
+    if (rc) return rc;
+    PrunedParams pp;
+    pp.lp = lp;
+    pp.inv_key = ctx->inv_key.p;
+    pp.inv_pos = ctx->inv_pos.p;
+    pp.inv_n = ctx->E * ctx->A;
+    pp.R = ctx->R;
+    pp.vbits = ctx->inv_vbits;
+    k_link_pruned<<<grid_for(ctx->R, LINK_WARPS), LINK_WARPS * 32, 0, ctx->stream>>>(pp);
     return DBL_OK;
   }
   if (mode != 1 && sampler != DBL_PCG_II && ring <= 160 * 1024) {
@@ -1426,7 +1482,7 @@ extern "C" int dbl_owned_masks(dbl_ctx *ctx, uint8_t *ent_owned, uint8_t *rec_ow
 }
 
 extern "C" int dbl_set_link_mode(dbl_ctx *ctx, int mode) {
-  if (!ctx || mode < 0 || mode > 1) return DBL_ERR_INVALID;
+  if (!ctx || mode < 0 || mode > 2) return DBL_ERR_INVALID;
   ctx->link_mode = mode;
   return DBL_OK;
 }

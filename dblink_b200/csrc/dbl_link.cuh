@@ -51,6 +51,7 @@ struct LinkParams {
   // "kernel order" of the attributes: constant attributes first, then the others, each group in ascending
   // attribute id.  Tiles, per-record constants and the multiplication order of the protocol use this order.
   int perm[DBL_MAX_ATTRS];
+  const int *blk_of_link;  // block id of every entity (k_link_pruned: block of a record = block of its entity)
   int hslots, hshift;  // common size of the per-row similarity hash tables (k_link_pcg2); 0 = unavailable
 };
 
@@ -491,5 +492,214 @@ __global__ void __launch_bounds__((MATCH_WARPS + 1) * 32) k_link_match(LinkParam
   const U2 u = uniform2(p.seed, PH_LINK, p.iter, (uint32_t)r, 0u);
   const int j = finish_draw(lane, n, nsteps, spc, nchunks, Q, run, u.u0, wf);
   store_link(p, lane, r, b, n, j);
+}
+#endif  // DBL_ENGINE_TU
+
+// ---------------------------------------------------------------------------------------------------
+// k_link_pruned: PCG-I / Gibbs with a per-sweep inverted index (the reference prunes the same way:
+// EntityInvertedIndex GU:41-76, getPossibleEntities GU:473-530 -- smallest posting list first).  Only the
+// candidates that agree with the record on its most selective observed non-distorted attribute are visited;
+// every other candidate has weight exactly 0 in the dense kernel, and adding +0.0 never changes a sum, so the
+// lane sums, chunk totals and the draw are bit-identical to k_link_match / k_link_generic.
+// Index: entries (key = (block*A + kernel attribute) << 32 | value, payload = candidate position j) sorted by
+// key, positions ascending inside a key.
+// ---------------------------------------------------------------------------------------------------
+#ifdef DBL_ENGINE_TU
+// key = ((block * A + kernel attribute) << vbits) | value; rows this rank does not own go to the dummy block P
+__global__ void k_inv_keys(int64_t E, int A, int P, int vbits, const int *__restrict__ y,
+                           const int *__restrict__ blk_sorted, const int *__restrict__ ent_sorted,
+                           const int *__restrict__ ent_ptr, const int *__restrict__ perm,
+                           unsigned long long *__restrict__ key, int *__restrict__ pos) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= E * A) return;
+  const int64_t i = t / A;
+  const int k = (int)(t % A);
+  const int b = min(blk_sorted[i], P);
+  const int e = ent_sorted[i];
+  const unsigned long long v = (b < P) ? (unsigned)y[(int64_t)e * A + perm[k]] : 0u;
+  key[t] = ((unsigned long long)((unsigned)b * (unsigned)A + (unsigned)k) << vbits) | v;
+  pos[t] = (b < P) ? (int)(i - ent_ptr[b]) : -1;
+}
+
+__device__ __forceinline__ int64_t inv_lower_bound(const unsigned long long *__restrict__ key, int64_t n,
+                                                   unsigned long long want) {
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (key[mid] < want) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+struct PrunedParams {
+  LinkParams lp;
+  const unsigned long long *inv_key;
+  const int *inv_pos;
+  long long inv_n;
+  long long R;
+  int vbits;
+};
+
+__global__ void __launch_bounds__(LINK_WARPS * 32) k_link_pruned(PrunedParams pp) {
+  __shared__ RecAttr s_ra[LINK_WARPS][DBL_MAX_ATTRS];
+  __shared__ int s_mm_attr[LINK_WARPS][DBL_MAX_ATTRS];
+  __shared__ int s_mm_x[LINK_WARPS][DBL_MAX_ATTRS];
+  const LinkParams &p = pp.lp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long ridx = (long long)blockIdx.x * LINK_WARPS + warp;
+  if (ridx >= p.rec_ptr[p.P]) return;  // records of blocks this rank owns come first in rec_sorted
+  const int r = p.rec_sorted[ridx];
+  const int b = p.blk_of_link ? p.blk_of_link[p.link[r]] : 0;
+  const int A = p.A;
+  const int n = p.ent_ptr[b + 1] - p.ent_ptr[b];
+  const int ntiles = p.tile_ptr[b + 1] - p.tile_ptr[b];
+  const size_t TW = tile_words(A);
+  const int *gtiles = p.tiles + (size_t)p.tile_ptr[b] * TW;
+  RecAttr *ra = s_ra[warp];
+  int nmm = 0;
+  long long plo = 0, phi = n;  // posting range in the index, or the whole block when nothing must match
+  int best = -1;
+  {
+    bool mm = false;
+    long long lo = 0, len = 0x7fffffffffffLL;
+    if (lane < A) {
+      RecAttr c;
+      prep_rec_attr(p, r, lane, c);
+      ra[lane] = c;
+      mm = (c.kind == 4);
+      if (mm) {
+        const unsigned long long base = (unsigned long long)((unsigned)b * (unsigned)A + (unsigned)lane) << pp.vbits;
+        lo = inv_lower_bound(pp.inv_key, pp.inv_n, base | (unsigned)c.x);
+        const long long hi = inv_lower_bound(pp.inv_key, pp.inv_n, base | ((unsigned)c.x + 1u));
+        len = hi - lo;
+      }
+    }
+    const unsigned mmask = __ballot_sync(FULL, mm);
+    nmm = __popc(mmask);
+    if (mm) {
+      const int rank = __popc(mmask & ((1u << lane) - 1u));
+      s_mm_attr[warp][rank] = lane;
+      s_mm_x[warp][rank] = ra[lane].x;
+    }
+    // shortest posting list (ties: lowest attribute)
+    long long bl = len;
+    int bk = mm ? lane : 64;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      const long long ol = __shfl_xor_sync(FULL, bl, d);
+      const int ok = __shfl_xor_sync(FULL, bk, d);
+      if (ol < bl || (ol == bl && ok < bk)) { bl = ol; bk = ok; }
+    }
+    if (nmm > 0) {
+      best = bk;
+      plo = __shfl_sync(FULL, lo, best);
+      phi = plo + bl;
+    }
+    __syncwarp();
+  }
+  const int *mma = s_mm_attr[warp];
+  const int *mmx = s_mm_x[warp];
+  const int nsteps = ntiles * (TE / 32);
+  const int tpc = max(1, (ntiles + 31) >> 5);
+  const int spc = (TE / 32) * tpc;
+  const int nchunks = (nsteps + spc - 1) / spc;
+  const int cand_per_chunk = TE * tpc;
+
+  // candidate j of index entry idx, its protocol weight (0 unless it survives every must-match attribute)
+  auto cand_weight = [&](long long idx, int &j) -> double {
+    j = -1;
+    if (idx >= phi) return 0.0;
+    j = (nmm > 0) ? pp.inv_pos[idx] : (int)idx;
+    const int *tile = gtiles + (size_t)(j / TE) * TW;
+    const int slot = j % TE;
+    bool ok = true;
+    for (int k = 0; k < nmm && ok; ++k)
+      if (mma[k] != best) ok = (tile[mma[k] * TE + slot] == mmx[k]);
+    if (!ok) return 0.0;
+    return generic_weight(ra, A, false, tile + slot, reinterpret_cast<const double *>(tile + (size_t)A * TE)[slot]);
+  };
+
+  // ---- pass 1: lane sums per chunk from the survivors only
+  double run = 0.0, Q = 0.0, s = 0.0;
+  int cur = 0;
+  bool dirty = false;
+  auto close_chunks_until = [&](int c_next) {  // finalise chunks cur .. c_next-1
+    while (cur < c_next) {
+      if (dirty) { run = run + butterfly_sum(s); s = 0.0; dirty = false; }
+      if (lane == cur) Q = run;
+      ++cur;
+    }
+  };
+  for (long long g = plo; g < phi; g += 32) {
+    int j;
+    const double w = cand_weight(g + lane, j);
+    unsigned live = __ballot_sync(FULL, w > 0.0);
+    while (live) {
+      const int i = __ffs(live) - 1;
+      live &= live - 1;
+      const int ji = __shfl_sync(FULL, j, i);
+      const double wi = shfl_d(w, i);
+      close_chunks_until(ji / cand_per_chunk);
+      if (lane == (ji & 31)) s = s + wi;
+      dirty = true;
+    }
+  }
+  close_chunks_until(nchunks);
+  if (!(run > 0.0) || isinf(run)) { fail_link(p, lane, r); return; }
+
+  // ---- pass 2: the same walk restricted to the chosen chunk
+  const U2 u = uniform2(p.seed, PH_LINK, p.iter, (uint32_t)r, 0u);
+  const double t = u.u0 * run;
+  unsigned m = __ballot_sync(FULL, lane < nchunks && Q > t);
+  const int chunk = m ? (__ffs(m) - 1) : (nchunks - 1);
+  double rsum = shfl_d(Q, chunk > 0 ? chunk - 1 : 0);
+  if (chunk == 0) rsum = 0.0;
+  double ls = 0.0;
+  for (long long g = plo; g < phi; g += 32) {
+    int j;
+    const double w = cand_weight(g + lane, j);
+    unsigned live = __ballot_sync(FULL, w > 0.0 && j / cand_per_chunk == chunk);
+    while (live) {
+      const int i = __ffs(live) - 1;
+      live &= live - 1;
+      const int ji = __shfl_sync(FULL, j, i);
+      const double wi = shfl_d(w, i);
+      if (lane == (ji & 31)) ls = ls + wi;
+    }
+  }
+  double Pfx = ls;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const double o = shfl_up_d(Pfx, d);
+    if (lane >= d) Pfx = Pfx + o;
+  }
+  m = __ballot_sync(FULL, rsum + Pfx > t);
+  int L;
+  if (m) L = __ffs(m) - 1;
+  else {
+    const unsigned pos = __ballot_sync(FULL, ls > 0.0);
+    L = pos ? (31 - __clz(pos)) : 0;
+  }
+  const double Pprev = shfl_up_d(Pfx, 1);
+  const double base_l = lane ? rsum + Pprev : rsum;
+  const double base = shfl_d(base_l, L);
+  double cum = 0.0;
+  int pick = -1, last_pos = -1;
+  for (long long g = plo; g < phi && pick < 0; g += 32) {
+    int j;
+    const double w = cand_weight(g + lane, j);
+    unsigned live = __ballot_sync(FULL, w > 0.0 && j / cand_per_chunk == chunk && (j & 31) == L);
+    while (live) {
+      const int i = __ffs(live) - 1;
+      live &= live - 1;
+      const int ji = __shfl_sync(FULL, j, i);
+      const double wi = shfl_d(w, i);
+      cum = cum + wi;
+      last_pos = ji;
+      if (base + cum > t) { pick = ji; break; }
+    }
+  }
+  if (pick < 0) pick = last_pos >= 0 ? last_pos : (chunk * cand_per_chunk + L < n ? chunk * cand_per_chunk + L : n - 1);
+  store_link(p, lane, r, b, n, pick);
 }
 #endif  // DBL_ENGINE_TU

@@ -174,8 +174,9 @@ int dbl_owned_masks(dbl_ctx *, uint8_t *ent_owned, uint8_t *rec_owned);
 
 /* count of kernels launched by this context since creation (bench.py's gpu_launches) */
 int64_t dbl_kernel_launches(const dbl_ctx *);
-/* Link-kernel selection: 0 = automatic (TMA-staged kernels when the model fits them), 1 = always the generic
- * fallback kernel.  Both produce identical draws; this exists so tests can cover the fallback. */
+/* Link-kernel selection: 0 = automatic (PCG-II: TMA-staged dense kernel; PCG-I/Gibbs: scoring pruned through a
+ * per-sweep inverted index), 1 = always the generic fallback kernel, 2 = dense TMA kernels for every sampler.
+ * All produce identical draws; this exists so tests can cover every kernel. */
 int dbl_set_link_mode(dbl_ctx *, int mode);
 /* CUDA-event time (ms) of the last dbl_sweep call, first operation to last operation on the context's stream */
 double dbl_last_sweep_ms(const dbl_ctx *);

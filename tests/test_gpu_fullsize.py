@@ -70,8 +70,9 @@ def test_full_size_properties(big, sampler):
             # a record can only link to an entity of the block it was in (GU:137, 192-198)
             assert np.array_equal(blk_before[da["link"]], blk_before[link_before])
     assert sa["pairs_scored"] == sb["pairs_scored"] > 3e10
-    # determinism: a fresh engine replays the same chain
+    # determinism: a fresh engine replays the same chain (here through the dense TMA kernels, mode 2)
     c = make()
+    c.set_link_mode(2)
     c.sweep(sampler, 2)
     dc = c.download_state()
     for k in ("link", "y", "z", "theta"):

@@ -39,11 +39,12 @@ def test_initial_state(oracle, levels, attr_ids):
     assert_same_state(eng, st)
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("sampler", SAMPLERS)
 @pytest.mark.parametrize("levels,attr_ids", [(0, ()), (2, (2, 3))])
 def test_chain_from_init(oracle, sampler, levels, attr_ids, mode):
-    """mode 0 = TMA-staged link kernels, mode 1 = generic fallback kernel: identical draws"""
+    """mode 0 = default kernels (TMA-staged PCG-II, index-pruned PCG-I), 1 = generic fallback, 2 = dense TMA kernels for
+    every sampler: identical draws"""
     g = synth_problem(seed=5, R=900, n_files=2)
     eng, rc, x, file = product_setup(g, 99, levels, attr_ids)
     eng.set_link_mode(mode)
