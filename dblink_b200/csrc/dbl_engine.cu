@@ -670,7 +670,7 @@ struct dbl_ctx {
   DevBuf<int> ent_ptr, tile_ptr, rec_ptr, cta_ptr, cta_ptr2, tiles;
   // inverted index of the block tables for the pruned PCG-I link kernel (built on demand, once per sweep)
   DevBuf<unsigned long long> inv_key_in, inv_key;
-  DevBuf<int> inv_pos_in, inv_pos;
+  DevBuf<int> inv_pos_in, inv_pos, inv_seg;
   DevBuf<unsigned char> inv_tmp;
   size_t inv_tmp_bytes = 0;
   bool inv_valid = false;
@@ -1186,7 +1186,11 @@ static int ensure_inverted_index(dbl_ctx *ctx) {
   CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->inv_tmp.p, tb, (const unsigned long long *)ctx->inv_key_in.p,
                                            ctx->inv_key.p, (const int *)ctx->inv_pos_in.p, ctx->inv_pos.p, (int)n, 0,
                                            std::min(64, nbits), ctx->stream));
-  ctx->launches += 4;
+  const int n_groups = (ctx->P + 1) * ctx->A;
+  if (ctx->inv_seg.n != (size_t)n_groups + 1) CUDA_TRY(ctx->inv_seg.alloc((size_t)n_groups + 1));
+  k_inv_segments<<<grid_for(n + 1, 256), 256, 0, ctx->stream>>>(n, n_groups, ctx->inv_vbits, ctx->inv_key.p,
+                                                                ctx->inv_seg.p);
+  ctx->launches += 5;
   ctx->inv_valid = true;
   CUDA_TRY(cudaGetLastError());
   return DBL_OK;
@@ -1228,6 +1232,7 @@ static int launch_link(dbl_ctx *ctx, int sampler, uint32_t it) {
     pp.inv_n = ctx->E * ctx->A;
     pp.R = ctx->R;
     pp.vbits = ctx->inv_vbits;
+    pp.inv_seg = ctx->inv_seg.p;
     k_link_pruned<<<grid_for(ctx->R, LINK_WARPS), LINK_WARPS * 32, 0, ctx->stream>>>(pp);
     return DBL_OK;
   }

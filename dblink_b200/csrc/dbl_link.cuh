@@ -521,9 +521,18 @@ __global__ void k_inv_keys(int64_t E, int A, int P, int vbits, const int *__rest
   pos[t] = (b < P) ? (int)(i - ent_ptr[b]) : -1;
 }
 
-__device__ __forceinline__ int64_t inv_lower_bound(const unsigned long long *__restrict__ key, int64_t n,
+// seg[g] = first index entry of group g = block * A + kernel attribute (one pass over the sorted keys)
+__global__ void k_inv_segments(int64_t n, int n_groups, int vbits, const unsigned long long *__restrict__ key,
+                               int *__restrict__ seg) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  const int cur = (i < n) ? (int)min((unsigned long long)n_groups, key[i] >> vbits) : n_groups;
+  const int prev = (i > 0) ? (int)min((unsigned long long)n_groups, key[i - 1] >> vbits) : -1;
+  for (int g = prev + 1; g <= cur; ++g) seg[g] = (int)i;
+}
+
+__device__ __forceinline__ int64_t inv_lower_bound(const unsigned long long *__restrict__ key, int64_t lo, int64_t hi,
                                                    unsigned long long want) {
-  int64_t lo = 0, hi = n;
   while (lo < hi) {
     const int64_t mid = (lo + hi) >> 1;
     if (key[mid] < want) lo = mid + 1; else hi = mid;
@@ -538,12 +547,16 @@ struct PrunedParams {
   long long inv_n;
   long long R;
   int vbits;
+  const int *inv_seg;  // (P+1)*A + 1 group offsets
 };
 
 __global__ void __launch_bounds__(LINK_WARPS * 32) k_link_pruned(PrunedParams pp) {
   __shared__ RecAttr s_ra[LINK_WARPS][DBL_MAX_ATTRS];
   __shared__ int s_mm_attr[LINK_WARPS][DBL_MAX_ATTRS];
   __shared__ int s_mm_x[LINK_WARPS][DBL_MAX_ATTRS];
+  constexpr int SCAP = 48;  // survivors kept for pass 2 (more than that: pass 2 walks the postings again)
+  __shared__ int s_sj[LINK_WARPS][SCAP];
+  __shared__ double s_sw[LINK_WARPS][SCAP];
   const LinkParams &p = pp.lp;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long ridx = (long long)blockIdx.x * LINK_WARPS + warp;
@@ -557,6 +570,7 @@ __global__ void __launch_bounds__(LINK_WARPS * 32) k_link_pruned(PrunedParams pp
   const int *gtiles = p.tiles + (size_t)p.tile_ptr[b] * TW;
   RecAttr *ra = s_ra[warp];
   int nmm = 0;
+  bool has_sim = false;  // some observed distorted non-constant attribute: weights are not all 1
   long long plo = 0, phi = n;  // posting range in the index, or the whole block when nothing must match
   int best = -1;
   {
@@ -569,13 +583,16 @@ __global__ void __launch_bounds__(LINK_WARPS * 32) k_link_pruned(PrunedParams pp
       mm = (c.kind == 4);
       if (mm) {
         const unsigned long long base = (unsigned long long)((unsigned)b * (unsigned)A + (unsigned)lane) << pp.vbits;
-        lo = inv_lower_bound(pp.inv_key, pp.inv_n, base | (unsigned)c.x);
-        const long long hi = inv_lower_bound(pp.inv_key, pp.inv_n, base | ((unsigned)c.x + 1u));
+        const int g = b * A + lane;
+        const long long s0 = pp.inv_seg[g], s1 = pp.inv_seg[g + 1];  // the E_b entries of (block, attribute)
+        lo = inv_lower_bound(pp.inv_key, s0, s1, base | (unsigned)c.x);
+        const long long hi = inv_lower_bound(pp.inv_key, lo, s1, base | ((unsigned)c.x + 1u));
         len = hi - lo;
       }
     }
     const unsigned mmask = __ballot_sync(FULL, mm);
     nmm = __popc(mmask);
+    has_sim = __any_sync(FULL, lane < A && ra[lane].kind == 2);
     if (mm) {
       const int rank = __popc(mmask & ((1u << lane) - 1u));
       s_mm_attr[warp][rank] = lane;
@@ -616,6 +633,7 @@ __global__ void __launch_bounds__(LINK_WARPS * 32) k_link_pruned(PrunedParams pp
     for (int k = 0; k < nmm && ok; ++k)
       if (mma[k] != best) ok = (tile[mma[k] * TE + slot] == mmx[k]);
     if (!ok) return 0.0;
+    if (!has_sim) return 1.0;  // GU:408-411: uniform over the candidates
     return generic_weight(ra, A, false, tile + slot, reinterpret_cast<const double *>(tile + (size_t)A * TE)[slot]);
   };
 
@@ -623,13 +641,14 @@ __global__ void __launch_bounds__(LINK_WARPS * 32) k_link_pruned(PrunedParams pp
   double run = 0.0, Q = 0.0, s = 0.0;
   int cur = 0;
   bool dirty = false;
-  auto close_chunks_until = [&](int c_next) {  // finalise chunks cur .. c_next-1
-    while (cur < c_next) {
+  auto close_chunks_until = [&](int c_next) {  // finalise chunks cur .. c_next-1 (only `cur` can hold mass)
+    if (cur < c_next) {
       if (dirty) { run = run + butterfly_sum(s); s = 0.0; dirty = false; }
-      if (lane == cur) Q = run;
-      ++cur;
+      if (lane >= cur && lane < c_next) Q = run;
+      cur = c_next;
     }
   };
+  int ns = 0;  // survivors seen (stored while they fit)
   for (long long g = plo; g < phi; g += 32) {
     int j;
     const double w = cand_weight(g + lane, j);
@@ -642,9 +661,12 @@ __global__ void __launch_bounds__(LINK_WARPS * 32) k_link_pruned(PrunedParams pp
       close_chunks_until(ji / cand_per_chunk);
       if (lane == (ji & 31)) s = s + wi;
       dirty = true;
+      if (ns < SCAP && lane == 0) { s_sj[warp][ns] = ji; s_sw[warp][ns] = wi; }
+      ++ns;
     }
   }
   close_chunks_until(nchunks);
+  __syncwarp();
   if (!(run > 0.0) || isinf(run)) { fail_link(p, lane, r); return; }
 
   // ---- pass 2: the same walk restricted to the chosen chunk
@@ -654,17 +676,25 @@ __global__ void __launch_bounds__(LINK_WARPS * 32) k_link_pruned(PrunedParams pp
   const int chunk = m ? (__ffs(m) - 1) : (nchunks - 1);
   double rsum = shfl_d(Q, chunk > 0 ? chunk - 1 : 0);
   if (chunk == 0) rsum = 0.0;
+  const bool stored = (ns <= SCAP);
   double ls = 0.0;
-  for (long long g = plo; g < phi; g += 32) {
-    int j;
-    const double w = cand_weight(g + lane, j);
-    unsigned live = __ballot_sync(FULL, w > 0.0 && j / cand_per_chunk == chunk);
-    while (live) {
-      const int i = __ffs(live) - 1;
-      live &= live - 1;
-      const int ji = __shfl_sync(FULL, j, i);
-      const double wi = shfl_d(w, i);
-      if (lane == (ji & 31)) ls = ls + wi;
+  if (stored) {
+    for (int i = 0; i < ns; ++i) {
+      const int ji = s_sj[warp][i];
+      if (ji / cand_per_chunk == chunk && lane == (ji & 31)) ls = ls + s_sw[warp][i];
+    }
+  } else {
+    for (long long g = plo; g < phi; g += 32) {
+      int j;
+      const double w = cand_weight(g + lane, j);
+      unsigned live = __ballot_sync(FULL, w > 0.0 && j / cand_per_chunk == chunk);
+      while (live) {
+        const int i = __ffs(live) - 1;
+        live &= live - 1;
+        const int ji = __shfl_sync(FULL, j, i);
+        const double wi = shfl_d(w, i);
+        if (lane == (ji & 31)) ls = ls + wi;
+      }
     }
   }
   double Pfx = ls;
@@ -685,18 +715,29 @@ __global__ void __launch_bounds__(LINK_WARPS * 32) k_link_pruned(PrunedParams pp
   const double base = shfl_d(base_l, L);
   double cum = 0.0;
   int pick = -1, last_pos = -1;
-  for (long long g = plo; g < phi && pick < 0; g += 32) {
-    int j;
-    const double w = cand_weight(g + lane, j);
-    unsigned live = __ballot_sync(FULL, w > 0.0 && j / cand_per_chunk == chunk && (j & 31) == L);
-    while (live) {
-      const int i = __ffs(live) - 1;
-      live &= live - 1;
-      const int ji = __shfl_sync(FULL, j, i);
-      const double wi = shfl_d(w, i);
-      cum = cum + wi;
-      last_pos = ji;
-      if (base + cum > t) { pick = ji; break; }
+  if (stored) {
+    for (int i = 0; i < ns && pick < 0; ++i) {
+      const int ji = s_sj[warp][i];
+      if (ji / cand_per_chunk == chunk && (ji & 31) == L) {
+        cum = cum + s_sw[warp][i];
+        last_pos = ji;
+        if (base + cum > t) pick = ji;
+      }
+    }
+  } else {
+    for (long long g = plo; g < phi && pick < 0; g += 32) {
+      int j;
+      const double w = cand_weight(g + lane, j);
+      unsigned live = __ballot_sync(FULL, w > 0.0 && j / cand_per_chunk == chunk && (j & 31) == L);
+      while (live) {
+        const int i = __ffs(live) - 1;
+        live &= live - 1;
+        const int ji = __shfl_sync(FULL, j, i);
+        const double wi = shfl_d(w, i);
+        cum = cum + wi;
+        last_pos = ji;
+        if (base + cum > t) { pick = ji; break; }
+      }
     }
   }
   if (pick < 0) pick = last_pos >= 0 ? last_pos : (chunk * cand_per_chunk + L < n ? chunk * cand_per_chunk + L : n - 1);
