@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libdblink_b200.so")
+SO_PATH = os.environ.get("DBL_LIB") or os.path.join(_HERE, "libdblink_b200.so")  # DBL_LIB: experiment builds
 
 OK, ERR_INVALID, ERR_CUDA, ERR_ZERO_MASS, ERR_STATE = 0, -1, -2, -3, -4
 PCG_I, PCG_II, GIBBS, GIBBS_SEQ = 0, 1, 2, 3

@@ -12,8 +12,8 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-SO = os.path.join(HERE, "libdblink_b200.so")
+OBJ = os.environ.get("DBL_OBJ") or os.path.join(HERE, "build")
+SO = os.environ.get("DBL_SO") or os.path.join(HERE, "libdblink_b200.so")  # DBL_SO / DBL_NVCC_FLAGS: experiment builds
 MAX_A = 16
 
 COMMON = [
@@ -21,7 +21,7 @@ COMMON = [
     # the draw protocol is defined over individually rounded binary64 operations: no FMA contraction
     "-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-O2,-pthread",
     "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-]
+] + os.environ.get("DBL_NVCC_FLAGS", "").split()
 
 
 def nvcc_path():

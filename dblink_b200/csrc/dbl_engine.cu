@@ -128,10 +128,35 @@ __global__ void k_hist(int64_t n, const int *__restrict__ key, int *__restrict__
   if (i < n) atomicAdd(&cnt[key[i]], 1);
 }
 // sort keys; entities / records this rank does not own go to the dummy slot (block P, entity E)
+// Records are grouped by block and, within a block, by a static cost class, so that the records sharing a CTA of
+// the link kernel (and its tile ring) advance at the same pace.  The order of records inside a block has no effect
+// on the draws (every record has its own counter-based stream).
+constexpr int REC_CLASS_BITS = 8;
 __global__ void k_rec_block_keys(int64_t R, const int *__restrict__ link, const int *__restrict__ blk,
-                                 const unsigned char *__restrict__ rec_owned, int P, int *__restrict__ key) {
+                                 const unsigned char *__restrict__ rec_owned,
+                                 const unsigned char *__restrict__ rec_class, int P, int *__restrict__ key) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < R) key[r] = rec_owned[r] ? blk[link[r]] : P;
+  if (r < R) key[r] = rec_owned[r] ? ((blk[link[r]] << REC_CLASS_BITS) | rec_class[r]) : (P << REC_CLASS_BITS);
+}
+// cost class of a record (x is static): bits 7..6 = number of missing non-constant attributes (each one adds a
+// gather per candidate), bits 5..0 = expected number of similar-but-different candidate values per 32-candidate
+// step (how often the warp takes the similarity multiply), from the empirical value frequencies.
+__global__ void k_rec_class(int64_t R, int A, const AttrDev *__restrict__ attrs, const int *__restrict__ x,
+                            unsigned char *__restrict__ cls) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  int miss = 0;
+  double h = 0.0;
+  for (int a = 0; a < A; ++a) {
+    const AttrDev &at = attrs[a];
+    if (at.is_const) continue;
+    const int xv = x[r * A + a];
+    if (xv < 0) { ++miss; continue; }
+    for (int i = at.rowptr[xv]; i < at.rowptr[xv + 1]; ++i)
+      if (at.col[i] != xv) h += at.probs[at.col[i]];
+  }
+  const int hq = min(63, (int)(h * 32.0 * 8.0));
+  cls[r] = (unsigned char)((min(miss, 3) << 6) | hq);
 }
 __global__ void k_ent_block_keys(int64_t E, const int *__restrict__ blk, const unsigned char *__restrict__ ent_owned,
                                  int P, int *__restrict__ key) {
@@ -145,11 +170,12 @@ __global__ void k_rec_link_keys(int64_t R, const int *__restrict__ link, const u
 }
 // offsets from sorted keys: ptr[k] = first position whose key is >= k, for k = 0..n_keys (keys beyond the data
 // point at n).  One pass over the sorted array; replaces an atomic histogram + scan.
-__global__ void k_segment_ptr(int64_t n, int n_keys, const int *__restrict__ sorted_key, int *__restrict__ ptr) {
+__global__ void k_segment_ptr(int64_t n, int n_keys, const int *__restrict__ sorted_key, int *__restrict__ ptr,
+                              int shift = 0) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i > n) return;
-  const int cur = (i < n) ? min(sorted_key[i], n_keys) : n_keys;
-  const int prev = (i > 0) ? min(sorted_key[i - 1], n_keys) : -1;
+  const int cur = (i < n) ? min(sorted_key[i] >> shift, n_keys) : n_keys;
+  const int prev = (i > 0) ? min(sorted_key[i - 1] >> shift, n_keys) : -1;
   for (int k = prev + 1; k <= cur; ++k) ptr[k] = (int)i;
 }
 // prefix sums over the P blocks (P is 2^numLevels: small) -- one CTA, Hillis-Steele over chunks
@@ -676,6 +702,7 @@ struct dbl_ctx {
   bool inv_valid = false;
   int inv_vbits = 32;
   DevBuf<int> link_sorted, rec_by_ent, ent_rec_cnt, ent_rec_ptr;
+  DevBuf<unsigned char> rec_class;  // static cost class of a record (k_rec_class)
   DevBuf<unsigned char> cub_tmp;
   size_t cub_bytes = 0;
   int max_ctas = 0;
@@ -902,6 +929,7 @@ static int alloc_state(dbl_ctx *ctx, int64_t R, int64_t E) {
   CUDA_TRY(ctx->entN.alloc(E));
   CUDA_TRY(ctx->ent_owned.alloc(E));
   CUDA_TRY(ctx->rec_owned.alloc(R));
+  CUDA_TRY(ctx->rec_class.alloc(R));
   CUDA_TRY(cudaMemsetAsync(ctx->ent_owned.p, 1, E, ctx->stream));
   CUDA_TRY(cudaMemsetAsync(ctx->rec_owned.p, 1, R, ctx->stream));
   CUDA_TRY(ctx->ent_dest.alloc(E));
@@ -958,13 +986,15 @@ static int relayout(dbl_ctx *ctx) {
   k_ent_block_keys<<<grid_for(E, 256), 256, 0, ctx->stream>>>(E, ctx->blk.p, ctx->ent_owned.p, P, ctx->ent_key.p);
   CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, (const int *)ctx->ent_key.p, ctx->blk_sorted.p,
                                            (const int *)ctx->iota.p, ctx->ent_sorted.p, (int)E, 0, pb, ctx->stream));
-  k_rec_block_keys<<<grid_for(R, 256), 256, 0, ctx->stream>>>(R, ctx->link.p, ctx->blk.p, ctx->rec_owned.p, P,
-                                                              ctx->rec_key.p);
+  k_rec_block_keys<<<grid_for(R, 256), 256, 0, ctx->stream>>>(R, ctx->link.p, ctx->blk.p, ctx->rec_owned.p,
+                                                              ctx->rec_class.p, P, ctx->rec_key.p);
   tb = ctx->cub_bytes;
   CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, (const int *)ctx->rec_key.p, ctx->rec_key_sorted.p,
-                                           (const int *)ctx->iota.p, ctx->rec_sorted.p, (int)R, 0, pb, ctx->stream));
+                                           (const int *)ctx->iota.p, ctx->rec_sorted.p, (int)R, 0,
+                                           pb + REC_CLASS_BITS, ctx->stream));
   k_segment_ptr<<<grid_for(E + 1, 256), 256, 0, ctx->stream>>>(E, P, ctx->blk_sorted.p, ctx->ent_ptr.p);
-  k_segment_ptr<<<grid_for(R + 1, 256), 256, 0, ctx->stream>>>(R, P, ctx->rec_key_sorted.p, ctx->rec_ptr.p);
+  k_segment_ptr<<<grid_for(R + 1, 256), 256, 0, ctx->stream>>>(R, P, ctx->rec_key_sorted.p, ctx->rec_ptr.p,
+                                                                REC_CLASS_BITS);
   k_block_scan<<<1, 32, 0, ctx->stream>>>(P, ctx->ent_ptr.p, ctx->rec_ptr.p, ctx->tile_ptr.p, ctx->cta_ptr.p,
                                           LINK_WARPS, ctx->cta_ptr2.p, MATCH_WARPS);
   CUDA_TRY(cudaMemsetAsync(ctx->tiles.p, 0, ctx->tiles.n * sizeof(int), ctx->stream));
@@ -1075,6 +1105,7 @@ extern "C" int dbl_state_init(dbl_ctx *ctx, int64_t R, const int32_t *x, const i
   if (rc) return rc;
   const int A = ctx->A;
   CUDA_TRY(cudaMemcpyAsync(ctx->x.p, x, sizeof(int) * R * A, cudaMemcpyHostToDevice, ctx->stream));
+  k_rec_class<<<grid_for(R, 256), 256, 0, ctx->stream>>>(R, A, ctx->attrs.p, ctx->x.p, ctx->rec_class.p);
   CUDA_TRY(cudaMemcpyAsync(ctx->file.p, file, sizeof(int) * R, cudaMemcpyHostToDevice, ctx->stream));
   k_init_entities<<<grid_for(E * A, 256), 256, 0, ctx->stream>>>(E, R, A, ctx->seed, ctx->attrs.p, ctx->x.p, ctx->y.p);
   k_init_records<<<grid_for(R, 256), 256, 0, ctx->stream>>>(E, R, A, ctx->x.p, ctx->y.p, ctx->link.p, ctx->zmask.p);
@@ -1098,6 +1129,7 @@ extern "C" int dbl_state_upload(dbl_ctx *ctx, int64_t R, int64_t E, const int32_
   const int A = ctx->A;
   DevBuf<uint8_t> &zb = ctx->zbytes;
   CUDA_TRY(cudaMemcpyAsync(ctx->x.p, x, sizeof(int) * R * A, cudaMemcpyHostToDevice, ctx->stream));
+  k_rec_class<<<grid_for(R, 256), 256, 0, ctx->stream>>>(R, A, ctx->attrs.p, ctx->x.p, ctx->rec_class.p);
   CUDA_TRY(cudaMemcpyAsync(ctx->file.p, file, sizeof(int) * R, cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(cudaMemcpyAsync(zb.p, z, (size_t)R * A, cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(cudaMemcpyAsync(ctx->link.p, link, sizeof(int) * R, cudaMemcpyHostToDevice, ctx->stream));

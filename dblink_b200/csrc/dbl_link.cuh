@@ -332,6 +332,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
         : "memory");
   }
 }
+#ifndef DBL_PRODUCER_HINT
+#define DBL_PRODUCER_HINT 0x989680u
+#endif
 // producer-side wait (off the critical path while the ring is full): long suspend-time hint so that the idle
 // producer lane does not steal issue slots from the consumer warps
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, unsigned parity) {
@@ -341,7 +344,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, unsigned parity
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(addr), "r"(parity), "r"(0x989680u)
+        : "r"(addr), "r"(parity), "r"(DBL_PRODUCER_HINT)
         : "memory");
   }
 }

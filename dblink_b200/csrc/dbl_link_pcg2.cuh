@@ -164,9 +164,19 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkPara
   // ---- pass 1 over the TMA-staged tiles
   double run = 0.0, Q = 0.0, acc = 0.0;
   int chunk = 0, tile_in_chunk = 0;
+#ifdef DBL_EXP_WAITCLK
+  long long wclk_ = 0;
+  const long long cstart_ = clock64();
+#endif
   for (int t = 0; t < ntiles; ++t) {
     const int s = t % LINK_STAGES;
+#ifdef DBL_EXP_WAITCLK
+    const long long c0_ = clock64();
+#endif
     mbar_wait(&rg.full[s], (t / LINK_STAGES) & 1);
+#ifdef DBL_EXP_WAITCLK
+    wclk_ += clock64() - c0_;
+#endif
     if (active) {
       const int *tile = rg.tiles + (size_t)s * TW;
       const double *tileN = reinterpret_cast<const double *>(tile + A * TE);
@@ -189,6 +199,9 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkPara
     __syncwarp();
     if (lane == 0) mbar_arrive(&rg.empty[s]);
   }
+#ifdef DBL_EXP_WAITCLK
+  const long long cloop_ = clock64() - cstart_;
+#endif
   if (!active) return;
   if (!(run > 0.0) || isinf(run)) { fail_link(p, lane, r); return; }
 
@@ -205,6 +218,10 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkPara
   const U2 u = uniform2(p.seed, PH_LINK, p.iter, (uint32_t)r, 0u);
   const int j = finish_draw(lane, n, nsteps, spc, nchunks, Q, run, u.u0, wf);
   store_link(p, lane, r, b, n, j);
+#ifdef DBL_EXP_WAITCLK
+  if (lane == 0 && (cta % 997) == 0 && p.iter == 2)
+    printf("cta %d warp %d ntiles %d loop %lld wait %lld total %lld\n", cta, warp, ntiles, cloop_, wclk_, clock64() - cstart_);
+#endif
 }
 
 inline size_t pcg2_smem_bytes(int A, int NS, int H) {
