@@ -78,6 +78,9 @@ SIGNATURES = {
     "dbl_links_download": (C.c_int, [vp, i32p, i32p]),
     "dbl_summary": (C.c_int, [vp, C.POINTER(SummaryHead), i64p, i64p, f64p]),
     "dbl_set_block_owners": (C.c_int, [vp, i32p]),
+    "dbl_block_sweep_begin": (C.c_int, [vp, C.c_int]),
+    "dbl_update_block": (C.c_int, [vp, C.c_int32]),
+    "dbl_block_sweep_end": (C.c_int, [vp]),
     "dbl_sweep_begin": (C.c_int, [vp, C.c_int, i64p, i64p]),
     "dbl_exchange_pack": (C.c_int, [vp, vp, vp]),
     "dbl_exchange_unpack": (C.c_int, [vp, vp, C.c_int64, vp, C.c_int64]),

@@ -533,6 +533,10 @@ __global__ void k_mark_ent_owned(int64_t E, const int *__restrict__ blk, const i
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e < E) ent_owned[e] = (owner[blk[e]] == rank);
 }
+__global__ void k_mark_ent_block(int64_t E, const int *__restrict__ blk, int block, unsigned char *__restrict__ ent_owned) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < E) ent_owned[e] = (blk[e] == block);
+}
 __global__ void k_mark_rec_owned(int64_t R, const int *__restrict__ link, const unsigned char *__restrict__ ent_owned,
                                  unsigned char *__restrict__ rec_owned) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -689,7 +693,10 @@ struct dbl_ctx {
   DevBuf<unsigned char> ent_owned, rec_owned;
   DevBuf<unsigned long long> move_cnt;  // [2*world] counts then [2*world] cursors
   std::vector<int64_t> h_move_ent, h_move_rec;
-  bool in_sweep = false;
+  bool in_sweep = false, in_block_sweep = false;
+  int block_sampler = 0;
+  std::vector<char> block_done;
+  DevBuf<int> blk_frozen;
 
   // layout
   DevBuf<int> iota, blk_sorted, ent_sorted, rec_key, rec_key_sorted, rec_sorted, ent_cnt, rec_cnt;
@@ -1284,18 +1291,23 @@ static int launch_link(dbl_ctx *ctx, int sampler, uint32_t it) {
 }
 
 // theta | summary -> links -> entity values -> N/blocks/distortions/summary of the shard owned by this rank
-static int sweep_local(dbl_ctx *ctx, int sampler) {
+// (1) theta | summary of the previous state (State.scala:83, GU:305-320) -- A*F scalars on the host
+static int draw_theta(dbl_ctx *ctx) {
   const int A = ctx->A, F = ctx->F;
   const uint32_t it = (uint32_t)(ctx->iteration + 1);
-  // (1) theta | summary of the previous state (State.scala:83, GU:305-320) -- A*F scalars on the host
-  {
-    std::vector<int64_t> agg((size_t)A * F);
-    for (int i = 0; i < A * F; ++i) agg[i] = ctx->h_counts[i];
-    host_draw_theta(A, F, ctx->alpha.data(), ctx->beta.data(), ctx->seed, agg.data(), ctx->file_sizes.data(), it,
-                    ctx->h_theta.data());
-    CUDA_TRY(cudaMemcpyAsync(ctx->theta.p, ctx->h_theta.data(), sizeof(double) * A * F, cudaMemcpyHostToDevice,
-                             ctx->stream));
-  }
+  std::vector<int64_t> agg((size_t)A * F);
+  for (int i = 0; i < A * F; ++i) agg[i] = ctx->h_counts[i];
+  host_draw_theta(A, F, ctx->alpha.data(), ctx->beta.data(), ctx->seed, agg.data(), ctx->file_sizes.data(), it,
+                  ctx->h_theta.data());
+  CUDA_TRY(cudaMemcpyAsync(ctx->theta.p, ctx->h_theta.data(), sizeof(double) * A * F, cudaMemcpyHostToDevice,
+                           ctx->stream));
+  return DBL_OK;
+}
+
+// (2)-(4) for the owned entities / records (all of them on an unsharded context): updatePartition, GU:156-211
+static int update_owned(dbl_ctx *ctx, int sampler, bool masked) {
+  const int A = ctx->A, F = ctx->F;
+  const uint32_t it = (uint32_t)(ctx->iteration + 1);
   // (2) links
   cudaEvent_t e0, e1;
   CUDA_TRY(cudaEventCreate(&e0));
@@ -1309,7 +1321,7 @@ static int sweep_local(dbl_ctx *ctx, int sampler) {
   ctx->pending_events.emplace_back(e0, e1);
   ctx->launches += 1;
   CUDA_TRY(cudaGetLastError());
-  if (ctx->world > 1) {  // the link kernel only writes records of owned blocks: keep the others as they were
+  if (masked) {  // the link kernel only writes records of owned blocks: keep the others as they were
     k_merge_links<<<grid_for(ctx->R, 256), 256, 0, ctx->stream>>>(ctx->R, ctx->rec_owned.p, ctx->link.p, ctx->newlink.p);
     ctx->launches += 1;
   }
@@ -1328,6 +1340,12 @@ static int sweep_local(dbl_ctx *ctx, int sampler) {
   return refresh_summary(ctx, true, sampler);
 }
 
+static int sweep_local(dbl_ctx *ctx, int sampler) {
+  int rc = draw_theta(ctx);
+  if (rc) return rc;
+  return update_owned(ctx, sampler, ctx->world > 1);
+}
+
 // (5) re-partition + summary fetch (also the sync point that bounds the sweep)
 static int sweep_finish(dbl_ctx *ctx) {
   int rc = relayout(ctx);
@@ -1341,6 +1359,7 @@ extern "C" int dbl_sweep(dbl_ctx *ctx, int sampler, int32_t n_sweeps) {
   if (sampler < 0 || sampler > 3 || n_sweeps < 0) { ctx->set_error("bad sampler / n_sweeps"); return DBL_ERR_INVALID; }
   if (!ctx->has_state) { ctx->set_error("dbl_sweep before dbl_state_init/upload"); return DBL_ERR_STATE; }
   if (ctx->world > 1) { ctx->set_error("dbl_sweep on a sharded context: use dbl_sweep_begin/exchange/end"); return DBL_ERR_STATE; }
+  if (ctx->in_sweep) { ctx->set_error("dbl_sweep inside an open sweep"); return DBL_ERR_STATE; }
   CUDA_TRY(cudaSetDevice(ctx->device));
   CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
   for (int s = 0; s < n_sweeps; ++s) {
@@ -1349,6 +1368,71 @@ extern "C" int dbl_sweep(dbl_ctx *ctx, int sampler, int32_t n_sweeps) {
     rc = sweep_finish(ctx);
     if (rc) return rc;
   }
+  CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+  CUDA_TRY(cudaEventSynchronize(ctx->ev1));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  ctx->last_sweep_ms = ms;
+  drain_link_events(ctx);
+  return DBL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// block-level entry points: one call per k-d-tree block, mirroring GibbsUpdates.updatePartition (GU:156-211)
+// ---------------------------------------------------------------------------------------------------
+extern "C" int dbl_block_sweep_begin(dbl_ctx *ctx, int sampler) {
+  if (!ctx) return DBL_ERR_INVALID;
+  if (sampler < 0 || sampler > 3) { ctx->set_error("bad sampler"); return DBL_ERR_INVALID; }
+  if (!ctx->has_state) { ctx->set_error("no state"); return DBL_ERR_STATE; }
+  if (ctx->world > 1) { ctx->set_error("block-level sweeps need an unsharded context"); return DBL_ERR_STATE; }
+  if (ctx->in_sweep) { ctx->set_error("a sweep is already open"); return DBL_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+  int rc = draw_theta(ctx);
+  if (rc) return rc;
+  // block membership is fixed for the whole sweep (the shuffle happens after every partition was updated, GU:144)
+  CUDA_TRY(ctx->blk_frozen.alloc(ctx->E));
+  CUDA_TRY(cudaMemcpyAsync(ctx->blk_frozen.p, ctx->blk.p, sizeof(int) * ctx->E, cudaMemcpyDeviceToDevice, ctx->stream));
+  ctx->block_done.assign(ctx->P, 0);
+  ctx->block_sampler = sampler;
+  ctx->in_sweep = true;
+  ctx->in_block_sweep = true;
+  return DBL_OK;
+}
+
+extern "C" int dbl_update_block(dbl_ctx *ctx, int32_t block_id) {
+  if (!ctx) return DBL_ERR_INVALID;
+  if (!ctx->in_block_sweep) { ctx->set_error("dbl_update_block outside dbl_block_sweep_begin/end"); return DBL_ERR_STATE; }
+  if (block_id < 0 || block_id >= ctx->P) { ctx->set_error("block id out of range"); return DBL_ERR_INVALID; }
+  if (ctx->block_done[block_id]) { ctx->set_error("block already updated in this sweep"); return DBL_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  k_mark_ent_block<<<grid_for(ctx->E, 256), 256, 0, ctx->stream>>>(ctx->E, ctx->blk_frozen.p, block_id, ctx->ent_owned.p);
+  k_mark_rec_owned<<<grid_for(ctx->R, 256), 256, 0, ctx->stream>>>(ctx->R, ctx->link.p, ctx->ent_owned.p,
+                                                                  ctx->rec_owned.p);
+  ctx->launches += 2;
+  int rc = relayout(ctx);  // tiles of this block only (everything else sorts into the dummy block)
+  if (rc) return rc;
+  rc = update_owned(ctx, ctx->block_sampler, true);
+  if (rc) return rc;
+  ctx->block_done[block_id] = 1;
+  return DBL_OK;
+}
+
+extern "C" int dbl_block_sweep_end(dbl_ctx *ctx) {
+  if (!ctx) return DBL_ERR_INVALID;
+  if (!ctx->in_block_sweep) { ctx->set_error("dbl_block_sweep_end without dbl_block_sweep_begin"); return DBL_ERR_STATE; }
+  for (int b = 0; b < ctx->P; ++b)
+    if (!ctx->block_done[b]) { ctx->set_error("dbl_block_sweep_end: not every block was updated"); return DBL_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  ctx->in_sweep = ctx->in_block_sweep = false;
+  CUDA_TRY(cudaMemsetAsync(ctx->ent_owned.p, 1, ctx->E, ctx->stream));
+  CUDA_TRY(cudaMemsetAsync(ctx->rec_owned.p, 1, ctx->R, ctx->stream));
+  int rc = build_links_csr(ctx);
+  if (rc) return rc;
+  rc = refresh_summary(ctx, false, 0);  // summary of the whole state (updateSummaryVariables, GU:219-301)
+  if (rc) return rc;
+  rc = sweep_finish(ctx);               // the shuffle: regroup by the new block ids
+  if (rc) return rc;
   CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
   CUDA_TRY(cudaEventSynchronize(ctx->ev1));
   float ms = 0.f;

@@ -323,6 +323,17 @@ class GibbsEngine:
         s = SAMPLERS[sampler] if isinstance(sampler, str) else int(sampler)
         _check(_lib.load().dbl_sweep(self._h, s, int(n)), "sweep", self._h)
 
+    def sweep_by_block(self, sampler="PCG-I", order=None):
+        """One application of State.nextState driven block by block, the way the reference runs one task per
+        partition (GibbsUpdates.updatePartition, GU:156-211).  `order` = the order the blocks are updated in
+        (default ascending); the resulting state does not depend on it."""
+        L = _lib.load()
+        s = SAMPLERS[sampler] if isinstance(sampler, str) else int(sampler)
+        _check(L.dbl_block_sweep_begin(self._h, s), "block_sweep_begin", self._h)
+        for b in (range(self.num_partitions) if order is None else order):
+            _check(L.dbl_update_block(self._h, int(b)), "update_block", self._h)
+        _check(L.dbl_block_sweep_end(self._h), "block_sweep_end", self._h)
+
     def summary(self):
         """SummaryVars (package.scala:116-119) of the current state + theta."""
         head = _lib.SummaryHead()

@@ -128,6 +128,17 @@ int64_t dbl_iteration(const dbl_ctx *);
  * updateSummaryVariables (GU:219-301).  Everything but the A x F Beta draws runs on the device. */
 int dbl_sweep(dbl_ctx *, int sampler, int32_t n_sweeps);
 
+/* The same transition one k-d-tree block at a time, mirroring the reference's per-partition task
+ * GibbsUpdates.updatePartition (GU:156-211), for call-for-call comparison with a CPU chain:
+ *   dbl_block_sweep_begin   updateDistProbs (GU:305-320): theta for the new iteration; block membership is frozen
+ *   dbl_update_block        link draws, entity values, distortions and new partition ids of ONE block (each block
+ *                           exactly once per sweep, in any order); rows of other blocks are not touched
+ *   dbl_block_sweep_end     the shuffle by new partition id (GU:144) + updateSummaryVariables (GU:219-301)
+ * begin + every block + end leaves exactly the state dbl_sweep(ctx, sampler, 1) leaves.  Unsharded contexts only. */
+int dbl_block_sweep_begin(dbl_ctx *, int sampler);
+int dbl_update_block(dbl_ctx *, int32_t block_id);
+int dbl_block_sweep_end(dbl_ctx *);
+
 /* Linkage structure for linkage-chain.parquet (State.getLinkageStructure, State.scala:102-112): record ->
  * entity links and each entity's current partition id. */
 int dbl_links_download(dbl_ctx *, int32_t *link_out /*R*/, int32_t *block_of_entity_out /*E*/);

@@ -201,3 +201,42 @@ def test_model_shapes(oracle, n_const, n_str):
         eng.sweep(sampler, 2)
         st.sweep(oracle.SAMPLERS[sampler], 2)
         assert_same_state(eng, st)
+
+
+@pytest.mark.parametrize("sampler", SAMPLERS)
+def test_sweep_block_by_block(oracle, sampler):
+    """dbl_block_sweep_begin / dbl_update_block / dbl_block_sweep_end (the reference's per-partition task,
+    GU:156-211): any block order gives the oracle's sweep; a block update only touches rows of that block."""
+    g = synth_problem(seed=17, R=1100, n_files=2)
+    eng, rc, x, file = product_setup(g, 7, 2, (2, 3))
+    m, st, tree, ox, ofile = oracle_setup(oracle, g, 7, 2, (2, 3))
+    P = eng.num_partitions
+    assert P == 4
+    rng = np.random.default_rng(0)
+    for it in range(4):
+        eng.sweep_by_block(sampler, order=rng.permutation(P))
+        assert st.sweep(oracle.SAMPLERS[sampler]) == 0
+        assert_same_state(eng, st)
+    # one block at a time: rows outside the block keep their values
+    from dblink_b200 import _lib
+    from dblink_b200.engine import SAMPLERS as S, _check
+    L = _lib.load()
+    before = eng.download_state()
+    _check(L.dbl_block_sweep_begin(eng._h, S[sampler]), "begin", eng._h)
+    assert L.dbl_sweep(eng._h, S[sampler], 1) != 0           # no whole-sweep call inside an open block sweep
+    _check(L.dbl_update_block(eng._h, 2), "update", eng._h)
+    assert L.dbl_update_block(eng._h, 2) != 0                 # each block once
+    assert L.dbl_update_block(eng._h, P) != 0
+    assert L.dbl_block_sweep_end(eng._h) != 0                 # not every block was updated
+    mid = eng.download_state()
+    ent_in = before["block"] == 2
+    rec_in = ent_in[before["link"]]
+    np.testing.assert_array_equal(mid["y"][~ent_in], before["y"][~ent_in])
+    np.testing.assert_array_equal(mid["link"][~rec_in], before["link"][~rec_in])
+    np.testing.assert_array_equal(mid["z"][~rec_in], before["z"][~rec_in])
+    assert ent_in[mid["link"][rec_in]].all()                   # links stay inside the block
+    for b in (3, 0, 1):
+        _check(L.dbl_update_block(eng._h, b), "update", eng._h)
+    _check(L.dbl_block_sweep_end(eng._h), "end", eng._h)
+    assert st.sweep(oracle.SAMPLERS[sampler]) == 0
+    assert_same_state(eng, st)
