@@ -115,7 +115,7 @@ void dbl_index::build_hash(int min_slots) {
   int maxlen = 0;
   for (int v = 0; v < V; ++v) maxlen = std::max(maxlen, rowptr[v + 1] - rowptr[v] - 1);
   int H = std::max(32, min_slots);
-  while (H < 2 * maxlen) H <<= 1;
+  while (H < maxlen) H <<= 1;  // a perfect hash needs H >= row length; the multiplier search below decides the rest
   for (; H <= 256; H <<= 1) {
     int lg = 0;
     while ((1 << lg) < H) ++lg;
