@@ -76,6 +76,7 @@ class ShardedGibbs:
         self.A, self.F = self.eng.A, self.eng.F
         self.owner = None
         self._ms = 0.0
+        self.trace = {}  # host wall-clock ms per phase of the sharded sweep, accumulated (rank-local)
 
     # ---- state ---------------------------------------------------------------------------------------
     def init_state(self, x, file_ids=None, population_size=0):
@@ -119,21 +120,32 @@ class ShardedGibbs:
         s = SAMPLERS[sampler] if isinstance(sampler, str) else int(sampler)
         W, ew = self.world, self.A + 1
         total_ms = 0.0
+        import time
+        tr = self.trace
         for _ in range(n):
             ec = np.zeros(W, np.int64)
             rc = np.zeros(W, np.int64)
+            t0 = time.perf_counter()
             _check(L.dbl_sweep_begin(h, s, _p(ec, _lib.i64p), _p(rc, _lib.i64p)), "sweep_begin", h)
+            t1 = time.perf_counter()
             send_ent = torch.empty(int(ec.sum()) * ew, dtype=torch.int32, device=self.device)
             send_rec = torch.empty(int(rc.sum()) * 3, dtype=torch.int32, device=self.device)
             _check(L.dbl_exchange_pack(h, send_ent.data_ptr() if send_ent.numel() else None,
                                        send_rec.data_ptr() if send_rec.numel() else None), "exchange_pack", h)
+            t2 = time.perf_counter()
             recv_ent, ne, recv_rec, nr = exchange(dist, send_ent, ec, send_rec, rc, ew, self.device, torch)
             torch.cuda.synchronize()
+            t3 = time.perf_counter()
             _check(L.dbl_exchange_unpack(h, recv_ent.data_ptr() if ne else None, ne,
                                          recv_rec.data_ptr() if nr else None, nr), "exchange_unpack", h)
             _check(L.dbl_sweep_end(h), "sweep_end", h)
+            t4 = time.perf_counter()
             total_ms += self.eng.last_sweep_ms()
             self._sync_summary()
+            t5 = time.perf_counter()
+            for k, v in (("begin", t1 - t0), ("pack", t2 - t1), ("exchange", t3 - t2), ("unpack_end", t4 - t3),
+                         ("summary", t5 - t4), ("sweeps", 1e-3)):
+                tr[k] = tr.get(k, 0.0) + v * 1e3
             self.last_exchange = (int(ec.sum()), int(rc.sum()))
         self._ms = total_ms
 
