@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cub/cub.cuh>
 #include <string>
@@ -703,7 +704,9 @@ struct dbl_ctx {
   DevBuf<int> ent_ptr, tile_ptr, rec_ptr, cta_ptr, cta_ptr2, tiles;
   // inverted index of the block tables for the pruned PCG-I link kernel (built on demand, once per sweep)
   DevBuf<unsigned long long> inv_key_in, inv_key;
-  DevBuf<int> inv_pos_in, inv_pos, inv_seg;
+  DevBuf<int> inv_pos_in, inv_pos, inv_seg, inv_vptr;
+  InvDense inv_dense;
+  bool inv_use_dense = false;
   DevBuf<unsigned char> inv_tmp;
   size_t inv_tmp_bytes = 0;
   bool inv_valid = false;
@@ -1225,10 +1228,24 @@ static int ensure_inverted_index(dbl_ctx *ctx) {
   CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->inv_tmp.p, tb, (const unsigned long long *)ctx->inv_key_in.p,
                                            ctx->inv_key.p, (const int *)ctx->inv_pos_in.p, ctx->inv_pos.p, (int)n, 0,
                                            std::min(64, nbits), ctx->stream));
-  const int n_groups = (ctx->P + 1) * ctx->A;
-  if (ctx->inv_seg.n != (size_t)n_groups + 1) CUDA_TRY(ctx->inv_seg.alloc((size_t)n_groups + 1));
-  k_inv_segments<<<grid_for(n + 1, 256), 256, 0, ctx->stream>>>(n, n_groups, ctx->inv_vbits, ctx->inv_key.p,
-                                                                ctx->inv_seg.p);
+  // dense (block, attribute, value) -> posting pointers when the table is small enough (P * sum of vocabulary
+  // sizes entries); otherwise (block, attribute) segment pointers + a binary search per record
+  InvDense &dn = ctx->inv_dense;
+  dn.A = ctx->A; dn.vbits = ctx->inv_vbits; dn.sumV = 0;
+  for (int k = 0; k < ctx->A; ++k) { dn.voff[k] = dn.sumV; dn.sumV += ctx->h_attrs[ctx->perm[k]].V; }
+  const long long n_ids = (long long)ctx->P * dn.sumV;
+  long long dense_max = 1ll << 25;  // entries; DBL_INV_DENSE_MAX overrides (tests force the binary-search path with 0)
+  if (const char *ev = getenv("DBL_INV_DENSE_MAX")) dense_max = atoll(ev);
+  ctx->inv_use_dense = n_ids <= dense_max;
+  if (ctx->inv_use_dense) {
+    if (ctx->inv_vptr.n != (size_t)n_ids + 1) CUDA_TRY(ctx->inv_vptr.alloc((size_t)n_ids + 1));
+    k_inv_value_ptr<<<grid_for(n + 1, 256), 256, 0, ctx->stream>>>(n, n_ids, dn, ctx->inv_key.p, ctx->inv_vptr.p);
+  } else {
+    const int n_groups = (ctx->P + 1) * ctx->A;
+    if (ctx->inv_seg.n != (size_t)n_groups + 1) CUDA_TRY(ctx->inv_seg.alloc((size_t)n_groups + 1));
+    k_inv_segments<<<grid_for(n + 1, 256), 256, 0, ctx->stream>>>(n, n_groups, ctx->inv_vbits, ctx->inv_key.p,
+                                                                  ctx->inv_seg.p);
+  }
   ctx->launches += 5;
   ctx->inv_valid = true;
   CUDA_TRY(cudaGetLastError());
@@ -1272,6 +1289,9 @@ static int launch_link(dbl_ctx *ctx, int sampler, uint32_t it) {
     pp.R = ctx->R;
     pp.vbits = ctx->inv_vbits;
     pp.inv_seg = ctx->inv_seg.p;
+    pp.inv_vptr = ctx->inv_use_dense ? ctx->inv_vptr.p : nullptr;
+    pp.sumV = ctx->inv_dense.sumV;
+    for (int k = 0; k < A; ++k) pp.voff[k] = ctx->inv_dense.voff[k];
     k_link_pruned<<<grid_for(ctx->R, LINK_WARPS), LINK_WARPS * 32, 0, ctx->stream>>>(pp);
     return DBL_OK;
   }

@@ -534,6 +534,28 @@ __global__ void k_inv_segments(int64_t n, int n_groups, int vbits, const unsigne
   for (int g = prev + 1; g <= cur; ++g) seg[g] = (int)i;
 }
 
+// vptr[(block * sumV) + voff[kernel attribute] + value] = first index entry of that (block, attribute, value); the
+// table is dense (values without entities get an empty range), so a record finds a posting list with two loads
+struct InvDense {
+  int A, sumV, vbits;
+  int voff[DBL_MAX_ATTRS];
+};
+__global__ void k_inv_value_ptr(int64_t n, long long n_ids, InvDense d, const unsigned long long *__restrict__ key,
+                                int *__restrict__ vptr) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  auto dense = [&](unsigned long long k) -> long long {
+    const unsigned long long g = k >> d.vbits;
+    const long long b = (long long)(g / (unsigned)d.A);
+    const int a = (int)(g % (unsigned)d.A);
+    const long long id = b * d.sumV + d.voff[a] + (long long)(k & ((1ull << d.vbits) - 1ull));
+    return id < n_ids ? id : n_ids;  // the dummy block (rows of other ranks) is not addressable
+  };
+  const long long cur = (i < n) ? dense(key[i]) : n_ids;
+  const long long prev = (i > 0) ? dense(key[i - 1]) : -1;
+  for (long long g = prev + 1; g <= cur; ++g) vptr[g] = (int)i;
+}
+
 __device__ __forceinline__ int64_t inv_lower_bound(const unsigned long long *__restrict__ key, int64_t lo, int64_t hi,
                                                    unsigned long long want) {
   while (lo < hi) {
@@ -550,6 +572,9 @@ struct PrunedParams {
   long long inv_n;
   long long R;
   int vbits;
+  const int *inv_vptr;  // dense (block, attribute, value) -> first entry; nullptr: binary search inside inv_seg
+  int sumV;
+  int voff[DBL_MAX_ATTRS];
   const int *inv_seg;  // (P+1)*A + 1 group offsets
 };
 
@@ -585,12 +610,18 @@ __global__ void __launch_bounds__(LINK_WARPS * 32) k_link_pruned(PrunedParams pp
       ra[lane] = c;
       mm = (c.kind == 4);
       if (mm) {
-        const unsigned long long base = (unsigned long long)((unsigned)b * (unsigned)A + (unsigned)lane) << pp.vbits;
-        const int g = b * A + lane;
-        const long long s0 = pp.inv_seg[g], s1 = pp.inv_seg[g + 1];  // the E_b entries of (block, attribute)
-        lo = inv_lower_bound(pp.inv_key, s0, s1, base | (unsigned)c.x);
-        const long long hi = inv_lower_bound(pp.inv_key, lo, s1, base | ((unsigned)c.x + 1u));
-        len = hi - lo;
+        if (pp.inv_vptr) {
+          const long long id = (long long)b * pp.sumV + pp.voff[lane] + c.x;
+          lo = pp.inv_vptr[id];
+          len = pp.inv_vptr[id + 1] - lo;
+        } else {
+          const unsigned long long base = (unsigned long long)((unsigned)b * (unsigned)A + (unsigned)lane) << pp.vbits;
+          const int g = b * A + lane;
+          const long long s0 = pp.inv_seg[g], s1 = pp.inv_seg[g + 1];  // the E_b entries of (block, attribute)
+          lo = inv_lower_bound(pp.inv_key, s0, s1, base | (unsigned)c.x);
+          const long long hi = inv_lower_bound(pp.inv_key, lo, s1, base | ((unsigned)c.x + 1u));
+          len = hi - lo;
+        }
       }
     }
     const unsigned mmask = __ballot_sync(FULL, mm);

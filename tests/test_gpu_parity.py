@@ -240,3 +240,16 @@ def test_sweep_block_by_block(oracle, sampler):
     _check(L.dbl_block_sweep_end(eng._h), "end", eng._h)
     assert st.sweep(oracle.SAMPLERS[sampler]) == 0
     assert_same_state(eng, st)
+
+
+def test_pruned_link_update_without_dense_pointers(oracle, monkeypatch):
+    """PCG-I with the (block, attribute, value) pointer table disabled: posting lists found by binary search inside
+    the (block, attribute) segments; same draws."""
+    monkeypatch.setenv("DBL_INV_DENSE_MAX", "0")
+    g = synth_problem(seed=21, R=1000, n_files=2)
+    eng, rc, x, file = product_setup(g, 5, 2, (2, 3))
+    m, st, tree, ox, ofile = oracle_setup(oracle, g, 5, 2, (2, 3))
+    for it in range(4):
+        eng.sweep("PCG-I", 1)
+        assert st.sweep(oracle.SAMPLERS["PCG-I"]) == 0
+        assert_same_state(eng, st)
