@@ -332,6 +332,51 @@ __global__ void k_values(ValParams p) {
   base_init(b, at, k);  // GU:584-586
   double total = 0.0, target = 0.0, cum = 0.0;
   int picked = -1, last_pos = -1;
+  if (hi - lo == 1) {
+    // one linked record (most entities): the candidate values are the record's own similarity row, so the factors
+    // come straight from that row (no searches, no first-appearance check); same operations as the general path
+    const int r = rec[lo];
+    const int xr = p.x[(int64_t)r * p.A + a];  // observed (k == 1)
+    const int q0 = at.is_const ? 0 : at.rowptr[xr];
+    const int nv = at.is_const ? 1 : (at.rowptr[xr + 1] - q0);
+    double extra = 0.0;  // what the collapsed update adds to the factor of v == x (GU:553,557,560)
+    if (collapsed) {
+      const double th = p.theta[a * p.F + p.file[r]];
+      extra = at.is_const ? (1.0 / th - 1.0) / at.phi[xr] : (1.0 / th - 1.0) / (at.phi[xr] * at.norm[xr]);
+    }
+    auto weight = [&](int q, int &v) -> double {
+      double G = 1.0;
+      if (at.is_const) {
+        v = xr;
+        if (collapsed) G = G * (1.0 + extra);
+      } else {
+        v = at.col[q0 + q];
+        const double e = at.expsim[q0 + q];
+        G = G * ((collapsed && v == xr) ? e + extra : e);
+      }
+      return base_prob(b, v) * (G - 1.0);  // GU:567 / 724
+    };
+    for (int q = 0; q < nv; ++q) {
+      int v;
+      total += weight(q, v);
+    }
+    if (u.u0 < 1.0 / (1.0 + total)) {  // GU:593-594
+      p.y[tid] = base_draw(b, u.u1);
+      return;
+    }
+    target = u.u1 * total;
+    for (int q = 0; q < nv && picked < 0; ++q) {
+      int v;
+      const double W = weight(q, v);
+      cum += W;
+      if (W > 0.0) last_pos = v;
+      if (cum > target) picked = v;
+    }
+    if (picked < 0) picked = last_pos;
+    if (picked < 0) picked = base_draw(b, u.u1);
+    p.y[tid] = picked;
+    return;
+  }
   for (int pass = 0; pass < 2; ++pass) {
     for (int i = lo; i < hi; ++i) {
       const int r = rec[i];
