@@ -1334,6 +1334,8 @@ static int launch_link(dbl_ctx *ctx, int sampler, uint32_t it) {
     pp.R = ctx->R;
     pp.vbits = ctx->inv_vbits;
     pp.inv_seg = ctx->inv_seg.p;
+    pp.rec_key_sorted = ctx->rec_key_sorted.p;
+    pp.rec_key_shift = REC_CLASS_BITS;
     pp.inv_vptr = ctx->inv_use_dense ? ctx->inv_vptr.p : nullptr;
     pp.sumV = ctx->inv_dense.sumV;
     for (int k = 0; k < A; ++k) pp.voff[k] = ctx->inv_dense.voff[k];

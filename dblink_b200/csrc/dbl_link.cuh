@@ -572,6 +572,8 @@ struct PrunedParams {
   long long inv_n;
   long long R;
   int vbits;
+  const int *rec_key_sorted;  // block-major sort key of rec_sorted[i]
+  int rec_key_shift;
   const int *inv_vptr;  // dense (block, attribute, value) -> first entry; nullptr: binary search inside inv_seg
   int sumV;
   int voff[DBL_MAX_ATTRS];
@@ -590,7 +592,7 @@ __global__ void __launch_bounds__(LINK_WARPS * 32) k_link_pruned(PrunedParams pp
   const long long ridx = (long long)blockIdx.x * LINK_WARPS + warp;
   if (ridx >= p.rec_ptr[p.P]) return;  // records of blocks this rank owns come first in rec_sorted
   const int r = p.rec_sorted[ridx];
-  const int b = p.blk_of_link ? p.blk_of_link[p.link[r]] : 0;
+  const int b = pp.rec_key_sorted[ridx] >> pp.rec_key_shift;  // the sort key of the record: block id above the cost class
   const int A = p.A;
   const int n = p.ent_ptr[b + 1] - p.ent_ptr[b];
   const int ntiles = p.tile_ptr[b + 1] - p.tile_ptr[b];
@@ -699,8 +701,13 @@ __global__ void __launch_bounds__(LINK_WARPS * 32) k_link_pruned(PrunedParams pp
       ++ns;
     }
   }
-  close_chunks_until(nchunks);
   __syncwarp();
+  if (ns == 1) {  // a single candidate with positive weight is drawn whatever the uniform is: skip the search
+    if (isinf(s_sw[warp][0])) { fail_link(p, lane, r); return; }
+    store_link(p, lane, r, b, n, s_sj[warp][0]);
+    return;
+  }
+  close_chunks_until(nchunks);
   if (!(run > 0.0) || isinf(run)) { fail_link(p, lane, r); return; }
 
   // ---- pass 2: the same walk restricted to the chosen chunk
