@@ -685,20 +685,52 @@ __global__ void __launch_bounds__(LINK_WARPS * 32) k_link_pruned(PrunedParams pp
     }
   };
   int ns = 0;  // survivors seen (stored while they fit)
-  for (long long g = plo; g < phi; g += 32) {
-    int j;
-    const double w = cand_weight(g + lane, j);
-    unsigned live = __ballot_sync(FULL, w > 0.0);
-    while (live) {
-      const int i = __ffs(live) - 1;
-      live &= live - 1;
-      const int ji = __shfl_sync(FULL, j, i);
-      const double wi = shfl_d(w, i);
-      close_chunks_until(ji / cand_per_chunk);
-      if (lane == (ji & 31)) s = s + wi;
-      dirty = true;
-      if (ns < SCAP && lane == 0) { s_sj[warp][ns] = ji; s_sw[warp][ns] = wi; }
-      ++ns;
+  auto add_survivor = [&](int ji, double wi) {
+    close_chunks_until(ji / cand_per_chunk);
+    if (lane == (ji & 31)) s = s + wi;
+    dirty = true;
+    if (ns < SCAP && lane == 0) { s_sj[warp][ns] = ji; s_sw[warp][ns] = wi; }
+    ++ns;
+  };
+  if (nmm > 1) {
+    // every lane tests its posting against ONE other must-match attribute; the few that pass are then checked
+    // by the whole warp, one attribute per lane, so a survivor costs one more load instead of a chain of them
+    int k1 = (mma[0] != best) ? 0 : 1;
+    const int a1 = mma[k1], x1 = mmx[k1];
+    for (long long g = plo; g < phi; g += 32) {
+      const long long idx = g + lane;
+      int j = -1;
+      bool pass = false;
+      if (idx < phi) {
+        j = pp.inv_pos[idx];
+        pass = (gtiles[(size_t)(j / TE) * TW + a1 * TE + (j % TE)] == x1);
+      }
+      unsigned live = __ballot_sync(FULL, pass);
+      while (live) {
+        const int i = __ffs(live) - 1;
+        live &= live - 1;
+        const int ji = __shfl_sync(FULL, j, i);
+        const int *tile = gtiles + (size_t)(ji / TE) * TW;
+        const int slot = ji % TE;
+        bool okl = true;
+        if (lane < nmm && mma[lane] != best) okl = (tile[mma[lane] * TE + slot] == mmx[lane]);
+        if (!__all_sync(FULL, okl)) continue;
+        const double wi = has_sim ? generic_weight(ra, A, false, tile + slot,
+                                                   reinterpret_cast<const double *>(tile + (size_t)A * TE)[slot])
+                                  : 1.0;  // GU:408-411: uniform over the candidates
+        if (wi > 0.0) add_survivor(ji, wi);
+      }
+    }
+  } else {
+    for (long long g = plo; g < phi; g += 32) {
+      int j;
+      const double w = cand_weight(g + lane, j);
+      unsigned live = __ballot_sync(FULL, w > 0.0);
+      while (live) {
+        const int i = __ffs(live) - 1;
+        live &= live - 1;
+        add_survivor(__shfl_sync(FULL, j, i), shfl_d(w, i));
+      }
     }
   }
   __syncwarp();
