@@ -770,6 +770,7 @@ struct dbl_ctx {
   std::vector<long long> h_counts;
   double h_loglik_part = 0.0;
   int64_t h_pairs = 0;
+  int h_owned_ent = -1;  // entities in the blocks this rank owns (= ent_ptr[P]) after the last relayout; -1 = unknown
 
   int64_t launches = 0;
   double link_ms = 0.0;
@@ -1058,6 +1059,7 @@ static int relayout(dbl_ctx *ctx) {
                                                            ctx->tiles.p, ctx->perm_dev.p, P);
   ctx->launches += 11;
   ctx->inv_valid = false;
+  ctx->h_owned_ent = -1;  // ent_ptr[P] changed; fetch_summary (or the index build) reads it back
   CUDA_TRY(cudaGetLastError());
   return DBL_OK;
 }
@@ -1091,8 +1093,11 @@ static int fetch_summary(dbl_ctx *ctx) {
   CUDA_TRY(cudaMemcpyAsync(&st, ctx->status.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   unsigned long long pr = 0;
   CUDA_TRY(cudaMemcpyAsync(&pr, ctx->pairs.p, sizeof(pr), cudaMemcpyDeviceToHost, ctx->stream));
+  int owned = -1;
+  if (ctx->ent_ptr.p) CUDA_TRY(cudaMemcpyAsync(&owned, ctx->ent_ptr.p + ctx->P, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   ctx->h_pairs = (int64_t)pr;
+  ctx->h_owned_ent = owned;
   if (st) {
     ctx->set_error("zero probability mass in a link draw");
     cudaMemsetAsync(ctx->status.p, 0, sizeof(int), ctx->stream);
@@ -1248,16 +1253,22 @@ DBL_DECL(9) DBL_DECL(10) DBL_DECL(11) DBL_DECL(12) DBL_DECL(13) DBL_DECL(14) DBL
 // (block, attribute, value) -> candidate positions, for k_link_pruned
 static int ensure_inverted_index(dbl_ctx *ctx) {
   if (ctx->inv_valid) return DBL_OK;
-  const int64_t n = ctx->E * ctx->A;
-  if (n > 0x7fffffff) { ctx->set_error("inverted index too large"); return DBL_ERR_INVALID; }
-  if (ctx->inv_key.n != (size_t)n) {
-    CUDA_TRY(ctx->inv_key_in.alloc(n));
-    CUDA_TRY(ctx->inv_key.alloc(n));
-    CUDA_TRY(ctx->inv_pos_in.alloc(n));
-    CUDA_TRY(ctx->inv_pos.alloc(n));
+  const int64_t cap = ctx->E * ctx->A;
+  if (cap > 0x7fffffff) { ctx->set_error("inverted index too large"); return DBL_ERR_INVALID; }
+  if (ctx->h_owned_ent < 0) {  // relayout without a summary fetch since (block-level sweeps)
+    CUDA_TRY(cudaMemcpyAsync(&ctx->h_owned_ent, ctx->ent_ptr.p + ctx->P, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  // only the entities of owned blocks are indexed: they come first in ent_sorted
+  const int64_t n = (int64_t)ctx->h_owned_ent * ctx->A;
+  if (ctx->inv_key.n != (size_t)cap) {
+    CUDA_TRY(ctx->inv_key_in.alloc(cap));
+    CUDA_TRY(ctx->inv_key.alloc(cap));
+    CUDA_TRY(ctx->inv_pos_in.alloc(cap));
+    CUDA_TRY(ctx->inv_pos.alloc(cap));
     size_t tb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
-                                    (const int *)nullptr, (int *)nullptr, (int)n, 0, 64, ctx->stream);
+                                    (const int *)nullptr, (int *)nullptr, (int)cap, 0, 64, ctx->stream);
     ctx->inv_tmp_bytes = tb + 256;
     CUDA_TRY(ctx->inv_tmp.alloc(ctx->inv_tmp_bytes));
   }
@@ -1265,14 +1276,17 @@ static int ensure_inverted_index(dbl_ctx *ctx) {
   for (int a = 0; a < ctx->A; ++a) vmax = std::max(vmax, ctx->h_attrs[a].V);
   ctx->inv_vbits = bits_for(vmax + 1);
   const int nbits = ctx->inv_vbits + bits_for((int64_t)(ctx->P + 1) * ctx->A);
-  k_inv_keys<<<grid_for(n, 256), 256, 0, ctx->stream>>>(ctx->E, ctx->A, ctx->P, ctx->inv_vbits, ctx->y.p,
-                                                        ctx->blk_sorted.p, ctx->ent_sorted.p, ctx->ent_ptr.p,
-                                                        ctx->perm_dev.p, ctx->inv_key_in.p, ctx->inv_pos_in.p);
-  size_t tb = ctx->inv_tmp_bytes;
-  // stable radix sort on the significant bits only: positions stay ascending inside a key
-  CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->inv_tmp.p, tb, (const unsigned long long *)ctx->inv_key_in.p,
-                                           ctx->inv_key.p, (const int *)ctx->inv_pos_in.p, ctx->inv_pos.p, (int)n, 0,
-                                           std::min(64, nbits), ctx->stream));
+  if (n > 0) {
+    k_inv_keys<<<grid_for(n, 256), 256, 0, ctx->stream>>>((int64_t)ctx->h_owned_ent, ctx->A, ctx->P, ctx->inv_vbits,
+                                                          ctx->y.p, ctx->blk_sorted.p, ctx->ent_sorted.p,
+                                                          ctx->ent_ptr.p, ctx->perm_dev.p, ctx->inv_key_in.p,
+                                                          ctx->inv_pos_in.p);
+    size_t tb = ctx->inv_tmp_bytes;
+    // stable radix sort on the significant bits only: positions stay ascending inside a key
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->inv_tmp.p, tb, (const unsigned long long *)ctx->inv_key_in.p,
+                                             ctx->inv_key.p, (const int *)ctx->inv_pos_in.p, ctx->inv_pos.p, (int)n,
+                                             0, std::min(64, nbits), ctx->stream));
+  }
   // dense (block, attribute, value) -> posting pointers when the table is small enough (P * sum of vocabulary
   // sizes entries); otherwise (block, attribute) segment pointers + a binary search per record
   InvDense &dn = ctx->inv_dense;
@@ -1330,7 +1344,7 @@ static int launch_link(dbl_ctx *ctx, int sampler, uint32_t it) {
     pp.lp = lp;
     pp.inv_key = ctx->inv_key.p;
     pp.inv_pos = ctx->inv_pos.p;
-    pp.inv_n = ctx->E * ctx->A;
+    pp.inv_n = (long long)ctx->h_owned_ent * ctx->A;
     pp.R = ctx->R;
     pp.vbits = ctx->inv_vbits;
     pp.inv_seg = ctx->inv_seg.p;
