@@ -195,11 +195,11 @@ __global__ void k_block_scan(int P, const int *__restrict__ ent_ptr, const int *
     tile_ptr[P] = t; cta_ptr[P] = c; cta_ptr2[P] = c2;
   }
 }
-// tiled, block-sorted copy of the entity table: tile = { int32 y[A][TE]; double N[TE] }
+// tiled, block-sorted copy of the entity table: tile = { int32 y[A][TE]; double N[TE]; uint32 packed_consts[TE] }
 __global__ void k_build_tiles(int64_t E, int A, const int *__restrict__ y, const double *__restrict__ entN,
                               const int *__restrict__ blk_sorted, const int *__restrict__ ent_sorted,
                               const int *__restrict__ ent_ptr, const int *__restrict__ tile_ptr,
-                              int *__restrict__ tiles, const int *__restrict__ perm, int P) {
+                              int *__restrict__ tiles, const int *__restrict__ perm, int P, int npack) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= E) return;
   const int b = blk_sorted[i];
@@ -210,6 +210,9 @@ __global__ void k_build_tiles(int64_t E, int A, const int *__restrict__ y, const
   const int slot = j % TE;
   for (int k = 0; k < A; ++k) tile[k * TE + slot] = y[(int64_t)e * A + perm[k]];  // kernel order
   reinterpret_cast<double *>(tile + (size_t)A * TE)[slot] = entN[e];
+  unsigned pk = 0;  // constant attributes (kernel positions 0..npack-1), one byte each, for k_link_pcg2
+  for (int k = 0; k < npack; ++k) pk |= ((unsigned)y[(int64_t)e * A + perm[k]] & 0xFFu) << (8 * k);
+  tile[(size_t)(A + 2) * TE + slot] = (int)pk;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -717,6 +720,7 @@ struct dbl_ctx {
   DevBuf<int> perm_dev;
   int perm[DBL_MAX_ATTRS] = {0};
   int n_str = 0;       // non-constant attributes
+  int pack_consts = 0; // constant attributes byte-packed into the tiles (0 = none)
   int hslots = 32, hshift = 27;  // common hash-table size of the non-constant attributes; hslots = 0: none
   std::vector<AttrDev> h_attrs;
   DevBuf<int> tree_buf;
@@ -883,6 +887,10 @@ static int upload_model(dbl_ctx *ctx, const dbl_model_desc *d) {
     int k = 0;
     for (int a = 0; a < A; ++a) if (ctx->h_attrs[a].is_const) ctx->perm[k++] = a;
     ctx->n_str = A - k;
+    // byte-packed copy of the constant attributes in the tiles (k_link_pcg2): 1..4 of them, every vocabulary <= 255
+    ctx->pack_consts = (k >= 1 && k <= 4) ? k : 0;
+    for (int q = 0; q < k; ++q) if (ctx->h_attrs[ctx->perm[q]].V > 255) ctx->pack_consts = 0;
+    if (getenv("DBL_NO_PACK")) ctx->pack_consts = 0;  // tests: the unpacked kernels on a packable model
     for (int a = 0; a < A; ++a) if (!ctx->h_attrs[a].is_const) ctx->perm[k++] = a;
     ctx->hslots = hash_ok ? Hmax : 0;
     ctx->hshift = 32;
@@ -1056,7 +1064,7 @@ static int relayout(dbl_ctx *ctx) {
   CUDA_TRY(cudaMemsetAsync(ctx->tiles.p, 0, ctx->tiles.n * sizeof(int), ctx->stream));
   k_build_tiles<<<grid_for(E, 256), 256, 0, ctx->stream>>>(E, A, ctx->y.p, ctx->entN.p, ctx->blk_sorted.p,
                                                            ctx->ent_sorted.p, ctx->ent_ptr.p, ctx->tile_ptr.p,
-                                                           ctx->tiles.p, ctx->perm_dev.p, P);
+                                                           ctx->tiles.p, ctx->perm_dev.p, P, ctx->pack_consts);
   ctx->launches += 11;
   ctx->inv_valid = false;
   ctx->h_owned_ent = -1;  // ent_ptr[P] changed; fetch_summary (or the index build) reads it back
@@ -1322,6 +1330,7 @@ static int launch_link(dbl_ctx *ctx, int sampler, uint32_t it) {
   lp.tiles = ctx->tiles.p; lp.newlink = ctx->newlink.p; lp.status = ctx->status.p; lp.pairs = ctx->pairs.p;
   for (int k = 0; k < A; ++k) lp.perm[k] = ctx->perm[k];
   lp.blk_of_link = ctx->blk.p;
+  lp.pack_consts = ctx->pack_consts;
   const size_t ring = (size_t)LINK_STAGES * tile_words(A) * 4 + 128;
   const int mode = ctx->link_mode;  // 0 auto, 1 force generic
   lp.hslots = ctx->hslots; lp.hshift = ctx->hshift;

@@ -25,7 +25,8 @@ constexpr int LINK_STAGES = 4;   // tile ring depth (8 measured: no gain)
 constexpr int LINK_MAX_UNROLL_A = 16;
 constexpr unsigned FULL = 0xffffffffu;
 
-__host__ __device__ inline size_t tile_words(int A) { return (size_t)A * TE + 2 * TE; }  // int32 words per tile
+// int32 words per tile: A value rows, the f64 row N(e), one row of byte-packed constant attributes (k_link_pcg2)
+__host__ __device__ inline size_t tile_words(int A) { return (size_t)A * TE + 3 * TE; }
 
 struct AttrDev {
   int V, is_const, kmax, hsize;
@@ -51,6 +52,7 @@ struct LinkParams {
   // "kernel order" of the attributes: constant attributes first, then the others, each group in ascending
   // attribute id.  Tiles, per-record constants and the multiplication order of the protocol use this order.
   int perm[DBL_MAX_ATTRS];
+  int pack_consts;         // tiles carry the byte-packed constant attributes (1..4 of them, vocabularies <= 255)
   const int *blk_of_link;  // block id of every entity (k_link_pruned: block of a record = block of its entity)
   int hslots, hshift;  // common size of the per-row similarity hash tables (k_link_pcg2); 0 = unavailable
 };
@@ -212,11 +214,12 @@ __device__ __forceinline__ bool rec_row_find(const RecAttr &c, int yv, double &e
 __device__ __forceinline__ double generic_weight(const RecAttr *ra, int A, bool pcg2, const int *ycol, double N) {
   double w;
   if (pcg2) {
-    w = N;
-    for (int a = 0; a < A; ++a) {
-      const int k = ra[a].kind;
-      if ((k == 1 || k == 2) && ycol[a * TE] == ra[a].x) w = w * ra[a].rmatch;
-    }
+    double c = 1.0;  // the constant attributes form their own product (a table look-up in k_link_pcg2)
+    for (int a = 0; a < A; ++a)
+      if (ra[a].kind == 1 && ycol[a * TE] == ra[a].x) c = c * ra[a].rmatch;
+    w = N * c;
+    for (int a = 0; a < A; ++a)
+      if (ra[a].kind == 2 && ycol[a * TE] == ra[a].x) w = w * ra[a].rmatch;
     for (int a = 0; a < A; ++a) {
       if (ra[a].kind != 2) continue;
       const int yv = ycol[a * TE];

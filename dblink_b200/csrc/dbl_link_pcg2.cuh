@@ -25,19 +25,41 @@ struct Pcg2Rec {
   double rm[A];                  // multiplier on an exact match
   unsigned hm[NS > 0 ? NS : 1];  // hash multipliers of the non-constant attributes
   unsigned mmask;                // missing non-constant attributes (bit = kernel position)
+  unsigned xpack;                // PK: the record's constant-attribute values, one byte each (0xFF = cannot match)
 };
+
+// PK kernels: index into the record's table of constant-attribute products from the byte-packed values of a
+// candidate: bit k of the index = (byte k of ypack == byte k of xpack)
+__device__ __forceinline__ unsigned pcg2_const_index(unsigned ypack, unsigned xpack) {
+  const unsigned d = ypack ^ xpack;
+  const unsigned nz = ((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d;  // bit 7 of a byte set <=> the byte of d is non-zero
+  const unsigned eq = (~nz & 0x80808080u) >> 7;               // bit 8k set <=> byte k equal
+  return (eq * 0x01020408u) >> 24;                            // gathers bits 0, 8, 16, 24 into bits 0..3
+}
 
 // CONVERGED: every lane of the warp executes the call (main loop), so the rare similar-value multiply is skipped
 // warp-wide with a vote; pass 2 calls it under divergence and must not vote.
-template <int A, int NS, int HC, bool CONVERGED>
+// PK: the A - NS constant attributes (1..4 of them, vocabularies <= 255) travel as one byte-packed word per
+// candidate (ypack) and their product comes from the record's 16-entry table ctab; otherwise y[0..A-NS) are used.
+template <int A, int NS, int HC, bool CONVERGED, bool PK>
 __device__ __forceinline__ double pcg2_weight(const Pcg2Rec<A, NS> &rc, const LinkParams &p, const char *tab,
-                                              const int *y, double N) {
+                                              const double *ctab, const int *y, unsigned ypack, double N) {
   const int hslots = HC ? HC : p.hslots;
   const int hshift = HC ? 27 : p.hshift;
   const int tabb = pcg2_tab_bytes(hslots);
   double w = N;
+  if constexpr (NS < A) {  // protocol 4.1: the constant attributes form their own product c; w = N * c
+    double c = 1.0;
+    if constexpr (PK) {
+      c = ctab[pcg2_const_index(ypack, rc.xpack)];
+    } else {
 #pragma unroll
-  for (int k = 0; k < A; ++k) mul_if_eq(w, y[k], rc.x[k], rc.rm[k]);
+      for (int k = 0; k < A - NS; ++k) mul_if_eq(c, y[k], rc.x[k], rc.rm[k]);
+    }
+    w = w * c;
+  }
+#pragma unroll
+  for (int k = A - NS; k < A; ++k) mul_if_eq(w, y[k], rc.x[k], rc.rm[k]);
   if (CONVERGED) {
     // probe all NS tables first (no control flow), then ONE vote: the multiply by a similarity is rare
     bool hit[NS > 0 ? NS : 1];
@@ -75,7 +97,7 @@ __device__ __forceinline__ double pcg2_weight(const Pcg2Rec<A, NS> &rc, const Li
   return w;
 }
 
-template <int A, int NS, int HC>
+template <int A, int NS, int HC, bool PK>
 __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int cta = blockIdx.x;
@@ -84,7 +106,8 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkPara
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = p.ent_ptr[b + 1] - p.ent_ptr[b];
   const int ntiles = p.tile_ptr[b + 1] - p.tile_ptr[b];
-  constexpr int TW = A * TE + 2 * TE;
+  constexpr int TW = A * TE + 3 * TE;  // tile_words(A)
+  constexpr int NC = A - NS;
   TileRing rg;
   rg.tiles = reinterpret_cast<int *>(smem);
   rg.full = reinterpret_cast<uint64_t *>(smem + (size_t)LINK_STAGES * TW * 4);
@@ -93,6 +116,9 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkPara
   static_assert(2 * LINK_STAGES * 8 <= 128, "barrier area");
   char *tab = reinterpret_cast<char *>(smem) + (size_t)LINK_STAGES * TW * 4 + 128 +
               (size_t)warp * (NS > 0 ? NS : 1) * pcg2_tab_bytes(HC ? HC : p.hslots);
+  double *ctab = reinterpret_cast<double *>(reinterpret_cast<char *>(smem) + (size_t)LINK_STAGES * TW * 4 + 128 +
+                                           (size_t)LINK_WARPS * (NS > 0 ? NS : 1) * pcg2_tab_bytes(HC ? HC : p.hslots)) +
+                 warp * 16;  // PK: products of the matching constant attributes, by match mask
   const int *gtiles = p.tiles + (size_t)p.tile_ptr[b] * TW;
   ring_init(rg, LINK_WARPS);
 
@@ -153,6 +179,20 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkPara
         vd[i] = (xq >= 0) ? at.hvals[(size_t)xq * H + i] : 1.0;
       }
     }
+    rc.xpack = 0xFFFFFFFFu;
+    if constexpr (PK) {
+      static_assert(!PK || (NC >= 1 && NC <= 4), "PK packs 1..4 constant attributes");
+#pragma unroll
+      for (int k = 0; k < NC; ++k)
+        rc.xpack = (rc.xpack & ~(0xFFu << (8 * k))) | ((unsigned)(rc.x[k] < 0 ? 0xFF : rc.x[k]) << (8 * k));
+      if (lane < 16) {
+        double c = 1.0;
+#pragma unroll
+        for (int k = 0; k < NC; ++k)
+          if ((lane >> k) & 1) c = c * rc.rm[k];
+        ctab[lane] = c;
+      }
+    }
     __syncwarp();
   }
 
@@ -185,8 +225,9 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkPara
         const int slot = q * 32 + lane;
         int y[A];
 #pragma unroll
-        for (int k = 0; k < A; ++k) y[k] = tile[k * TE + slot];
-        acc = acc + pcg2_weight<A, NS, HC, true>(rc, p, tab, y, tileN[slot]);
+        for (int k = PK ? NC : 0; k < A; ++k) y[k] = tile[k * TE + slot];
+        const unsigned ypack = PK ? (unsigned)tile[(A + 2) * TE + slot] : 0u;
+        acc = acc + pcg2_weight<A, NS, HC, true, PK>(rc, p, tab, ctab, y, ypack, tileN[slot]);
       }
       if (++tile_in_chunk == tpc || t + 1 == ntiles) {
         run = run + butterfly_sum(acc);
@@ -212,8 +253,10 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkPara
     const int slot = j % TE;
     int y[A];
 #pragma unroll
-    for (int k = 0; k < A; ++k) y[k] = tile[k * TE + slot];
-    return pcg2_weight<A, NS, HC, false>(rc, p, tab, y, reinterpret_cast<const double *>(tile + A * TE)[slot]);
+    for (int k = PK ? NC : 0; k < A; ++k) y[k] = tile[k * TE + slot];
+    const unsigned ypack = PK ? (unsigned)tile[(A + 2) * TE + slot] : 0u;
+    return pcg2_weight<A, NS, HC, false, PK>(rc, p, tab, ctab, y, ypack,
+                                             reinterpret_cast<const double *>(tile + A * TE)[slot]);
   };
   const U2 u = uniform2(p.seed, PH_LINK, p.iter, (uint32_t)r, 0u);
   const int j = finish_draw(lane, n, nsteps, spc, nchunks, Q, run, u.u0, wf);
@@ -225,29 +268,36 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkPara
 }
 
 inline size_t pcg2_smem_bytes(int A, int NS, int H) {
-  return (size_t)LINK_STAGES * tile_words(A) * 4 + 128 + (size_t)LINK_WARPS * (NS > 0 ? NS : 1) * pcg2_tab_bytes(H);
+  return (size_t)LINK_STAGES * tile_words(A) * 4 + 128 + (size_t)LINK_WARPS * (NS > 0 ? NS : 1) * pcg2_tab_bytes(H) +
+         (size_t)LINK_WARPS * 16 * sizeof(double);
 }
 
 // launch k_link_pcg2<A, NS, HC> for a runtime NS in [0, A]; HC = 32 (compile-time table size) when the model's
 // tables have 32 slots, else 0 (size read from the parameters); returns cudaError_t as int
-template <int A, int NS, int HC>
+template <int A, int NS, int HC, bool PK>
 int pcg2_launch_one(int grid, cudaStream_t stream, const LinkParams &lp) {
   const size_t smem = pcg2_smem_bytes(A, NS, lp.hslots);
   static size_t configured = 0;
   if (configured < smem) {
-    cudaError_t e = cudaFuncSetAttribute(k_link_pcg2<A, NS, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_link_pcg2<A, NS, HC, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     configured = smem;
   }
-  k_link_pcg2<A, NS, HC><<<grid, (LINK_WARPS + 1) * 32, smem, stream>>>(lp);
+  k_link_pcg2<A, NS, HC, PK><<<grid, (LINK_WARPS + 1) * 32, smem, stream>>>(lp);
   return (int)cudaGetLastError();
 }
 
 template <int A, int NS>
 struct Pcg2Launch {
   static int go(int ns, int grid, cudaStream_t stream, const LinkParams &lp) {
-    if (ns == NS)
-      return lp.hslots == 32 ? pcg2_launch_one<A, NS, 32>(grid, stream, lp) : pcg2_launch_one<A, NS, 0>(grid, stream, lp);
+    if (ns == NS) {
+      // byte-packed constant attributes: 1..4 of them, every vocabulary <= 255 (lp.pack_consts), 32-slot tables
+      if constexpr (A - NS >= 1 && A - NS <= 4) {
+        if (lp.pack_consts && lp.hslots == 32) return pcg2_launch_one<A, NS, 32, true>(grid, stream, lp);
+      }
+      return lp.hslots == 32 ? pcg2_launch_one<A, NS, 32, false>(grid, stream, lp)
+                             : pcg2_launch_one<A, NS, 0, false>(grid, stream, lp);
+    }
     if constexpr (NS > 0) return Pcg2Launch<A, NS - 1>::go(ns, grid, stream, lp);
     return (int)cudaErrorInvalidValue;
   }

@@ -905,12 +905,13 @@ static double protocol_weight(const orc_state *s, int sampler, const rec_attr_t 
   const orc_model *m = s->m;
   int A = m->A;
   double w;
-  /* multiplication order of the protocol: three passes over the attributes, each in attribute order */
+  /* multiplication order of the protocol: passes over the attributes, each in attribute order */
   if (sampler == ORC_PCG_II) {
-    w = nprod;
-    for (int a = 0; a < A; ++a) /* (i) exact matches: constant attributes first, then the others */
-      if (ra[a].kind == 1 && ye[a] == ra[a].x) w = w * ra[a].rmatch;
+    double c = 1.0; /* (i) exact matches: the constant attributes form their own product, applied to N(e) once */
     for (int a = 0; a < A; ++a)
+      if (ra[a].kind == 1 && ye[a] == ra[a].x) c = c * ra[a].rmatch;
+    w = nprod * c;
+    for (int a = 0; a < A; ++a) /* then the non-constant attributes */
       if (ra[a].kind == 2 && ye[a] == ra[a].x) w = w * ra[a].rmatch;
     for (int a = 0; a < A; ++a) { /* (ii) similar but different values */
       double e;

@@ -253,3 +253,16 @@ def test_pruned_link_update_without_dense_pointers(oracle, monkeypatch):
         eng.sweep("PCG-I", 1)
         assert st.sweep(oracle.SAMPLERS["PCG-I"]) == 0
         assert_same_state(eng, st)
+
+
+def test_pcg2_unpacked_constants_on_a_packable_model(oracle, monkeypatch):
+    """k_link_pcg2 reads the constant attributes of a candidate as one byte-packed word when there are 1..4 of them
+    with vocabularies <= 255; DBL_NO_PACK forces the per-attribute kernels on the same model: same draws."""
+    monkeypatch.setenv("DBL_NO_PACK", "1")
+    g = synth_problem(seed=23, R=900, n_files=2)
+    eng, rc, x, file = product_setup(g, 11, 2, (2, 3))
+    m, st, tree, ox, ofile = oracle_setup(oracle, g, 11, 2, (2, 3))
+    for it in range(4):
+        eng.sweep("PCG-II", 1)
+        assert st.sweep(oracle.SAMPLERS["PCG-II"]) == 0
+        assert_same_state(eng, st)
