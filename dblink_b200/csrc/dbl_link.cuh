@@ -218,8 +218,10 @@ __device__ __forceinline__ double generic_weight(const RecAttr *ra, int A, bool 
     for (int a = 0; a < A; ++a)
       if (ra[a].kind == 1 && ycol[a * TE] == ra[a].x) c = c * ra[a].rmatch;
     w = N * c;
+    double d = 1.0;  // and so do the exact matches of the non-constant attributes
     for (int a = 0; a < A; ++a)
-      if (ra[a].kind == 2 && ycol[a * TE] == ra[a].x) w = w * ra[a].rmatch;
+      if (ra[a].kind == 2 && ycol[a * TE] == ra[a].x) d = d * ra[a].rmatch;
+    w = w * d;
     for (int a = 0; a < A; ++a) {
       if (ra[a].kind != 2) continue;
       const int yv = ycol[a * TE];

@@ -28,6 +28,10 @@ struct Pcg2Rec {
   unsigned xpack;                // PK: the record's constant-attribute values, one byte each (0xFF = cannot match)
 };
 
+// up to 8 non-constant attributes: the product of the exact-match multipliers comes from a per-record table indexed
+// by the match mask (2^NS doubles per warp in shared memory)
+__host__ __device__ constexpr bool pcg2_dtab(int NS) { return NS >= 1 && NS <= 8; }
+
 // PK kernels: index into the record's table of constant-attribute products from the byte-packed values of a
 // candidate: bit k of the index = (byte k of ypack == byte k of xpack)
 __device__ __forceinline__ unsigned pcg2_const_index(unsigned ypack, unsigned xpack) {
@@ -43,7 +47,8 @@ __device__ __forceinline__ unsigned pcg2_const_index(unsigned ypack, unsigned xp
 // candidate (ypack) and their product comes from the record's 16-entry table ctab; otherwise y[0..A-NS) are used.
 template <int A, int NS, int HC, bool CONVERGED, bool PK>
 __device__ __forceinline__ double pcg2_weight(const Pcg2Rec<A, NS> &rc, const LinkParams &p, const char *tab,
-                                              const double *ctab, const int *y, unsigned ypack, double N) {
+                                              const double *ctab, const double *dtab, const int *y, unsigned ypack,
+                                              double N) {
   const int hslots = HC ? HC : p.hslots;
   const int hshift = HC ? 27 : p.hshift;
   const int tabb = pcg2_tab_bytes(hslots);
@@ -58,8 +63,19 @@ __device__ __forceinline__ double pcg2_weight(const Pcg2Rec<A, NS> &rc, const Li
     }
     w = w * c;
   }
+  if constexpr (NS >= 1) {  // protocol 4.1: so do the exact matches of the non-constant attributes (product d)
+    double d = 1.0;
+    if constexpr (pcg2_dtab(NS)) {
+      unsigned di = 0;
 #pragma unroll
-  for (int k = A - NS; k < A; ++k) mul_if_eq(w, y[k], rc.x[k], rc.rm[k]);
+      for (int q = 0; q < NS; ++q) di |= (y[A - NS + q] == rc.x[A - NS + q]) ? (1u << q) : 0u;
+      d = dtab[di];
+    } else {
+#pragma unroll
+      for (int k = A - NS; k < A; ++k) mul_if_eq(d, y[k], rc.x[k], rc.rm[k]);
+    }
+    w = w * d;
+  }
   if (CONVERGED) {
     // probe all NS tables first (no control flow), then ONE vote: the multiply by a similarity is rare
     bool hit[NS > 0 ? NS : 1];
@@ -119,6 +135,7 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkPara
   double *ctab = reinterpret_cast<double *>(reinterpret_cast<char *>(smem) + (size_t)LINK_STAGES * TW * 4 + 128 +
                                            (size_t)LINK_WARPS * (NS > 0 ? NS : 1) * pcg2_tab_bytes(HC ? HC : p.hslots)) +
                  warp * 16;  // PK: products of the matching constant attributes, by match mask
+  double *dtab = ctab + (LINK_WARPS - warp) * 16 + warp * (pcg2_dtab(NS) ? (1 << NS) : 0);  // same for the others
   const int *gtiles = p.tiles + (size_t)p.tile_ptr[b] * TW;
   ring_init(rg, LINK_WARPS);
 
@@ -193,6 +210,15 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkPara
         ctab[lane] = c;
       }
     }
+    if constexpr (pcg2_dtab(NS)) {
+      for (int idx = lane; idx < (1 << NS); idx += 32) {
+        double d = 1.0;
+#pragma unroll
+        for (int q = 0; q < NS; ++q)
+          if ((idx >> q) & 1) d = d * rc.rm[NC + q];
+        dtab[idx] = d;
+      }
+    }
     __syncwarp();
   }
 
@@ -227,7 +253,7 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkPara
 #pragma unroll
         for (int k = PK ? NC : 0; k < A; ++k) y[k] = tile[k * TE + slot];
         const unsigned ypack = PK ? (unsigned)tile[(A + 2) * TE + slot] : 0u;
-        acc = acc + pcg2_weight<A, NS, HC, true, PK>(rc, p, tab, ctab, y, ypack, tileN[slot]);
+        acc = acc + pcg2_weight<A, NS, HC, true, PK>(rc, p, tab, ctab, dtab, y, ypack, tileN[slot]);
       }
       if (++tile_in_chunk == tpc || t + 1 == ntiles) {
         run = run + butterfly_sum(acc);
@@ -255,7 +281,7 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkPara
 #pragma unroll
     for (int k = PK ? NC : 0; k < A; ++k) y[k] = tile[k * TE + slot];
     const unsigned ypack = PK ? (unsigned)tile[(A + 2) * TE + slot] : 0u;
-    return pcg2_weight<A, NS, HC, false, PK>(rc, p, tab, ctab, y, ypack,
+    return pcg2_weight<A, NS, HC, false, PK>(rc, p, tab, ctab, dtab, y, ypack,
                                              reinterpret_cast<const double *>(tile + A * TE)[slot]);
   };
   const U2 u = uniform2(p.seed, PH_LINK, p.iter, (uint32_t)r, 0u);
@@ -269,7 +295,7 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkPara
 
 inline size_t pcg2_smem_bytes(int A, int NS, int H) {
   return (size_t)LINK_STAGES * tile_words(A) * 4 + 128 + (size_t)LINK_WARPS * (NS > 0 ? NS : 1) * pcg2_tab_bytes(H) +
-         (size_t)LINK_WARPS * 16 * sizeof(double);
+         (size_t)LINK_WARPS * (16 + (pcg2_dtab(NS) ? (1 << NS) : 0)) * sizeof(double);
 }
 
 // launch k_link_pcg2<A, NS, HC> for a runtime NS in [0, A]; HC = 32 (compile-time table size) when the model's

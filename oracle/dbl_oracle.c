@@ -911,8 +911,10 @@ static double protocol_weight(const orc_state *s, int sampler, const rec_attr_t 
     for (int a = 0; a < A; ++a)
       if (ra[a].kind == 1 && ye[a] == ra[a].x) c = c * ra[a].rmatch;
     w = nprod * c;
-    for (int a = 0; a < A; ++a) /* then the non-constant attributes */
-      if (ra[a].kind == 2 && ye[a] == ra[a].x) w = w * ra[a].rmatch;
+    double d = 1.0; /* and so do the exact matches of the non-constant attributes */
+    for (int a = 0; a < A; ++a)
+      if (ra[a].kind == 2 && ye[a] == ra[a].x) d = d * ra[a].rmatch;
+    w = w * d;
     for (int a = 0; a < A; ++a) { /* (ii) similar but different values */
       double e;
       if (ra[a].kind == 2 && ye[a] != ra[a].x && row_find(m->idx[a], ra[a].x, ye[a], &e)) w = w * e;
