@@ -66,10 +66,10 @@ __device__ __forceinline__ double pcg2_weight(const Pcg2Rec<A, NS> &rc, const Li
   if constexpr (NS >= 1) {  // protocol 4.1: so do the exact matches of the non-constant attributes (product d)
     double d = 1.0;
     if constexpr (pcg2_dtab(NS)) {
-      unsigned di = 0;
+      unsigned di = 0;  // byte offset into the table: bit q of the index = attribute q matches
 #pragma unroll
-      for (int q = 0; q < NS; ++q) di |= (y[A - NS + q] == rc.x[A - NS + q]) ? (1u << q) : 0u;
-      d = dtab[di];
+      for (int q = 0; q < NS; ++q) di += (y[A - NS + q] == rc.x[A - NS + q]) ? (8u << q) : 0u;
+      d = *reinterpret_cast<const double *>(reinterpret_cast<const char *>(dtab) + di);
     } else {
 #pragma unroll
       for (int k = A - NS; k < A; ++k) mul_if_eq(d, y[k], rc.x[k], rc.rm[k]);
