@@ -53,11 +53,15 @@ def exchange(dist, send_ent, ent_counts, send_rec, rec_counts, ent_words, device
 
 
 def allreduce_summary(dist, counts, loglik, device, torch):
-    t = torch.tensor(counts, dtype=torch.int64, device=device)
+    """One all-reduce for the integer summary words and the log-likelihood: the counts travel as float64 (exact
+    below 2^53; they are bounded by records x attributes)."""
+    buf = np.empty(len(counts) + 1, np.float64)
+    buf[:-1] = counts
+    buf[-1] = loglik
+    t = torch.from_numpy(buf).to(device)
     dist.all_reduce(t)
-    ll = torch.tensor([loglik], dtype=torch.float64, device=device)
-    dist.all_reduce(ll)
-    return t.cpu().numpy(), float(ll[0])
+    out = t.cpu().numpy()
+    return np.rint(out[:-1]).astype(np.int64), float(out[-1])
 
 
 class ShardedGibbs:
