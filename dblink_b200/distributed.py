@@ -80,6 +80,7 @@ class ShardedGibbs:
         self.A, self.F = self.eng.A, self.eng.F
         self.owner = None
         self._ms = 0.0
+        self._stage = {}  # device staging buffers of upload_state
         self.trace = {}  # host wall-clock ms per phase of the sharded sweep, accumulated (rank-local)
 
     # ---- state ---------------------------------------------------------------------------------------
@@ -97,9 +98,39 @@ class ShardedGibbs:
         rec = np.bincount(blk[link], minlength=P).astype(np.float64)
         self.set_owners(lpt_assign(ent * rec, self.world))
 
+    def _gather_upload(self, name, a, dtype):
+        """Full device copy of the host array `a` (identical on every rank): each rank copies 1/world of it over
+        PCIe, one in-place all-gather over NVLink completes it."""
+        torch, dist, W = self.torch, self.dist, self.world
+        flat = np.ascontiguousarray(a, dtype=dtype).reshape(-1)
+        n = flat.size
+        chunk = (n + W - 1) // W
+        key = (name, n)
+        full = self._stage.get(key)
+        if full is None:
+            full = self._stage[key] = torch.empty(W * chunk, dtype=torch.from_numpy(flat[:0].copy()).dtype,
+                                                  device=self.device)
+        lo, hi = min(n, self.rank * chunk), min(n, (self.rank + 1) * chunk)
+        if hi > lo:
+            full[lo:hi].copy_(torch.from_numpy(flat[lo:hi]), non_blocking=True)
+        dist.all_gather_into_tensor(full, full[self.rank * chunk:(self.rank + 1) * chunk])
+        return full
+
     def upload_state(self, x, file_ids, z, link, y, theta, iteration=0):
-        """Every rank uploads the same full state (State.read), then keeps the blocks it owns."""
-        self.eng.upload_state(x, file_ids, z, link, y, theta, iteration)
+        """Every rank is handed the same full state (State.read) and keeps the blocks it owns.  The host-to-device
+        traffic is shared: a rank copies its 1/world slice of each array and the slices are all-gathered."""
+        x = np.asarray(x)
+        y = np.asarray(y)
+        if x.ndim != 2 or y.ndim != 2 or x.shape[1] != self.A or y.shape[1] != self.A:
+            raise ValueError("state arrays do not match the model")
+        dx = self._gather_upload("x", x, np.int32)
+        df = self._gather_upload("file", file_ids, np.int32)
+        dz = self._gather_upload("z", z, np.uint8)
+        dl = self._gather_upload("link", link, np.int32)
+        dy = self._gather_upload("y", y, np.int32)
+        self.torch.cuda.current_stream().synchronize()  # the engine copies from these buffers on its own stream
+        self.eng.upload_state_device(x.shape[0], y.shape[0], dx.data_ptr(), df.data_ptr(), dz.data_ptr(),
+                                     dl.data_ptr(), dy.data_ptr(), theta, iteration)
         self.set_owners(self.owner)
 
     def set_owners(self, owner):
@@ -177,9 +208,10 @@ class ShardedGibbs:
         _check(_lib.load().dbl_owned_masks(e._h, _p(em, _lib.u8p), _p(rm, _lib.u8p)), "owned_masks", e._h)
         return em.astype(bool), rm.astype(bool)
 
-    def download_state(self):
+    def download_state(self, out=None):
         """The full state on every rank: each rank exports the rows it owns into device buffers (zeros elsewhere),
-        one all-reduce (NCCL) per array sums them, one device-to-host copy brings them back."""
+        one all-reduce (NCCL) per array sums them, one device-to-host copy brings them back.  `out` may hold
+        preallocated (e.g. pinned) host arrays under the keys z, link, y, block; they are filled in place."""
         torch, dist, e = self.torch, self.dist, self.eng
         R, E, A = e.num_records, e.num_entities, self.A
         y = torch.empty(E * A, dtype=torch.int32, device=self.device)
@@ -192,5 +224,16 @@ class ShardedGibbs:
             dist.all_reduce(t)  # exactly one rank owns each row
         theta = np.zeros((A, self.F))
         _check(_lib.load().dbl_summary(e._h, None, None, None, _p(theta, _lib.f64p)), "summary", e._h)
-        return {"theta": theta, "y": y.cpu().numpy().reshape(E, A), "block": blk.cpu().numpy(),
-                "link": link.cpu().numpy(), "z": z.cpu().numpy().reshape(R, A)}
+        res = {"theta": theta}
+        for k, dev, shape in (("y", y, (E, A)), ("block", blk, (E,)), ("link", link, (R,)), ("z", z, (R, A))):
+            host = out.get(k) if out else None
+            if host is None:
+                res[k] = dev.cpu().numpy().reshape(shape)
+            else:
+                torch.from_numpy(host.reshape(-1)).copy_(dev, non_blocking=True)
+                res[k] = host
+        torch.cuda.current_stream().synchronize()
+        if out and out.get("theta") is not None:
+            out["theta"][...] = theta
+            res["theta"] = out["theta"]
+        return res

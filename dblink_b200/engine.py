@@ -273,6 +273,17 @@ class GibbsEngine:
                                             _p(z, _lib.u8p), _p(link, _lib.i32p), _p(y, _lib.i32p),
                                             _p(theta, _lib.f64p), int(iteration)), "upload_state", self._h)
 
+    def upload_state_device(self, R, E, x_ptr, file_ptr, z_ptr, link_ptr, y_ptr, theta, iteration=0):
+        """upload_state from DEVICE buffers (raw addresses of int32 x[R,A], file[R], uint8 z[R,A], int32 link[R],
+        y[E,A]); theta stays a host array."""
+        theta = _f64(theta)
+        if theta.size != self.A * self.F:
+            raise ValueError("state arrays do not match the model")
+        cast = lambda p, t: C.cast(C.c_void_p(int(p)), t)
+        _check(_lib.load().dbl_state_upload(self._h, int(R), int(E), cast(x_ptr, _lib.i32p), cast(file_ptr, _lib.i32p),
+                                            cast(z_ptr, _lib.u8p), cast(link_ptr, _lib.i32p), cast(y_ptr, _lib.i32p),
+                                            _p(theta, _lib.f64p), int(iteration)), "upload_state", self._h)
+
     def set_partitioner(self, partitioner):
         """Install the partition function fitted on the initial entity values (State.scala:309-316)."""
         self.partitioner = partitioner

@@ -112,7 +112,8 @@ int32_t dbl_num_partitions(const dbl_ctx *);
 int dbl_state_init(dbl_ctx *, int64_t num_records, const int32_t *x, const int32_t *file,
                    int64_t population_size);
 /* Arbitrary state (resume; State.read, State.scala:160-193).  z = R x A bytes, link = R global entity ids,
- * y = E x A value ids, theta = A x F. */
+ * y = E x A value ids, theta = A x F (host).  x, file, z, link, y may be host OR device pointers (unified
+ * addressing decides): a multi-GPU caller can stage slices and all-gather them on the device first. */
 int dbl_state_upload(dbl_ctx *, int64_t num_records, int64_t num_entities, const int32_t *x, const int32_t *file,
                      const uint8_t *z, const int32_t *link, const int32_t *y, const double *theta,
                      int64_t iteration);

@@ -87,6 +87,16 @@ def gpu_mode():
             assert ps["num_isolates"] == os_["num_isolates"]
             assert np.array_equal(ps["agg_dist"], os_["agg_dist"]) and np.array_equal(ps["rec_dist"], os_["rec_dist"])
             assert abs(ps["log_likelihood"] - os_["log_likelihood"]) <= 1e-9 * abs(os_["log_likelihood"])
+        # resume from host arrays (sliced upload + all-gather) into pinned output buffers, then keep following the oracle
+        pinned = {k: torch.empty(d[k].shape, dtype=torch.from_numpy(d[k][:0].copy()).dtype, pin_memory=True).numpy()
+                  for k in ("z", "link", "y", "block")}
+        eng.upload_state(x, file, d["z"], d["link"], d["y"], d["theta"], iteration=eng.iteration)
+        for it in range(2):
+            eng.sweep(sampler, 1)
+            st.sweep(O.SAMPLERS[sampler])
+            d = eng.download_state(out=pinned)
+            for k in ("theta", "link", "y", "z"):
+                assert np.array_equal(d[k], getattr(st, k)), ("after upload", sampler, it, k, rank)
         t = torch.tensor([moved], device="cuda")
         dist.all_reduce(t)
         if world > 1:
