@@ -1,11 +1,17 @@
-// k_link_pcg2<A, NS>: the PCG-II link update (updateEntityIdCollapsed, GU:363-395) with everything about the
-// model shape known at compile time: A attributes in kernel order, the last NS of them non-constant.
+// k_link_pcg2<A, NS, HC, PK>: the PCG-II link update (updateEntityIdCollapsed, GU:363-395) with everything about
+// the model shape known at compile time: A attributes in kernel order, the last NS of them non-constant; HC = 32
+// when the hash tables have 32 slots (else the size is a run-time parameter); PK = the constant attributes arrive
+// byte-packed.
 //
 //  * the block's entity table streams through shared memory in TE-entity tiles moved by TMA bulk copies
 //    (cp.async.bulk.shared::cluster.global + mbarrier ring, one producer warp per CTA);
-//  * each consumer warp owns one record; its constants (value ids, exact-match multipliers, hash multipliers)
-//    are registers; the sparse similarity row of each non-constant record attribute is a 32-slot perfect-hash
-//    table in shared memory: one key word per bank, so a probe is one conflict-free wavefront;
+//  * each consumer warp owns one record; its constants (value ids, hash multipliers) are registers;
+//  * exact matches: the multipliers of the matching constant attributes and of the matching non-constant
+//    attributes are two products, each fetched from a per-record table in shared memory indexed by
+//    the match mask (16 entries for PK, 2^NS entries for NS <= 8);
+//  * similar-but-different values: the sparse similarity row of each non-constant record attribute is a 32-slot
+//    perfect-hash table in shared memory, one key word per bank, so a probe is one conflict-free wavefront; one
+//    warp vote per step decides whether anybody needs the multiply;
 //  * lane l scores candidate 32*step + l; lane sums / chunk totals / draw as in DESIGN.md section 4.
 #pragma once
 #include "dbl_link.cuh"
@@ -14,7 +20,7 @@
 // for every attribute of the model; 32 = one key per bank = conflict-free probes).
 __device__ __host__ __forceinline__ int pcg2_tab_bytes(int H) { return H * 12; }
 
-// w *= r when y == x (ptxas turns any predicated form into DMUL + 2 FSEL; plain C avoids extra moves)
+// w *= r when y == x (shapes without a product table; ptxas turns any predicated form into DMUL + 2 FSEL)
 __device__ __forceinline__ void mul_if_eq(double &w, int y, int x, double r) {
   if (y == x) w = w * r;
 }
