@@ -1,7 +1,7 @@
 """Chain driver: Sampler.sample (Sampler.scala:51-124) over a GibbsEngine / ShardedGibbs."""
 import os
 
-from .writers import DiagnosticsWriter, LinkageChainWriter, linkage_structure
+from .writers import DiagnosticsWriter, LinkageChainWriter, linkage_structure_arrow
 
 SUPPORTED_SAMPLERS = ("PCG-I", "PCG-II", "Gibbs", "Gibbs-Sequential")  # ProjectStep.scala:35
 
@@ -9,7 +9,9 @@ SUPPORTED_SAMPLERS = ("PCG-I", "PCG-II", "Gibbs", "Gibbs-Sequential")  # Project
 def sample(engine, record_ids, attribute_names, sample_size, output_path, burnin_interval=0, thinning_interval=1,
            write_buffer_size=10, sampler="PCG-I", population_size=None, on_sample=None):
     """Generates `sample_size` posterior samples by successively applying the transition operator; writes
-    linkage-chain.parquet and diagnostics.csv under output_path.  Returns the number of sweeps performed."""
+    linkage-chain.parquet and diagnostics.csv under output_path.  Returns the number of sweeps performed.
+    on_sample(summary, parts) sees every recorded sample; parts = {partition id: pyarrow ListArray of clusters}
+    (`.to_pylist()` gives the lists of record ids)."""
     if sample_size <= 0:
         raise ValueError("`sampleSize` must be positive.")            # Sampler.scala:61
     if burnin_interval < 0:
@@ -27,9 +29,13 @@ def sample(engine, record_ids, attribute_names, sample_size, output_path, burnin
     lw = LinkageChainWriter(os.path.join(output_path, "linkage-chain.parquet"), write_buffer_size, continue_chain)
     dw = DiagnosticsWriter(os.path.join(output_path, "diagnostics.csv"), attribute_names, continue_chain)
 
+    import pyarrow as pa
+
+    ids = pa.array([str(r) for r in record_ids], pa.string())
+
     def record():
         link, blk = engine.links()
-        parts = linkage_structure(link, blk, record_ids)
+        parts = linkage_structure_arrow(link, blk, ids)  # {partition id: ListArray of clusters}
         s = engine.summary()
         lw.append(s["iteration"], parts)
         dw.write_row(s, pop)

@@ -211,3 +211,42 @@ def test_bench_reference_arm_runs():
         line = json.loads(res.stdout.strip().splitlines()[-1])
         assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "iterations/s"
         assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_arrow_linkage_structure_equals_list_form(tmp_path):
+    """linkage_structure_arrow (no Python loop over clusters) == linkage_structure, in memory and through the
+    hive-partitioned Parquet chain; mixed buffers (Arrow + list rows) are written too."""
+    import time
+
+    from dblink_b200 import writers as w
+
+    rng = np.random.default_rng(3)
+    for R, E, P in ((1, 1, 1), (50, 50, 4), (3000, 2500, 8)):
+        link = rng.integers(0, E, R).astype(np.int32)
+        blk = rng.integers(0, P, E).astype(np.int32)
+        ids = ["rec-%d" % i for i in range(R)]
+        lists = w.linkage_structure(link, blk, ids)
+        arrow = w.linkage_structure_arrow(link, blk, ids)
+        assert {p: a.to_pylist() for p, a in arrow.items()} == lists
+        path = os.path.join(tmp_path, "chain-%d.parquet" % R)
+        lw = w.LinkageChainWriter(path, write_buffer_size=3)
+        lw.append(0, arrow)
+        lw.append(5, lists)   # one buffer holding both forms
+        lw.append(10, arrow)
+        lw.append(15, arrow)
+        lw.close()
+        chain = w.read_linkage_chain(path)
+        assert [c[0] for c in chain] == [0, 5, 10, 15]
+        assert all(c[1] == lists for c in chain)
+    # the point of the Arrow form: no per-cluster Python work
+    R = 200_000
+    link = rng.integers(0, R, R).astype(np.int32)
+    blk = rng.integers(0, 16, R).astype(np.int32)
+    import pyarrow as pa
+
+    ids = pa.array(["r%d" % i for i in range(R)], pa.string())
+    t0 = time.perf_counter()
+    arrow = w.linkage_structure_arrow(link, blk, ids)
+    dt = time.perf_counter() - t0
+    assert sum(len(a) for a in arrow.values()) == len(np.unique(link))
+    assert dt < 2.0
