@@ -6,7 +6,9 @@ step runs on the GPU engine, summarize / evaluate run on the host from linkage-c
 import os
 import shutil
 
-from . import analysis, config as hocon, sampler as chain, state_io, writers
+import numpy as np
+
+from . import analysis, analysis_arrays, config as hocon, sampler as chain, state_io, writers
 from .engine import GibbsEngine, KDTreePartitioner
 from .records import Attribute, RecordsCache, SimilarityFn, read_csv
 
@@ -68,6 +70,25 @@ class Project:
         if d["ent_ids"] is None:
             return None
         return analysis.membership_to_clusters(d["rec_ids"], d["ent_ids"])
+
+    def true_labels(self):
+        """Ground truth as a function: record ids (pyarrow array, the chain's dictionary) -> int labels in that
+        order; None when the data has no entity id column."""
+        d = self.load()
+        if d["ent_ids"] is None:
+            return None
+
+        def lookup(record_ids):
+            import pyarrow as pa
+            import pyarrow.compute as pc
+
+            pos = pc.index_in(record_ids, value_set=pa.array([str(r) for r in d["rec_ids"]], pa.string()))
+            if pos.null_count:
+                raise ValueError("the chain mentions record ids that are not in the data")
+            _, lab = np.unique(np.asarray([str(e) for e in d["ent_ids"]], dtype=object), return_inverse=True)
+            return lab[pos.to_numpy(zero_copy_only=False)]
+
+        return lookup
 
     def _new_engine(self):
         d = self.load()
@@ -154,30 +175,34 @@ class Project:
                              self.output_path, prm["burnin_interval"], prm["thinning_interval"], sampler=prm["sampler"])
                 self.save_state(eng)  # Sampler.scala:120
             elif name == "summarize":
-                ch = writers.read_linkage_chain(os.path.join(self.output_path, "linkage-chain.parquet"),
-                                                prm["lower_iteration_cutoff"])
+                # array implementations (analysis_arrays): same quantities as analysis.py, no loop over clusters
+                ch = analysis_arrays.read_chain_arrays(os.path.join(self.output_path, "linkage-chain.parquet"),
+                                                       prm["lower_iteration_cutoff"])
                 for q in prm["quantities"]:
                     if q == "cluster-size-distribution":
-                        writers.save_cluster_size_distribution(analysis.cluster_size_distribution(ch), self.output_path)
+                        writers.save_cluster_size_distribution(analysis_arrays.cluster_size_distribution(ch),
+                                                               self.output_path)
                     elif q == "partition-sizes":
-                        writers.save_partition_sizes(analysis.partition_sizes(ch), self.output_path)
+                        writers.save_partition_sizes(analysis_arrays.partition_sizes(ch), self.output_path)
                     else:
-                        self._save_smpc(analysis.shared_most_probable_clusters(ch))
+                        labels = analysis_arrays.shared_most_probable_clusters(ch)
+                        self._save_smpc(analysis_arrays.labels_to_clusters(labels, ch.record_ids))
             elif name == "evaluate":
-                truth = self.true_clusters()
-                if truth is None:
+                true_labels = self.true_labels()
+                if true_labels is None:
                     raise ValueError("Ground truth entity ids are required for evaluation")  # ProjectStep.scala:65
-                ch = writers.read_linkage_chain(os.path.join(self.output_path, "linkage-chain.parquet"),
-                                                prm["lower_iteration_cutoff"])
-                smpc = analysis.shared_most_probable_clusters(ch)
-                self._save_smpc(smpc)
+                ch = analysis_arrays.read_chain_arrays(os.path.join(self.output_path, "linkage-chain.parquet"),
+                                                       prm["lower_iteration_cutoff"])
+                labels = analysis_arrays.shared_most_probable_clusters(ch)
+                self._save_smpc(analysis_arrays.labels_to_clusters(labels, ch.record_ids))
+                truth = true_labels(ch.record_ids)
                 text = []
                 for m in prm["metrics"]:
                     if m == "pairwise":
-                        results["pairwise"] = analysis.pairwise_metrics(smpc, truth)
+                        results["pairwise"] = analysis_arrays.pairwise_metrics(labels, truth)
                         text.append(analysis.format_pairwise(results["pairwise"]))
                     else:
-                        results["cluster"] = analysis.adjusted_rand_index(smpc, truth)
+                        results["cluster"] = analysis_arrays.adjusted_rand_index(labels, truth)
                         text.append(analysis.format_cluster(results["cluster"]))
                 with open(os.path.join(self.output_path, "evaluation-results.txt"), "w") as fh:
                     fh.write("\n".join(text) + "\n")

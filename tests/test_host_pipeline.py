@@ -250,3 +250,46 @@ def test_arrow_linkage_structure_equals_list_form(tmp_path):
     dt = time.perf_counter() - t0
     assert sum(len(a) for a in arrow.values()) == len(np.unique(link))
     assert dt < 2.0
+
+
+def test_array_summaries_equal_the_set_based_ones(tmp_path):
+    """analysis_arrays (vectorised: signatures, run-length mode, contingency tables) == analysis (sets and loops) on
+    random chains read back from linkage-chain.parquet, including ties between equally frequent clusters."""
+    from dblink_b200 import analysis as an, analysis_arrays as aa, writers as w
+
+    rng = np.random.default_rng(11)
+    for trial, (R, E, P, S) in enumerate(((6, 4, 2, 4), (40, 25, 3, 7), (300, 220, 5, 9))):
+        ids = ["id%03d" % i for i in range(R)]
+        blk = rng.integers(0, P, E).astype(np.int32)
+        path = os.path.join(tmp_path, "chain%d.parquet" % trial)
+        lw = w.LinkageChainWriter(path, write_buffer_size=4)
+        base = rng.integers(0, E, R).astype(np.int32)
+        for s in range(S):
+            link = base.copy()
+            move = rng.random(R) < 0.3                      # samples share most clusters: repeated and tied modes
+            link[move] = rng.integers(0, E, int(move.sum()))
+            if s % 3 == 0:
+                base = link
+            lw.append(10 * s, w.linkage_structure_arrow(link, blk, ids))
+        lw.close()
+        for cutoff in (0, 20):
+            ch = w.read_linkage_chain(path, cutoff)
+            ca = aa.read_chain_arrays(path, cutoff)
+            assert list(ca.iterations) == [c[0] for c in ch]
+            assert aa.cluster_size_distribution(ca) == an.cluster_size_distribution(ch)
+            assert aa.partition_sizes(ca) == an.partition_sizes(ch)
+            labels = aa.shared_most_probable_clusters(ca)
+            got = {frozenset(c) for c in aa.labels_to_clusters(labels, ca.record_ids)}
+            assert got == set(an.shared_most_probable_clusters(ch))
+            truth_of = rng.integers(0, max(2, R // 2), R)
+            id_list = ca.record_ids.to_pylist()
+            truth_sets = an.membership_to_clusters(id_list, truth_of)
+            pm_a, pm_s = aa.pairwise_metrics(labels, truth_of), an.pairwise_metrics(list(got), truth_sets)
+            assert (pm_a["TP"], pm_a["FP"], pm_a["FN"]) == (pm_s["TP"], pm_s["FP"], pm_s["FN"])
+            assert pm_a["f1score"] == pytest.approx(pm_s["f1score"], nan_ok=True)
+            assert aa.adjusted_rand_index(labels, truth_of) == pytest.approx(an.adjusted_rand_index(list(got), truth_sets))
+    # a sample straight from link arrays
+    link = np.array([3, 0, 3, 2, 0, 4], np.int32)
+    mem, off, part = aa.sample_from_links(link, np.array([0, 1, 1, 0, 0], np.int32))
+    assert [list(mem[off[i]:off[i + 1]]) for i in range(len(off) - 1)] == [[1, 4], [3], [0, 2], [5]]
+    assert list(part) == [0, 1, 0, 0]
