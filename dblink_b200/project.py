@@ -10,7 +10,8 @@ import numpy as np
 
 from . import analysis, analysis_arrays, config as hocon, sampler as chain, state_io, writers
 from .engine import GibbsEngine, KDTreePartitioner
-from .records import Attribute, RecordsCache, SimilarityFn, read_csv
+from .records import (Attribute, RecordsCache, SimilarityFn, build_cache_from_columns, read_csv,  # noqa: F401
+                      read_csv_columns)
 
 SUPPORTED_METRICS = ("pairwise", "cluster")  # ProjectStep.scala:36
 SUPPORTED_QUANTITIES = ("cluster-size-distribution", "partition-sizes", "shared-most-probable-clusters")  # :37
@@ -58,11 +59,14 @@ class Project:
     def load(self):
         if self._loaded is None:
             names = [a.name for a in self.matching_attributes]
-            rec_ids, files, values, ent_ids = read_csv(self.data_path, self.rec_id_attribute, names,
-                                                       self.file_id_attribute, self.ent_id_attribute, self.null_value)
-            cache = RecordsCache.build(values, files, self.matching_attributes, self.expected_max_cluster_size)
-            x, f = cache.transform_records(values, files)
-            self._loaded = {"rec_ids": rec_ids, "ent_ids": ent_ids, "cache": cache, "x": x, "file": f}
+            # columnar path (pyarrow): same cache / value ids as read_csv + RecordsCache.build + transform_records
+            rec_ids, files, columns, ent_ids = read_csv_columns(self.data_path, self.rec_id_attribute, names,
+                                                                self.file_id_attribute, self.ent_id_attribute,
+                                                                self.null_value)
+            cache, x, f = build_cache_from_columns(columns, files, self.matching_attributes,
+                                                   self.expected_max_cluster_size)
+            self._loaded = {"rec_ids": rec_ids.to_pylist(), "ent_ids": None if ent_ids is None else ent_ids.to_pylist(),
+                            "cache": cache, "x": x, "file": f}
         return self._loaded
 
     def true_clusters(self):

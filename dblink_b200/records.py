@@ -131,3 +131,71 @@ def read_csv(path, rec_id_col, attribute_names, file_id_col=None, ent_id_col=Non
             if ent_id_col:
                 ent_ids.append(row[ent_id_col])
     return rec_ids, files, values, (ent_ids if ent_id_col else None)
+
+
+# ---- columnar path (pyarrow): the same results without a Python loop over records ------------------------
+def read_csv_columns(path, rec_id_col, attribute_names, file_id_col=None, ent_id_col=None, null_value="NA"):
+    """read_csv through pyarrow.csv: -> (rec_ids, files, columns, ent_ids) with pyarrow string arrays (nulls =
+    missing) instead of Python lists; .gz is handled by pyarrow.  Every column is read as a string, as the
+    reference does (State.scala:350-371)."""
+    import pyarrow as pa
+    import pyarrow.compute as pc
+    import pyarrow.csv as pacsv
+
+    wanted = [rec_id_col] + list(attribute_names) + ([file_id_col] if file_id_col else []) + \
+             ([ent_id_col] if ent_id_col else [])
+    tbl = pacsv.read_csv(path, convert_options=pacsv.ConvertOptions(
+        column_types={c: pa.string() for c in wanted}, include_columns=list(dict.fromkeys(wanted)),
+        null_values=[], strings_can_be_null=False))
+
+    def col(name):
+        return tbl.column(name).combine_chunks()
+
+    def nullable(a):  # the null marker and the empty string are missing values
+        return pc.if_else(pc.or_(pc.equal(a, null_value), pc.equal(a, "")), pa.scalar(None, pa.string()), a)
+
+    rec_ids = col(rec_id_col)
+    files = col(file_id_col) if file_id_col else pa.array(["0"] * len(rec_ids), pa.string())
+    columns = [nullable(col(a)) for a in attribute_names]
+    return rec_ids, files, columns, (col(ent_id_col) if ent_id_col else None)
+
+
+def build_cache_from_columns(columns, files, attributes: List[Attribute], expected_max_cluster_size: int = 10):
+    """RecordsCache.build + transform_records on pyarrow string columns -> (cache, x int32[R, A], file int32[R])."""
+    import pyarrow.compute as pc
+
+    if len(columns) != len(attributes):
+        raise ValueError("attribute specifications do not match the records")  # RecordsCache.scala:72
+    R = len(files)
+    if R == 0:
+        raise ValueError("no records")
+    fenc = files.dictionary_encode()
+    fnames = fenc.dictionary.to_pylist()
+    forder = np.argsort(np.asarray(fnames, dtype=object), kind="stable")  # sorted file ids; position = integer id
+    frank = np.empty(len(fnames), np.int32)
+    frank[forder] = np.arange(len(fnames), dtype=np.int32)
+    fcodes = fenc.indices.to_numpy(zero_copy_only=False)
+    file = frank[fcodes]
+    fsz = np.bincount(file, minlength=len(fnames))
+    x = np.full((R, len(attributes)), -1, np.int32)
+    indexes, missing = [], {}
+    for a, (colm, attr) in enumerate(zip(columns, attributes)):
+        enc = colm.dictionary_encode()
+        vals = enc.dictionary.to_pylist()
+        codes = enc.indices.to_numpy(zero_copy_only=False)  # NaN / masked where null
+        valid = np.asarray(pc.is_valid(colm).to_numpy(zero_copy_only=False), bool)
+        ci = np.where(valid, np.nan_to_num(codes, nan=0).astype(np.int64), 0)
+        cnt = np.bincount(ci[valid], minlength=len(vals))
+        sf = attr.similarity_fn
+        ix = AttributeIndex.build({v: float(c) for v, c in zip(vals, cnt) if c > 0},
+                                  "constant" if sf.is_constant else "levenshtein", sf.threshold, sf.max_similarity,
+                                  expected_max_cluster_size)
+        lut = np.array([ix.value_idx_of(v) if c > 0 else -1 for v, c in zip(vals, cnt)] + [-1], np.int32)
+        x[:, a] = np.where(valid, lut[ci], -1)
+        indexes.append(ix)
+        miss = np.bincount(file[~valid], minlength=len(fnames))
+        for f in np.flatnonzero(miss):
+            missing[(fnames[forder[f]], a)] = int(miss[f])
+    sorted_names = [fnames[i] for i in forder]
+    cache = RecordsCache(attributes, indexes, sorted_names, [int(v) for v in fsz], missing)
+    return cache, x, file

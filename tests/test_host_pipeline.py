@@ -293,3 +293,37 @@ def test_array_summaries_equal_the_set_based_ones(tmp_path):
     mem, off, part = aa.sample_from_links(link, np.array([0, 1, 1, 0, 0], np.int32))
     assert [list(mem[off[i]:off[i + 1]]) for i in range(len(off) - 1)] == [[1, 4], [3], [0, 2], [5]]
     assert list(part) == [0, 1, 0, 0]
+
+
+def test_columnar_records_path_equals_the_list_path(tmp_path):
+    """read_csv_columns + build_cache_from_columns (pyarrow, no loop over records) give the same value ids, file
+    ids, index sizes and missing counts as read_csv + RecordsCache.build + transform_records."""
+    from dblink_b200 import records as R
+
+    rng = np.random.default_rng(5)
+    path = os.path.join(tmp_path, "d.csv")
+    names = ["c0", "s0", "s1"]
+    vocab = [["a", "b", "c"], ["SMITH", "SMYTH", "JONES", "JONAS", "BROWN"], ["ANN", "ANNE", "BOB", ""]]
+    with open(path, "w") as fh:
+        fh.write("id,src," + ",".join(names) + ",truth\n")
+        for r in range(400):
+            vals = [("NA" if rng.random() < 0.1 else vocab[a][rng.integers(len(vocab[a]))]) for a in range(3)]
+            fh.write("r%d,%s,%s,e%d\n" % (r, "fileB" if rng.random() < 0.4 else "fileA", ",".join(vals), r // 2))
+    attrs = [R.Attribute("c0"), R.Attribute("s0", R.SimilarityFn("LevenshteinSimilarityFn", 7, 10)),
+             R.Attribute("s1", R.SimilarityFn("LevenshteinSimilarityFn", 7, 10))]
+    for file_col in ("src", None):
+        ri, f, v, e = R.read_csv(path, "id", names, file_col, "truth", "NA")
+        c1 = R.RecordsCache.build(v, f, attrs, 5)
+        x1, f1 = c1.transform_records(v, f)
+        ri2, f2, cols, e2 = R.read_csv_columns(path, "id", names, file_col, "truth", "NA")
+        c2, x2, ff2 = R.build_cache_from_columns(cols, f2, attrs, 5)
+        assert ri2.to_pylist() == ri and e2.to_pylist() == e
+        np.testing.assert_array_equal(x1, x2)
+        np.testing.assert_array_equal(f1, ff2)
+        assert (c1.file_ids, c1.file_sizes, c1.missing_counts) == (c2.file_ids, c2.file_sizes, c2.missing_counts)
+        for a in range(3):
+            assert c1.indexes[a].num_values == c2.indexes[a].num_values
+            for v_ in set(vocab[a]) - {""}:
+                assert c1.indexes[a].value_idx_of(v_) == c2.indexes[a].value_idx_of(v_)
+    with pytest.raises(ValueError):
+        R.build_cache_from_columns(cols[:2], f2, attrs, 5)
