@@ -37,6 +37,19 @@ struct Pcg2Rec {
 // up to 8 non-constant attributes: the product of the exact-match multipliers comes from a per-record table indexed
 // by the match mask (2^NS doubles per warp in shared memory)
 __host__ __device__ constexpr bool pcg2_dtab(int NS) { return NS >= 1 && NS <= 8; }
+// Position (in entries) of attribute q's bit in that table.  Not 1 << q: the weights are chosen so that every subset
+// sum is distinct AND the single-attribute entries (by far the most used after entry 0) fall in different
+// shared-memory banks from entry 0 and from each other (position mod 16 all distinct and non-zero); with powers of
+// two, attributes 4 and 5 would sit 128 and 256 bytes from entry 0, i.e. in its banks.
+__host__ __device__ constexpr int pcg2_dtab_weight(int q) {
+  constexpr int w[8] = {1, 2, 4, 8, 19, 38, 75, 149};
+  return w[q];
+}
+__host__ __device__ constexpr int pcg2_dtab_entries(int NS) {
+  int n = 1;
+  for (int q = 0; q < NS; ++q) n += pcg2_dtab_weight(q);
+  return pcg2_dtab(NS) ? n : 0;
+}
 
 // PK kernels: index into the record's table of constant-attribute products from the byte-packed values of a
 // candidate: bit k of the index = (byte k of ypack == byte k of xpack)
@@ -74,7 +87,7 @@ __device__ __forceinline__ double pcg2_weight(const Pcg2Rec<A, NS> &rc, const Li
     if constexpr (pcg2_dtab(NS)) {
       unsigned di = 0;  // byte offset into the table: bit q of the index = attribute q matches
 #pragma unroll
-      for (int q = 0; q < NS; ++q) di += (y[A - NS + q] == rc.x[A - NS + q]) ? (8u << q) : 0u;
+      for (int q = 0; q < NS; ++q) di += (y[A - NS + q] == rc.x[A - NS + q]) ? 8u * pcg2_dtab_weight(q) : 0u;
       d = *reinterpret_cast<const double *>(reinterpret_cast<const char *>(dtab) + di);
     } else {
 #pragma unroll
@@ -141,7 +154,7 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkPara
   double *ctab = reinterpret_cast<double *>(reinterpret_cast<char *>(smem) + (size_t)LINK_STAGES * TW * 4 + 128 +
                                            (size_t)LINK_WARPS * (NS > 0 ? NS : 1) * pcg2_tab_bytes(HC ? HC : p.hslots)) +
                  warp * 16;  // PK: products of the matching constant attributes, by match mask
-  double *dtab = ctab + (LINK_WARPS - warp) * 16 + warp * (pcg2_dtab(NS) ? (1 << NS) : 0);  // same for the others
+  double *dtab = ctab + (LINK_WARPS - warp) * 16 + warp * pcg2_dtab_entries(NS);  // same for the others
   const int *gtiles = p.tiles + (size_t)p.tile_ptr[b] * TW;
   ring_init(rg, LINK_WARPS);
 
@@ -217,12 +230,13 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkPara
       }
     }
     if constexpr (pcg2_dtab(NS)) {
-      for (int idx = lane; idx < (1 << NS); idx += 32) {
+      for (int idx = lane; idx < (1 << NS); idx += 32) {  // idx = match mask; stored at its weighted position
         double d = 1.0;
+        int pos = 0;
 #pragma unroll
         for (int q = 0; q < NS; ++q)
-          if ((idx >> q) & 1) d = d * rc.rm[NC + q];
-        dtab[idx] = d;
+          if ((idx >> q) & 1) { d = d * rc.rm[NC + q]; pos += pcg2_dtab_weight(q); }
+        dtab[pos] = d;
       }
     }
     __syncwarp();
@@ -301,7 +315,7 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkPara
 
 inline size_t pcg2_smem_bytes(int A, int NS, int H) {
   return (size_t)LINK_STAGES * tile_words(A) * 4 + 128 + (size_t)LINK_WARPS * (NS > 0 ? NS : 1) * pcg2_tab_bytes(H) +
-         (size_t)LINK_WARPS * (16 + (pcg2_dtab(NS) ? (1 << NS) : 0)) * sizeof(double);
+         (size_t)LINK_WARPS * (16 + pcg2_dtab_entries(NS)) * sizeof(double);
 }
 
 // launch k_link_pcg2<A, NS, HC> for a runtime NS in [0, A]; HC = 32 (compile-time table size) when the model's
