@@ -327,3 +327,35 @@ def test_columnar_records_path_equals_the_list_path(tmp_path):
                 assert c1.indexes[a].value_idx_of(v_) == c2.indexes[a].value_idx_of(v_)
     with pytest.raises(ValueError):
         R.build_cache_from_columns(cols[:2], f2, attrs, 5)
+
+
+def test_array_summaries_edge_cases(tmp_path):
+    from dblink_b200 import analysis_arrays as aa, writers as w
+
+    # one sample, one record
+    path = os.path.join(tmp_path, "one.parquet")
+    lw = w.LinkageChainWriter(path)
+    lw.append(0, w.linkage_structure_arrow(np.array([0], np.int32), np.array([0], np.int32), ["only"]))
+    lw.close()
+    ca = aa.read_chain_arrays(path)
+    assert list(ca.iterations) == [0] and ca.num_records == 1
+    assert aa.cluster_size_distribution(ca) == {0: {1: 1}} and aa.partition_sizes(ca) == {0: {0: 1}}
+    labels = aa.shared_most_probable_clusters(ca)
+    assert list(labels) == [0]
+    assert aa.labels_to_clusters(labels, ca.record_ids) == [["only"]]
+    m = aa.pairwise_metrics(labels, np.array([7]))
+    assert (m["TP"], m["FP"], m["FN"]) == (0, 0, 0) and m["f1score"] != m["f1score"]  # NaN, as PairwiseMetrics does
+    # cutoff beyond the chain: empty
+    empty = aa.read_chain_arrays(path, lower_iteration_cutoff=5)
+    assert len(empty.samples) == 0 and empty.num_records == 0
+    # a record whose two candidate clusters are equally frequent keeps the one seen first
+    ids = ["a", "b", "c"]
+    blk = np.zeros(3, np.int32)
+    path2 = os.path.join(tmp_path, "tie.parquet")
+    lw = w.LinkageChainWriter(path2)
+    lw.append(0, w.linkage_structure_arrow(np.array([0, 0, 2], np.int32), blk, ids))   # {a,b} {c}
+    lw.append(1, w.linkage_structure_arrow(np.array([0, 1, 1], np.int32), blk, ids))   # {a} {b,c}
+    lw.close()
+    ca = aa.read_chain_arrays(path2)
+    got = {frozenset(c) for c in aa.labels_to_clusters(aa.shared_most_probable_clusters(ca), ca.record_ids)}
+    assert got == {frozenset("ab"), frozenset("c")}
