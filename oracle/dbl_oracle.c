@@ -13,6 +13,7 @@
 #include "dbl_oracle_priv.h"
 
 #include <math.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -1137,6 +1138,42 @@ double orc_ref_dist_prob(const orc_state *s, int64_t r, int a) {
 /* One sweep: State.nextState (State.scala:78-99) -> updatePartition (GU:156-211)               */
 /* ------------------------------------------------------------------------------------------ */
 
+typedef struct {
+  orc_state *s;
+  int sampler, tid, nthreads, status;
+  uint32_t it;
+  int64_t maxn;
+  const int64_t *bptr;
+  const int32_t *bent;
+  const double *entN;
+  int32_t *newlink;
+} link_job;
+
+/* link update of the records tid, tid + nthreads, ...: every record against every entity of its block */
+static void *link_worker(void *arg) {
+  link_job *jb = (link_job *)arg;
+  orc_state *s = jb->s;
+  const orc_model *m = s->m;
+  const int A = m->A;
+  rec_attr_t *ra = (rec_attr_t *)malloc(sizeof(rec_attr_t) * (size_t)A);
+  double *w = (double *)malloc(sizeof(double) * (size_t)(jb->maxn + 1));
+  for (int64_t r = jb->tid; r < s->R; r += jb->nthreads) {
+    int b = s->blk[s->link[r]];
+    const int32_t *cand = jb->bent + jb->bptr[b];
+    int64_t n = jb->bptr[b + 1] - jb->bptr[b];
+    prep_record(s, r, jb->sampler, ra);
+    for (int64_t j = 0; j < n; ++j)
+      w[j] = protocol_weight(s, jb->sampler, ra, s->y + (int64_t)cand[j] * A, jb->entN[cand[j]]);
+    double u[2];
+    orc_uniform2(m->seed, ORC_PHASE_LINK, jb->it, (uint32_t)r, 0, u);
+    int st;
+    int j = orc_draw_index(w, n, u[0], &st);
+    if (st) { jb->status = 1; jb->newlink[r] = s->link[r]; } else jb->newlink[r] = cand[j];
+  }
+  free(w); free(ra);
+  return NULL;
+}
+
 int orc_state_sweep(orc_state *s, int sampler) {
   const orc_model *m = s->m;
   int A = m->A, F = m->F;
@@ -1166,23 +1203,30 @@ int orc_state_sweep(orc_state *s, int sampler) {
   double *entN = (double *)malloc(sizeof(double) * (size_t)(s->E + 1));
   for (int64_t e = 0; e < s->E; ++e) entN[e] = entity_norm_product(s, s->y + e * A);
   int32_t *newlink = (int32_t *)malloc(sizeof(int32_t) * (size_t)(s->R + 1));
-  rec_attr_t *ra = (rec_attr_t *)malloc(sizeof(rec_attr_t) * (size_t)A);
   int64_t maxn = 0;
   for (int b = 0; b < nblk; ++b) if (bptr[b + 1] - bptr[b] > maxn) maxn = bptr[b + 1] - bptr[b];
-  double *w = (double *)malloc(sizeof(double) * (size_t)(maxn + 1));
-  for (int64_t r = 0; r < s->R; ++r) {
-    int b = s->blk[s->link[r]];
-    const int32_t *cand = bent + bptr[b];
-    int64_t n = bptr[b + 1] - bptr[b];
-    prep_record(s, r, sampler, ra);
-    for (int64_t j = 0; j < n; ++j) w[j] = protocol_weight(s, sampler, ra, s->y + (int64_t)cand[j] * A, entN[cand[j]]);
-    double u[2];
-    orc_uniform2(m->seed, ORC_PHASE_LINK, it, (uint32_t)r, 0, u);
-    int st;
-    int j = orc_draw_index(w, n, u[0], &st);
-    if (st) { status = 1; newlink[r] = s->link[r]; } else newlink[r] = cand[j];
+  {
+    /* the draws of different records are independent (own counter each): ORC_THREADS > 1 splits the records over
+       threads so that full-size states can be checked in seconds; the result does not depend on the split */
+    int nthreads = 1;
+    const char *ev = getenv("ORC_THREADS");
+    if (ev && atoi(ev) > 1) nthreads = atoi(ev);
+    if (nthreads > 256) nthreads = 256;
+    link_job jobs[256];
+    pthread_t th[256];
+    for (int t = 0; t < nthreads; ++t) {
+      link_job *jb = &jobs[t];
+      jb->s = s; jb->sampler = sampler; jb->it = it; jb->tid = t; jb->nthreads = nthreads; jb->maxn = maxn;
+      jb->bptr = bptr; jb->bent = bent; jb->entN = entN; jb->newlink = newlink; jb->status = 0;
+      if (nthreads == 1) link_worker(jb);
+      else pthread_create(&th[t], NULL, link_worker, jb);
+    }
+    for (int t = 0; t < nthreads; ++t) {
+      if (nthreads > 1) pthread_join(th[t], NULL);
+      status |= jobs[t].status;
+    }
   }
-  free(w); free(ra); free(entN); free(bent); free(bptr);
+  free(entN); free(bent); free(bptr);
   memcpy(s->link, newlink, sizeof(int32_t) * (size_t)s->R);
   free(newlink);
   /* (3) entity values (GU:731-755) */

@@ -79,3 +79,37 @@ def test_full_size_properties(big, sampler):
         assert np.array_equal(da[k], dc[k])
     for e in (a, b, c):
         e.close()
+
+
+def test_baseline_config3_bit_parity_with_the_oracle(monkeypatch):
+    """BASELINE.json configs[2] (100k records / 8 string attributes / 16 blocks) against the oracle itself: its link
+    update runs on all host threads (ORC_THREADS; the split does not change the draws), so a block of 6 250
+    entities per record is affordable.  Bit-exact links, values, flags, theta after every sweep."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    import dblink_b200 as D
+    from dblink_b200 import synth
+
+    monkeypatch.setenv("ORC_THREADS", str(min(128, os.cpu_count() or 1)))
+    enc = synth.generate_encoded(1, 100_000, synth.config_attrs(3), dup=0.10, distortion=0.05, missing=0.01, n_files=1)
+    indexes, x, file, F = synth.build_encoded(enc)
+    eng = D.GibbsEngine(indexes, [a.alpha for a in enc["attributes"]], [a.beta for a in enc["attributes"]], None, 2024, F)
+    eng.init_state(x, file)
+    part = D.KDTreePartitioner(4, [0, 1, 2, 3]).fit(eng.download_state()["y"])
+    eng.set_partitioner(part)
+    st, tree = bench.cpu_prepare(enc, 4, [0, 1, 2, 3])  # the oracle's own tables, initial state and tree, seed 2024
+    assert tree.n_leaves == eng.num_partitions == 16
+    d = eng.download_state()
+    for k in ("link", "y", "z", "theta", "block"):
+        np.testing.assert_array_equal(d[k], getattr(st, k), err_msg="initial " + k)
+    from oracle import oracle as O
+
+    for sampler in ("PCG-II", "PCG-I", "PCG-II"):
+        eng.sweep(sampler, 1)
+        assert st.sweep(O.SAMPLERS[sampler]) == 0
+        d = eng.download_state()
+        for k in ("theta", "link", "y", "z", "block"):
+            np.testing.assert_array_equal(d[k], getattr(st, k), err_msg=f"{sampler} {k}")
