@@ -166,3 +166,23 @@ def test_chain_targets_exact_posterior(oracle, sampler):
     tv = 0.5 * sum(abs(exact.get(k, 0.0) - counts.get(k, 0) / n_keep) for k in set(exact) | set(counts))
     assert tv < 0.03, (tv, sorted(exact.items(), key=lambda kv: -kv[1])[:4],
                        sorted(((k, v / n_keep) for k, v in counts.items()), key=lambda kv: -kv[1])[:4])
+
+
+def test_threaded_link_phase_gives_the_same_chain(oracle, monkeypatch):
+    """ORC_THREADS splits the link update over host threads; every record has its own counter-based stream, so the
+    chain is the same for any split."""
+    import numpy as np
+
+    from helpers import oracle_setup, synth_problem
+
+    g = synth_problem(seed=9, R=900, n_files=2)
+    out = {}
+    for nt in ("1", "3", "8"):
+        monkeypatch.setenv("ORC_THREADS", nt)
+        m, st, tree, ox, ofile = oracle_setup(oracle, g, 77, 2, (2, 3))
+        for s in ("PCG-II", "PCG-I", "Gibbs", "Gibbs-Sequential"):
+            assert st.sweep(oracle.SAMPLERS[s], 2) == 0
+        out[nt] = (st.link.copy(), st.y.copy(), st.z.copy(), st.theta.copy())
+    for nt in ("3", "8"):
+        for a, b in zip(out["1"], out[nt]):
+            assert np.array_equal(a, b)
