@@ -113,3 +113,34 @@ def test_baseline_config3_bit_parity_with_the_oracle(monkeypatch):
         d = eng.download_state()
         for k in ("theta", "link", "y", "z", "block"):
             np.testing.assert_array_equal(d[k], getattr(st, k), err_msg=f"{sampler} {k}")
+
+
+@pytest.mark.skipif(__import__("os").environ.get("DBL_FULLSIZE_ORACLE") != "1",
+                    reason="set DBL_FULLSIZE_ORACLE=1: one PCG-II sweep of the 1M table through the oracle "
+                           "(1.6e10 pairs; about half a minute on 128 host threads)")
+def test_baseline_config4_bit_parity_with_the_oracle(monkeypatch):
+    """BASELINE.json configs[3] (1M / 10 attributes / 64 blocks): one PCG-II and one PCG-I sweep against the oracle
+    with its link phase on all host threads.  Opt-in because of the CPU time."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    import dblink_b200 as D
+    from dblink_b200 import synth
+    from oracle import oracle as O
+
+    monkeypatch.setenv("ORC_THREADS", str(min(256, os.cpu_count() or 1)))
+    enc = synth.generate_encoded(2, 1_000_000, synth.config_attrs(4), dup=0.10, distortion=0.05, missing=0.01, n_files=2)
+    indexes, x, file, F = synth.build_encoded(enc)
+    eng = D.GibbsEngine(indexes, [a.alpha for a in enc["attributes"]], [a.beta for a in enc["attributes"]], None, 2024, F)
+    eng.init_state(x, file)
+    split = [4, 5, 6, 7, 8, 9]
+    eng.set_partitioner(D.KDTreePartitioner(6, split).fit(eng.download_state()["y"]))
+    st, tree = bench.cpu_prepare(enc, 6, split)
+    for sampler in ("PCG-II", "PCG-I"):
+        eng.sweep(sampler, 1)
+        assert st.sweep(O.SAMPLERS[sampler]) == 0
+        d = eng.download_state()
+        for k in ("theta", "link", "y", "z", "block"):
+            np.testing.assert_array_equal(d[k], getattr(st, k), err_msg=f"{sampler} {k}")
