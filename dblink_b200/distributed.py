@@ -119,6 +119,8 @@ class ShardedGibbs:
     def upload_state(self, x, file_ids, z, link, y, theta, iteration=0):
         """Every rank is handed the same full state (State.read) and keeps the blocks it owns.  The host-to-device
         traffic is shared: a rank copies its 1/world slice of each array and the slices are all-gathered."""
+        if self.owner is None:
+            raise RuntimeError("upload_state needs the partitioner and block placement of init_state first")
         x = np.asarray(x)
         y = np.asarray(y)
         if x.ndim != 2 or y.ndim != 2 or x.shape[1] != self.A or y.shape[1] != self.A:
