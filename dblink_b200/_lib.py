@@ -16,6 +16,8 @@ MAX_ATTRS = 32
 i32p = C.POINTER(C.c_int32)
 i64p = C.POINTER(C.c_int64)
 u8p = C.POINTER(C.c_uint8)
+u64p = C.POINTER(C.c_uint64)
+COMM_BLOB_BYTES = 192
 f64p = C.POINTER(C.c_double)
 vp = C.c_void_p
 
@@ -84,10 +86,21 @@ SIGNATURES = {
     "dbl_sweep_begin": (C.c_int, [vp, C.c_int, i64p, i64p]),
     "dbl_exchange_pack": (C.c_int, [vp, vp, vp]),
     "dbl_exchange_unpack": (C.c_int, [vp, vp, C.c_int64, vp, C.c_int64]),
-    "dbl_sweep_end": (C.c_int, [vp]),
+    "dbl_sweep_end": (C.c_int, [vp, i64p, C.c_double, C.c_int32]),
     "dbl_summary_words": (C.c_int32, [vp]),
     "dbl_partial_summary": (C.c_int, [vp, i64p, f64p]),
-    "dbl_set_global_summary": (C.c_int, [vp, i64p, C.c_double]),
+    "dbl_sweep_async": (C.c_int, [vp, C.c_int, C.c_int32]),
+    "dbl_sync": (C.c_int, [vp]),
+    "dbl_state_hash": (C.c_int, [vp, u64p]),
+    "dbl_block_owners": (C.c_int, [vp, i32p]),
+    "dbl_comm_export": (C.c_int, [vp, vp]),
+    "dbl_comm_import": (C.c_int, [vp, vp, C.c_int32]),
+    "dbl_set_rebalance": (C.c_int, [vp, C.c_int32, C.c_double]),
+    "dbl_last_exchange": (C.c_int, [vp, i64p, i64p, i64p]),
+    "dbl_download_owned": (C.c_int, [vp, i64p, i32p, i32p, i32p, i64p, i32p, i32p, u8p]),
+    "dbl_det_log": (C.c_double, [C.c_double]),
+    "dbl_det_exp": (C.c_double, [C.c_double]),
+    "dbl_draw_theta": (C.c_int, [C.c_int32, C.c_int32, f64p, f64p, C.c_uint64, i64p, i64p, C.c_int64, f64p]),
     "dbl_export_owned_dev": (C.c_int, [vp, vp, vp, vp, vp]),
     "dbl_owned_masks": (C.c_int, [vp, u8p, u8p]),
     "dbl_kernel_launches": (C.c_int64, [vp]),

@@ -139,12 +139,13 @@ def most_probable_signature(sig, block=65536):
         new[::S] = True                                      # a run never crosses records
         run_start = np.flatnonzero(new)
         count = np.diff(np.r_[run_start, n * S])
-        # one key per run: larger count wins, then the earlier first sample; the run index rides in the low digits
-        nrun = len(run_start)
-        key = (count.astype(np.int64) * (S + 1) + (S - first_sample[run_start])) * nrun + (nrun - 1 - np.arange(nrun))
-        rec_first_run = np.searchsorted(run_start, np.arange(n) * S)
-        top = np.maximum.reduceat(key, rec_first_run)
-        win = nrun - 1 - (top % nrun)
+        # winner per record: larger count first, then the earlier first sample (a lexicographic sort of the runs; a
+        # packed integer key would overflow int64 for chains of ~50k samples)
+        rec_of_run = run_start // S
+        by = np.lexsort((first_sample[run_start], -count, rec_of_run))
+        lead = np.ones(len(by), bool)
+        lead[1:] = rec_of_run[by][1:] != rec_of_run[by][:-1]
+        win = by[lead]                                       # one run per record, in record order
         best[lo:lo + n] = srt[run_start[win]]
         freq[lo:lo + n] = count[win] / S
     return best, freq

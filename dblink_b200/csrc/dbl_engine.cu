@@ -13,6 +13,7 @@
 // CPU oracle (oracle/dbl_oracle.c, -ffp-contract=off) reproduces every draw bit for bit.  Draw protocol:
 // DESIGN.md section 4.
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cmath>
@@ -80,30 +81,78 @@ __device__ __forceinline__ int tree_leaf(const TreeDev &t, const int *yrow) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// k_entity_post: per entity N(e) = prod_{non-const a} n_a(y_a); new block id (GU:206); entity part of the
-// summary: isolates (GU:267-269) and sum_a log phi_a(y_a) (GU:234-237, 271-274).
+// Row kernels run in one of two modes:
+//   prefix mode (inside a sweep): rows = the first ctl[CTL_OWNED_*] entries of ent_sorted / rec_sorted, i.e. exactly
+//     the entities / records of the blocks this rank owns, counted on the DEVICE (no host round trip); grid-stride,
+//     so the launch does not depend on the count; the kernel returns at once when the sweep was abandoned;
+//   mask mode (state set-up): every row whose ownership byte is set.
 // ---------------------------------------------------------------------------------------------------
-__global__ void k_entity_post(int64_t E, int A, const int *__restrict__ y, const AttrDev *__restrict__ attrs,
-                              TreeDev tree, double *__restrict__ entN, int *__restrict__ blk,
-                              const int *__restrict__ ent_rec_ptr, long long *__restrict__ counts, int iso_slot,
-                              double *__restrict__ loglik, const unsigned char *__restrict__ ent_owned) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+struct RowSet {
+  const long long *ctl;         // control block
+  const int *sorted;            // ent_sorted / rec_sorted (prefix mode) or nullptr (mask mode)
+  const unsigned char *owned;   // ownership bytes (mask mode)
+  int64_t n_all;                // E or R
+  int count_word;               // CTL_OWNED_ENT / CTL_OWNED_REC
+  __device__ __forceinline__ int64_t count() const { return sorted ? (int64_t)ctl[count_word] : n_all; }
+  __device__ __forceinline__ int64_t row(int64_t i) const {
+    if (sorted) return sorted[i];
+    return owned[i] ? i : -1;
+  }
+  __device__ __forceinline__ bool dead() const { return sorted && sweep_dead(ctl); }
+};
+#define GRID_STRIDE(i, n) \
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
+
+// one atomic per distinct key among the active lanes of the warp
+__device__ __forceinline__ void warp_hist_add(unsigned long long *bins, int key) {
+  const unsigned peers = __match_any_sync(__activemask(), key);
+  if ((__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&bins[key], (unsigned long long)__popc(peers));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_entity_post: per entity N(e) = prod_{non-const a} n_a(y_a); new block id (GU:206); entity part of the
+// summary: isolates (GU:267-269) and sum_a log phi_a(y_a) (GU:234-237, 271-274); sizes of the new blocks (the
+// input of the block -> rank placement, partitioning/LPTScheduler.scala:57-76).
+// part = partial summary words of this rank: [A*F] aggDist, [A+1] recDist, isolates, log-likelihood (f64 bits),
+// [P] entities per block, [P] records per block.
+// ---------------------------------------------------------------------------------------------------
+struct EntPostParams {
+  RowSet rows;
+  int A;
+  const int *y;
+  const AttrDev *attrs;
+  TreeDev tree;
+  double *entN;
+  int *blk;
+  const int *ent_rec_ptr;  // nullptr: no summary
+  unsigned long long *part;
+  int iso_slot, ll_slot, blk_slot;  // blk_slot < 0: no block histogram
+};
+__global__ void __launch_bounds__(256) k_entity_post(EntPostParams p) {
+  if (p.rows.dead()) return;
+  const int64_t n = p.rows.count();
   double ll = 0.0;
   int iso = 0;
-  if (e < E && ent_owned[e]) {
-    const int *ye = y + e * A;
-    double n = 1.0;
-    for (int a = 0; a < A; ++a) {
-      const AttrDev &at = attrs[a];
+  GRID_STRIDE(i, n) {
+    const int64_t e = p.rows.row(i);
+    if (e < 0) continue;
+    const int *ye = p.y + e * p.A;
+    double nn = 1.0;
+    for (int a = 0; a < p.A; ++a) {
+      const AttrDev &at = p.attrs[a];
       const int v = ye[a];
-      if (!at.is_const) n = n * at.norm[v];
+      if (!at.is_const) nn = nn * at.norm[v];
       ll += at.logphi[v];
     }
-    entN[e] = n;
-    blk[e] = tree.n_nodes > 0 ? tree_leaf(tree, ye) : 0;
-    if (ent_rec_ptr) iso = (ent_rec_ptr[e] == ent_rec_ptr[e + 1]);
+    p.entN[e] = nn;
+    const int b = p.tree.n_nodes > 0 ? tree_leaf(p.tree, ye) : 0;
+    p.blk[e] = b;
+    if (p.ent_rec_ptr) {
+      iso += (p.ent_rec_ptr[e] == p.ent_rec_ptr[e + 1]);
+      if (p.blk_slot >= 0) warp_hist_add(p.part + p.blk_slot, b);
+    }
   }
-  if (counts) {
+  if (p.ent_rec_ptr) {
     typedef cub::BlockReduce<double, 256> BR;
     typedef cub::BlockReduce<int, 256> BRI;
     __shared__ typename BR::TempStorage t1;
@@ -111,8 +160,8 @@ __global__ void k_entity_post(int64_t E, int A, const int *__restrict__ y, const
     const double s = BR(t1).Sum(ll);
     const int c = BRI(t2).Sum(iso);
     if (threadIdx.x == 0) {
-      atomicAdd(loglik, s);
-      if (c) atomicAdd((unsigned long long *)&counts[iso_slot], (unsigned long long)c);
+      if (s != 0.0) atomicAdd(reinterpret_cast<double *>(&p.part[p.ll_slot]), s);
+      if (c) atomicAdd(&p.part[p.iso_slot], (unsigned long long)c);
     }
   }
 }
@@ -179,10 +228,11 @@ __global__ void k_segment_ptr(int64_t n, int n_keys, const int *__restrict__ sor
   const int prev = (i > 0) ? min(sorted_key[i - 1] >> shift, n_keys) : -1;
   for (int k = prev + 1; k <= cur; ++k) ptr[k] = (int)i;
 }
-// prefix sums over the P blocks (P is 2^numLevels: small) -- one CTA, Hillis-Steele over chunks
+// prefix sums over the P blocks (P is 2^numLevels: small); also publishes the owned counts (everything before the
+// dummy block) in the control block -- they size the prefix-mode row kernels of the next sweep
 __global__ void k_block_scan(int P, const int *__restrict__ ent_ptr, const int *__restrict__ rec_ptr,
                              int *__restrict__ tile_ptr, int *__restrict__ cta_ptr, int warps_per_cta,
-                             int *__restrict__ cta_ptr2, int warps_per_cta2) {
+                             int *__restrict__ cta_ptr2, int warps_per_cta2, long long *__restrict__ ctl) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     int t = 0, c = 0, c2 = 0;
     for (int b = 0; b < P; ++b) {
@@ -193,6 +243,8 @@ __global__ void k_block_scan(int P, const int *__restrict__ ent_ptr, const int *
       c2 += (nr + warps_per_cta2 - 1) / warps_per_cta2;
     }
     tile_ptr[P] = t; cta_ptr[P] = c; cta_ptr2[P] = c2;
+    ctl[CTL_OWNED_ENT] = ent_ptr[P];
+    ctl[CTL_OWNED_REC] = rec_ptr[P];
   }
 }
 // tiled, block-sorted copy of the entity table: tile = { int32 y[A][TE]; double N[TE]; uint32 packed_consts[TE] }
@@ -216,20 +268,57 @@ __global__ void k_build_tiles(int64_t E, int A, const int *__restrict__ y, const
 }
 
 // ---------------------------------------------------------------------------------------------------
+// sweep bookkeeping on the device (the host only enqueues): theta draw, link commit, end of sweep
+// ---------------------------------------------------------------------------------------------------
+// updateDistProbs GU:305-320: theta[a,f] ~ Beta(alpha_a + aggDist[a,f], beta_a + N_f - aggDist[a,f]) from the GLOBAL
+// summary of the previous state.  Every rank draws the same values from the same counter-based stream (replaces
+// the broadcast, State.scala:84).  theta_prev keeps the old values: an abandoned sweep restores them.
+__global__ void k_theta(int A, int F, uint64_t seed, long long *__restrict__ ctl, const long long *__restrict__ glob,
+                        const double *__restrict__ alpha, const double *__restrict__ beta,
+                        const double *__restrict__ file_size, double *__restrict__ theta,
+                        double *__restrict__ theta_prev) {
+  if (sweep_dead(ctl)) return;
+  const uint32_t it = (uint32_t)(ctl[CTL_ITER] + 1);
+  for (int i = threadIdx.x; i < A * F; i += blockDim.x) {
+    const int a = i / F, f = i % F;
+    theta_prev[i] = theta[i];
+    theta[i] = draw_theta_one(seed, it, (uint32_t)i, alpha[a], beta[a], (double)glob[i], file_size[f]);
+  }
+  if (threadIdx.x == 0) { ctl[CTL_MOVED_ENT] = 0; ctl[CTL_MOVED_REC] = 0; }
+}
+// the link kernels write their draws to newlink; they become the state only if no categorical of the sweep was
+// without mass (the reference fails the task and no new state exists, IndexNonUniformDiscreteDist.scala:78-79)
+__global__ void k_commit_links(RowSet rows, const int *__restrict__ newlink, int *__restrict__ link) {
+  if (rows.dead()) return;
+  const int64_t n = rows.count();
+  GRID_STRIDE(i, n) {
+    const int64_t r = rows.row(i);
+    if (r >= 0) link[r] = newlink[r];
+  }
+}
+// single rank: the partial summary is the global one
+__global__ void k_reduce_local(int nw, const long long *__restrict__ ctl, const unsigned long long *__restrict__ part,
+                               long long *__restrict__ glob) {
+  if (sweep_dead(ctl)) return;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) glob[i] = (long long)part[i];
+}
+__global__ void k_finish(long long *__restrict__ ctl) {
+  if (threadIdx.x == 0 && !sweep_dead(ctl)) ctl[CTL_ITER] += 1;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // k_values: one thread per (entity, attribute).  updateEntityValueCollapsed GU:576-599 +
 // perturbedDistYCollapsed GU:534-570 (PCG-I/II); updateEntityValue GU:605-646 + perturbedDistY GU:702-727.
 // ---------------------------------------------------------------------------------------------------
 struct ValParams {
   int A, F, sampler;
   uint64_t seed;
-  uint32_t iter;
-  int64_t E;
+  RowSet rows;  // owned entities
   const AttrDev *attrs;
   const int *x, *file;
   const unsigned *zmask;
   const double *theta;
   const int *ent_rec_ptr, *rec_by_ent;
-  const unsigned char *ent_owned;
   int *y;
 };
 
@@ -300,15 +389,11 @@ __device__ __forceinline__ bool in_support(const ValParams &p, const AttrDev &at
   return row_find(at, xr, v, e);
 }
 
-__global__ void k_values(ValParams p) {
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= p.E * p.A) return;
-  const int64_t e = tid / p.A;
-  if (!p.ent_owned[e]) return;
-  const int a = (int)(tid % p.A);
+// new value of attribute a of entity e
+__device__ int value_update(const ValParams &p, uint32_t iter, int64_t e, int a) {
   const AttrDev &at = p.attrs[a];
   const bool collapsed = (p.sampler == DBL_PCG_I || p.sampler == DBL_PCG_II);
-  const U2 u = uniform2(p.seed, PH_VALUE, p.iter, (uint32_t)e, (uint32_t)a);
+  const U2 u = uniform2(p.seed, PH_VALUE, iter, (uint32_t)e, (uint32_t)a);
   const int lo = p.ent_rec_ptr[e], hi = p.ent_rec_ptr[e + 1];
   const int *rec = p.rec_by_ent;
 
@@ -317,19 +402,17 @@ __global__ void k_values(ValParams p) {
   BaseDist b;
   if (k == 0) {  // GU:588-589
     base_init(b, at, 0);
-    p.y[tid] = base_draw(b, u.u1);
-    return;
+    return base_draw(b, u.u1);
   }
   if (!collapsed) {
     for (int i = lo; i < hi; ++i) {  // GU:619-630
       const int r = rec[i];
       const int xr = p.x[(int64_t)r * p.A + a];
-      if (xr >= 0 && !((p.zmask[r] >> a) & 1u)) { p.y[tid] = xr; return; }
+      if (xr >= 0 && !((p.zmask[r] >> a) & 1u)) return xr;
     }
     if (at.is_const) {  // GU:633-634
       base_init(b, at, 0);
-      p.y[tid] = base_draw(b, u.u1);
-      return;
+      return base_draw(b, u.u1);
     }
   }
   base_init(b, at, k);  // GU:584-586
@@ -354,8 +437,8 @@ __global__ void k_values(ValParams p) {
         if (collapsed) G = G * (1.0 + extra);
       } else {
         v = at.col[q0 + q];
-        const double e = at.expsim[q0 + q];
-        G = G * ((collapsed && v == xr) ? e + extra : e);
+        const double ex = at.expsim[q0 + q];
+        G = G * ((collapsed && v == xr) ? ex + extra : ex);
       }
       return base_prob(b, v) * (G - 1.0);  // GU:567 / 724
     };
@@ -363,10 +446,7 @@ __global__ void k_values(ValParams p) {
       int v;
       total += weight(q, v);
     }
-    if (u.u0 < 1.0 / (1.0 + total)) {  // GU:593-594
-      p.y[tid] = base_draw(b, u.u1);
-      return;
-    }
+    if (u.u0 < 1.0 / (1.0 + total)) return base_draw(b, u.u1);  // GU:593-594
     target = u.u1 * total;
     for (int q = 0; q < nv && picked < 0; ++q) {
       int v;
@@ -377,8 +457,7 @@ __global__ void k_values(ValParams p) {
     }
     if (picked < 0) picked = last_pos;
     if (picked < 0) picked = base_draw(b, u.u1);
-    p.y[tid] = picked;
-    return;
+    return picked;
   }
   for (int pass = 0; pass < 2; ++pass) {
     for (int i = lo; i < hi; ++i) {
@@ -414,16 +493,25 @@ __global__ void k_values(ValParams p) {
       }
     }
     if (pass == 0) {
-      if (u.u0 < 1.0 / (1.0 + total)) {  // GU:593-594
-        p.y[tid] = base_draw(b, u.u1);
-        return;
-      }
+      if (u.u0 < 1.0 / (1.0 + total)) return base_draw(b, u.u1);  // GU:593-594
       target = u.u1 * total;
     }
   }
   if (picked < 0) picked = last_pos;
   if (picked < 0) picked = base_draw(b, u.u1);
-  p.y[tid] = picked;
+  return picked;
+}
+
+__global__ void __launch_bounds__(128) k_values(ValParams p) {
+  if (p.rows.dead()) return;
+  const uint32_t iter = (uint32_t)(p.rows.ctl[CTL_ITER] + 1);
+  const int64_t n = p.rows.count() * p.A;
+  GRID_STRIDE(t, n) {
+    const int64_t e = p.rows.row(t / p.A);
+    if (e < 0) continue;
+    const int a = (int)(t % p.A);
+    p.y[e * p.A + a] = value_update(p, iter, e, a);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -433,23 +521,26 @@ __global__ void k_values(ValParams p) {
 struct DistParams {
   int A, F, draw;
   uint64_t seed;
-  uint32_t iter;
-  int64_t R;
+  RowSet rows;  // owned records
   const AttrDev *attrs;
-  const int *x, *file, *link, *y;
+  const int *x, *file, *link, *y, *blk;
   unsigned *zmask;
   const double *theta;
-  long long *counts;  // [A*F] aggDist, then [A+1] recDist
-  double *loglik;
-  const unsigned char *rec_owned;
+  unsigned long long *part;  // [A*F] aggDist, then [A+1] recDist, ...
+  int ll_slot, blk_slot;     // blk_slot < 0: no block histogram
 };
 
-__global__ void k_dist(DistParams p) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_dist(DistParams p) {
+  if (p.rows.dead()) return;
+  const uint32_t iter = (uint32_t)(p.rows.ctl[CTL_ITER] + 1);
+  const int64_t n = p.rows.count();
   double ll = 0.0;
-  if (r < p.R && p.rec_owned[r]) {
+  GRID_STRIDE(i, n) {
+    const int64_t r = p.rows.row(i);
+    if (r < 0) continue;
     const int f = p.file[r];
-    const int *ye = p.y + (int64_t)p.link[r] * p.A;
+    const int e = p.link[r];
+    const int *ye = p.y + (int64_t)e * p.A;
     unsigned zm = p.zmask[r];
     int nd = 0;
     for (int a = 0; a < p.A; ++a) {
@@ -460,12 +551,12 @@ __global__ void k_dist(DistParams p) {
       if (p.draw) {
         const double th = p.theta[a * p.F + f];
         if (xv < 0) {
-          const U2 u = uniform2(p.seed, PH_DIST, p.iter, (uint32_t)r, (uint32_t)a);
+          const U2 u = uniform2(p.seed, PH_DIST, iter, (uint32_t)r, (uint32_t)a);
           z = u.u0 < th;  // GU:331-334
         } else if (xv != yv) {
           z = true;  // GU:352-354
         } else {
-          const U2 u = uniform2(p.seed, PH_DIST, p.iter, (uint32_t)r, (uint32_t)a);
+          const U2 u = uniform2(p.seed, PH_DIST, iter, (uint32_t)r, (uint32_t)a);
           double pr1 = th * at.phi[xv];
           if (!at.is_const) {
             double ediag = 1.0;
@@ -484,27 +575,25 @@ __global__ void k_dist(DistParams p) {
       }
       if (z) {
         ++nd;
-        atomicAdd((unsigned long long *)&p.counts[a * p.F + f], 1ull);  // GU:246
-        if (xv >= 0) {                                                   // GU:248-258
+        atomicAdd(&p.part[a * p.F + f], 1ull);  // GU:246
+        if (xv >= 0) {                          // GU:248-258
           ll += at.logphi[xv];
           if (!at.is_const) {
             ll += at.lognorm[yv];
-            double e;
-            if (row_find(at, xv, yv, e)) ll += log(e);
+            double ex;
+            if (row_find(at, xv, yv, ex)) ll += log(ex);
           }
         }
       }
     }
     if (p.draw) p.zmask[r] = zm;
-    // GU:265 -- warp-aggregated: one atomic per distinct count in the warp
-    const unsigned peers = __match_any_sync(__activemask(), nd);
-    if ((__ffs(peers) - 1) == (int)(threadIdx.x & 31))
-      atomicAdd((unsigned long long *)&p.counts[p.A * p.F + nd], (unsigned long long)__popc(peers));
+    warp_hist_add(p.part + p.A * p.F, nd);  // GU:265
+    if (p.blk_slot >= 0) warp_hist_add(p.part + p.blk_slot, p.blk[e]);
   }
   typedef cub::BlockReduce<double, 256> BR;
   __shared__ typename BR::TempStorage tmp;
   const double s = BR(tmp).Sum(ll);
-  if (threadIdx.x == 0 && s != 0.0) atomicAdd(p.loglik, s);
+  if (threadIdx.x == 0 && s != 0.0) atomicAdd(reinterpret_cast<double *>(&p.part[p.ll_slot]), s);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -591,6 +680,269 @@ __global__ void k_mark_rec_owned(int64_t R, const int *__restrict__ link, const 
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r < R) rec_owned[r] = ent_owned[link[r]];
 }
+
+// ---- (1) peer-to-peer exchange: the data plane of a sharded dbl_sweep ---------------------------------------
+// Every rank owns one communication buffer (cudaMalloc, exported with cudaIpc, mapped by every peer over
+// NVLink/NVSwitch).  The kernels that decide which clusters leave write the messages STRAIGHT into the destination
+// rank's receive buffer (slot from a system-scope atomic on the destination's cursor), the partial summary goes into
+// a slot of every peer, one flag barrier follows, then every rank unpacks what it received and reduces the summary
+// slots in rank order.  No host round trip, no separate pack / count / send / receive steps.  Receive buffers have
+// room for EVERY entity and record (an entity moves at most once per sweep), and everything is double buffered by
+// barrier parity, so a fast rank can run ahead by one sweep without overwriting what a slow one still reads.
+constexpr int MAX_WORLD = 16;
+struct CommDev {
+  int rank, world, A, nws;  // nws = summary words per slot (partial summary + status)
+  long long cap_e, cap_r;
+  unsigned char *base[MAX_WORLD];  // communication buffer of every rank (own buffer at [rank])
+  size_t off_cursor, off_slots, off_ent, off_rec;
+  __device__ __forceinline__ unsigned long long *arrive(int d) const { return reinterpret_cast<unsigned long long *>(base[d]); }
+  __device__ __forceinline__ unsigned long long *cursor(int d, int par) const {
+    return reinterpret_cast<unsigned long long *>(base[d] + off_cursor) + 2 * par;
+  }
+  __device__ __forceinline__ long long *slot(int d, int par, int src) const {
+    return reinterpret_cast<long long *>(base[d] + off_slots) + ((size_t)par * world + src) * nws;
+  }
+  __device__ __forceinline__ int *recv_ent(int d, int par) const {
+    return reinterpret_cast<int *>(base[d] + off_ent) + (size_t)par * cap_e * (A + 1);
+  }
+  __device__ __forceinline__ int *recv_rec(int d, int par) const {
+    return reinterpret_cast<int *>(base[d] + off_rec) + (size_t)par * cap_r * 3;
+  }
+};
+__device__ __forceinline__ int comm_parity(const long long *ctl) { return (int)((ctl[CTL_EPOCH] + 1) & 1); }
+
+// slot in rank d's buffer for every lane that has a message for d: one system-scope atomic per destination and warp.
+// Every lane of the warp calls it (d < 0: nothing to send).
+__device__ __forceinline__ long long remote_slot(unsigned long long *const *cursors_unused, const CommDev &c, int par,
+                                                 int which, int d) {
+  (void)cursors_unused;
+  const int lane = threadIdx.x & 31;
+  const unsigned grp = __match_any_sync(FULL, d);
+  const int leader = __ffs(grp) - 1;
+  unsigned long long basev = 0;
+  if (d >= 0 && lane == leader) basev = atomicAdd_system(c.cursor(d, par) + which, (unsigned long long)__popc(grp));
+  basev = __shfl_sync(FULL, basev, leader);
+  return (long long)basev + __popc(grp & ((1u << lane) - 1u));
+}
+
+struct MoveParams {
+  CommDev c;
+  long long *ctl;
+  int A;
+  const int *ent_sorted, *rec_sorted;
+  const int *blk, *owner, *link, *y;
+  const unsigned *zmask;
+  int *ent_dest;
+  unsigned char *ent_owned, *rec_owned;
+};
+__global__ void __launch_bounds__(256) k_move_ent(MoveParams p) {
+  if (sweep_dead(p.ctl)) return;
+  const int64_t n = p.ctl[CTL_OWNED_ENT];
+  const int64_t n32 = (n + 31) & ~(int64_t)31;  // whole warps stay in the loop together
+  const int par = comm_parity(p.ctl);
+  int sent = 0;
+  GRID_STRIDE(i, n32) {
+    int d = -1;
+    int64_t e = -1;
+    if (i < n) {
+      e = p.ent_sorted[i];
+      const int o = p.owner[p.blk[e]];
+      if (o != p.c.rank) d = o;
+      p.ent_dest[e] = d;
+    }
+    const long long slot = remote_slot(nullptr, p.c, par, 0, d);
+    if (d >= 0) {
+      int *m = p.c.recv_ent(d, par) + slot * (p.A + 1);
+      m[0] = (int)e;
+      for (int a = 0; a < p.A; ++a) m[1 + a] = p.y[e * p.A + a];
+      p.ent_owned[e] = 0;
+      ++sent;
+    }
+  }
+  if (sent) atomicAdd(reinterpret_cast<unsigned long long *>(&p.ctl[CTL_MOVED_ENT]), (unsigned long long)sent);
+}
+__global__ void __launch_bounds__(256) k_move_rec(MoveParams p) {
+  if (sweep_dead(p.ctl)) return;
+  const int64_t n = p.ctl[CTL_OWNED_REC];
+  const int64_t n32 = (n + 31) & ~(int64_t)31;
+  const int par = comm_parity(p.ctl);
+  int sent = 0;
+  GRID_STRIDE(i, n32) {
+    int d = -1;
+    int64_t r = -1;
+    if (i < n) {
+      r = p.rec_sorted[i];
+      d = p.ent_dest[p.link[r]];
+    }
+    const long long slot = remote_slot(nullptr, p.c, par, 1, d);
+    if (d >= 0) {
+      int *m = p.c.recv_rec(d, par) + slot * 3;
+      m[0] = (int)r; m[1] = p.link[r]; m[2] = (int)p.zmask[r];
+      p.rec_owned[r] = 0;
+      ++sent;
+    }
+  }
+  if (sent) atomicAdd(reinterpret_cast<unsigned long long *>(&p.ctl[CTL_MOVED_REC]), (unsigned long long)sent);
+}
+// partial summary (+ status) into a slot of every rank, then the barrier: rank r stores the new epoch into
+// arrive[r] of every peer (release, system scope) and waits until its own arrive[] shows every peer (acquire).
+// Never skipped, even when the sweep was abandoned locally: the peers are waiting.  A peer that does not show up
+// within timeout_cycles sets ST_PEER_TIMEOUT instead of hanging the GPU.
+__global__ void __launch_bounds__(256) k_publish_barrier(CommDev c, long long *ctl, const unsigned long long *part, int nw,
+                                                         long long timeout_cycles) {
+  const long long epoch = ctl[CTL_EPOCH] + 1;
+  const int par = (int)(epoch & 1);
+  __shared__ int s_timeout;
+  if (threadIdx.x == 0) s_timeout = 0;
+  for (int i = threadIdx.x; i < c.nws; i += blockDim.x) {
+    const long long v = (i < nw) ? (long long)part[i] : ctl[CTL_STATUS];
+    for (int d = 0; d < c.world; ++d) c.slot(d, par, c.rank)[i] = v;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < c.world) {
+    const int d = threadIdx.x;
+    __threadfence_system();
+    unsigned long long *flag = c.arrive(d) + c.rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"((unsigned long long)epoch) : "memory");
+    const unsigned long long *mine = c.arrive(c.rank) + d;
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned long long v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+      if (v >= (unsigned long long)epoch) break;
+      if (clock64() - t0 > timeout_cycles) { s_timeout = 1; break; }
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ctl[CTL_EPOCH] = epoch;
+    if (s_timeout) ctl[CTL_STATUS] |= ST_PEER_TIMEOUT;
+  }
+}
+// what the peers wrote for this rank (parity of the barrier just passed)
+__device__ __forceinline__ int done_parity(const long long *ctl) { return (int)(ctl[CTL_EPOCH] & 1); }
+struct UnpackParams {
+  CommDev c;
+  const long long *ctl;
+  int A;
+  const AttrDev *attrs;
+  TreeDev tree;
+  int *y, *blk, *link;
+  double *entN;
+  unsigned *zmask;
+  unsigned char *ent_owned, *rec_owned;
+};
+__global__ void __launch_bounds__(256) k_unpack_ent_p2p(UnpackParams p) {
+  if (p.ctl[CTL_STATUS] & ST_PEER_TIMEOUT) return;
+  const int par = done_parity(p.ctl);
+  const int64_t n = (int64_t) * reinterpret_cast<volatile unsigned long long *>(p.c.cursor(p.c.rank, par));
+  const int *buf = p.c.recv_ent(p.c.rank, par);
+  GRID_STRIDE(i, n) {
+    const int *m = buf + i * (p.A + 1);
+    const int64_t e = m[0];
+    double nn = 1.0;
+    for (int a = 0; a < p.A; ++a) {
+      const int v = m[1 + a];
+      p.y[e * p.A + a] = v;
+      if (!p.attrs[a].is_const) nn = nn * p.attrs[a].norm[v];
+    }
+    p.entN[e] = nn;
+    p.blk[e] = p.tree.n_nodes > 0 ? tree_leaf(p.tree, m + 1) : 0;
+    p.ent_owned[e] = 1;
+  }
+}
+__global__ void __launch_bounds__(256) k_unpack_rec_p2p(UnpackParams p) {
+  if (p.ctl[CTL_STATUS] & ST_PEER_TIMEOUT) return;
+  const int par = done_parity(p.ctl);
+  const int64_t n = (int64_t) * reinterpret_cast<volatile unsigned long long *>(p.c.cursor(p.c.rank, par) + 1);
+  const int *buf = p.c.recv_rec(p.c.rank, par);
+  GRID_STRIDE(i, n) {
+    const int *m = buf + i * 3;
+    const int64_t r = m[0];
+    p.link[r] = m[1];
+    p.zmask[r] = (unsigned)m[2];
+    p.rec_owned[r] = 1;
+  }
+}
+// global summary = sum of the slots in rank order (SummaryAccumulators.scala:54-63; integer words exact, the
+// log-likelihood word is an f64 sum in a fixed order, so every rank gets identical bits); a peer's status makes the
+// sweep fail here as well; the cursors of this parity are cleared for their next use two barriers from now
+__global__ void __launch_bounds__(256) k_reduce_peers(CommDev c, long long *ctl, int nw, int ll_slot,
+                                                      long long *__restrict__ glob) {
+  const int par = done_parity(ctl);
+  __shared__ long long s_status;
+  if (threadIdx.x == 0) s_status = 0;
+  __syncthreads();
+  const bool timed_out = (ctl[CTL_STATUS] & ST_PEER_TIMEOUT) != 0;
+  for (int i = threadIdx.x; i < c.nws && !timed_out; i += blockDim.x) {
+    if (i == nw) {  // status word
+      long long st = 0;
+      for (int s = 0; s < c.world; ++s) st |= c.slot(c.rank, par, s)[i];
+      if (st) atomicOr(reinterpret_cast<unsigned long long *>(&s_status), (unsigned long long)st);
+    } else if (i == ll_slot) {
+      double sum = 0.0;
+      for (int s = 0; s < c.world; ++s) sum += __longlong_as_double(c.slot(c.rank, par, s)[i]);
+      glob[i] = __double_as_longlong(sum);
+    } else {
+      long long sum = 0;
+      for (int s = 0; s < c.world; ++s) sum += c.slot(c.rank, par, s)[i];
+      glob[i] = sum;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_status && !ctl[CTL_STATUS]) ctl[CTL_STATUS] = (s_status & ST_ZERO_MASS) ? (ST_ZERO_MASS | ST_PEER_ERROR) : ST_PEER_ERROR;
+    unsigned long long *cur = c.cursor(c.rank, par);
+    cur[0] = 0; cur[1] = 0;
+  }
+}
+// Block -> rank placement on the device (partitioning/LPTScheduler.scala:57-76: longest processing time first, cost
+// of a block = records x entities), re-evaluated from the GLOBAL block sizes of the state just produced, so every
+// rank computes the same table.  The new table only re-routes: blocks migrate with the next exchange as ordinary
+// cluster messages.  Adopted only when the current table is more than `threshold` above the LPT makespan.
+__global__ void k_lpt(int P, int world, int ent_slot, int rec_slot, const long long *__restrict__ glob,
+                      long long *__restrict__ ctl, int period, double threshold, int *__restrict__ owner,
+                      int *__restrict__ scratch /* 2*P ints */, double *__restrict__ dscratch /* P + world doubles */) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (sweep_dead(ctl) || period <= 0 || ((ctl[CTL_ITER] + 1) % period) != 0) return;
+  int *order = scratch, *cand = scratch + P;
+  double *cost = dscratch, *load = dscratch + P;
+  double total = 0.0;
+  for (int b = 0; b < P; ++b) {
+    cost[b] = (double)glob[ent_slot + b] * (double)glob[rec_slot + b];
+    total += cost[b];
+    order[b] = b;
+  }
+  if (!(total > 0.0)) return;
+  for (int i = 1; i < P; ++i) {  // insertion sort by (-cost, block id)
+    const int b = order[i];
+    int j = i - 1;
+    while (j >= 0 && (cost[order[j]] < cost[b] || (cost[order[j]] == cost[b] && order[j] > b))) { order[j + 1] = order[j]; --j; }
+    order[j + 1] = b;
+  }
+  for (int r = 0; r < world; ++r) load[r] = 0.0;
+  for (int i = 0; i < P; ++i) {
+    const int b = order[i];
+    int best = 0;
+    for (int r = 1; r < world; ++r) if (load[r] < load[best]) best = r;
+    cand[b] = best;
+    load[best] += cost[b];
+  }
+  double lpt_max = 0.0;
+  for (int r = 0; r < world; ++r) lpt_max = fmax(lpt_max, load[r]);
+  for (int r = 0; r < world; ++r) load[r] = 0.0;
+  for (int b = 0; b < P; ++b) load[owner[b]] += cost[b];
+  double cur_max = 0.0;
+  for (int r = 0; r < world; ++r) cur_max = fmax(cur_max, load[r]);
+  if (cur_max > threshold * lpt_max) {
+    for (int b = 0; b < P; ++b) owner[b] = cand[b];
+    ctl[CTL_REPLACED] += 1;
+  }
+}
+
+// ---- (2) host-mediated exchange (multi-node / no peer access): counts to the host, messages packed into caller
+// buffers, the host moves them (e.g. NCCL all-to-all) and hands back what arrived -----------------------------------
 __global__ void k_move_count_ent(int64_t E, const int *__restrict__ blk, const int *__restrict__ owner, int rank,
                                  const unsigned char *__restrict__ ent_owned, int *__restrict__ ent_dest,
                                  unsigned long long *__restrict__ cnt) {
@@ -615,7 +967,7 @@ __global__ void k_move_pack_ent(int64_t E, int A, const int *__restrict__ y, con
                                 int *__restrict__ buf) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
-  const int d = ent_dest[e];
+  const int d = ent_owned[e] ? ent_dest[e] : -1;
   if (d < 0) return;
   const unsigned long long slot = atomicAdd(&cursor[d], 1ull);
   int *m = buf + slot * (A + 1);
@@ -634,11 +986,6 @@ __global__ void k_move_pack_rec(int64_t R, const int *__restrict__ link, const u
   int *m = buf + slot * 3;
   m[0] = (int)r; m[1] = link[r]; m[2] = (int)zmask[r];
   rec_owned[r] = 0;
-}
-__global__ void k_merge_links(int64_t R, const unsigned char *__restrict__ rec_owned, const int *__restrict__ old_link,
-                              int *__restrict__ new_link) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < R && !rec_owned[r]) new_link[r] = old_link[r];
 }
 __global__ void k_unpack_ent(int64_t n, int A, const int *__restrict__ buf, const AttrDev *__restrict__ attrs,
                              TreeDev tree, int *__restrict__ y, double *__restrict__ entN, int *__restrict__ blk,
@@ -667,8 +1014,12 @@ __global__ void k_unpack_rec(int64_t n, const int *__restrict__ buf, int *__rest
   zmask[r] = (unsigned)m[2];
   rec_owned[r] = 1;
 }
+__global__ void k_set_words(int n, const long long *__restrict__ src, long long *__restrict__ dst) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
 
-// owned rows of the state into caller-provided device buffers, zeros elsewhere (the host sums them over ranks)
+// ---- read-out of a sharded state --------------------------------------------------------------------------
+// owned rows of the state into caller-provided device buffers, zeros elsewhere (summing over ranks = full state)
 __global__ void k_export_ent(int64_t E, int A, const unsigned char *__restrict__ owned, const int *__restrict__ y,
                              const int *__restrict__ blk, int *__restrict__ y_out, int *__restrict__ blk_out) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -687,6 +1038,61 @@ __global__ void k_export_rec(int64_t R, int A, const unsigned char *__restrict__
   const unsigned zm = o ? zmask[r] : 0u;
   for (int a = 0; a < A; ++a) z_out[r * A + a] = (zm >> a) & 1u;
 }
+// owned rows only, compacted in the order of ent_sorted / rec_sorted (block-major): ids + rows
+__global__ void k_gather_ent(int64_t n, int A, const int *__restrict__ ent_sorted, const int *__restrict__ y,
+                             const int *__restrict__ blk, int *__restrict__ ids, int *__restrict__ y_out,
+                             int *__restrict__ blk_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t e = ent_sorted[i];
+  ids[i] = (int)e;
+  for (int a = 0; a < A; ++a) y_out[i * A + a] = y[e * A + a];
+  blk_out[i] = blk[e];
+}
+__global__ void k_gather_rec(int64_t n, int A, const int *__restrict__ rec_sorted, const int *__restrict__ link,
+                             const unsigned *__restrict__ zmask, int *__restrict__ ids, int *__restrict__ link_out,
+                             unsigned char *__restrict__ z_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t r = rec_sorted[i];
+  ids[i] = (int)r;
+  link_out[i] = link[r];
+  const unsigned zm = zmask[r];
+  for (int a = 0; a < A; ++a) z_out[i * A + a] = (zm >> a) & 1u;
+}
+// Order-independent 64-bit fingerprint of the owned rows: sum over rows of a mixed hash of (row id, row contents).
+// Sums of the per-rank values (mod 2^64) are the same for every rank count and placement.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(256) k_state_hash(RowSet ents, RowSet recs, int A, const int *__restrict__ y,
+                                                    const int *__restrict__ link, const unsigned *__restrict__ zmask,
+                                                    unsigned long long *__restrict__ out /*2*/) {
+  unsigned long long he = 0, hr = 0;
+  const int64_t ne = ents.count(), nr = recs.count();
+  GRID_STRIDE(i, ne) {
+    const int64_t e = ents.row(i);
+    if (e < 0) continue;
+    unsigned long long h = mix64(0xE000000000000000ull ^ (unsigned long long)e);
+    for (int a = 0; a < A; ++a) h = mix64(h ^ (unsigned long long)(unsigned)y[e * A + a]);
+    he += h;
+  }
+  GRID_STRIDE(i, nr) {
+    const int64_t r = recs.row(i);
+    if (r < 0) continue;
+    unsigned long long h = mix64(0xA000000000000000ull ^ (unsigned long long)r);
+    h = mix64(h ^ (unsigned long long)(unsigned)link[r]);
+    h = mix64(h ^ (unsigned long long)zmask[r]);
+    hr += h;
+  }
+  typedef cub::BlockReduce<unsigned long long, 256> BR;
+  __shared__ typename BR::TempStorage t1, t2;
+  const unsigned long long se = BR(t1).Sum(he), sr = BR(t2).Sum(hr);
+  if (threadIdx.x == 0) { atomicAdd(&out[0], se); atomicAdd(&out[1], sr); }
+}
 
 // ---------------------------------------------------------------------------------------------------
 // host-side context
@@ -703,6 +1109,21 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
   ~DevBuf() { release(); }
 };
+
+// what dbl_comm_export hands to the peers (DBL_COMM_BLOB_BYTES)
+struct CommBlob {
+  uint32_t magic;
+  int32_t rank, world, device;
+  int64_t pid;
+  uint64_t ptr;  // address in the exporting process (used when the importer IS that process)
+  uint64_t bytes;
+  int64_t E, R;
+  int32_t A, nws;
+  cudaIpcMemHandle_t handle;
+  char pad[DBL_COMM_BLOB_BYTES - 4 - 12 - 8 - 8 - 8 - 16 - 8 - (int)sizeof(cudaIpcMemHandle_t)];
+};
+static_assert(sizeof(CommBlob) == DBL_COMM_BLOB_BYTES, "blob layout");
+constexpr uint32_t COMM_MAGIC = 0xDB1B2002u;
 
 struct dbl_ctx {
   int A = 0, F = 0, P = 1, device = 0;
@@ -725,6 +1146,7 @@ struct dbl_ctx {
   std::vector<AttrDev> h_attrs;
   DevBuf<int> tree_buf;
   TreeDev tree{};
+  DevBuf<double> prior;  // alpha[A], beta[A], file sizes[F] (k_theta)
 
   // state
   int64_t R = 0, E = 0, iteration = 0;
@@ -733,23 +1155,58 @@ struct dbl_ctx {
   DevBuf<uint8_t> zbytes;  // staging for the byte-per-flag host format of z
   DevBuf<int> vflag, file_cnt;
   DevBuf<unsigned> zmask;
-  DevBuf<double> entN, theta;
+  DevBuf<double> entN;
   std::vector<double> h_theta;
   std::vector<int64_t> file_sizes;
+
+  // control block (one allocation, mirrored in pinned host memory by snapshot()):
+  //   [CTL_WORDS] ctl | [nw] partial summary | [nw] global summary | [A*F] theta | [A*F] theta_prev | [2] hash
+  DevBuf<long long> cb;
+  long long *h_cb = nullptr;  // pinned
+  size_t cb_words = 0;
+  int nw = 0;  // summary words: A*F + (A+1) + 2 + 2*P
+  long long *ctl() const { return cb.p; }
+  unsigned long long *part() const { return reinterpret_cast<unsigned long long *>(cb.p + CTL_WORDS); }
+  long long *glob() const { return cb.p + CTL_WORDS + nw; }
+  double *theta() const { return reinterpret_cast<double *>(cb.p + CTL_WORDS + 2 * (size_t)nw); }
+  double *theta_prev() const { return theta() + (size_t)A * F; }
+  unsigned long long *hash_words() const { return reinterpret_cast<unsigned long long *>(theta_prev() + (size_t)A * F); }
+  const long long *h_ctl() const { return h_cb; }
+  const long long *h_part() const { return h_cb + CTL_WORDS; }
+  const long long *h_glob() const { return h_cb + CTL_WORDS + nw; }
+  const double *h_theta_dev() const { return reinterpret_cast<const double *>(h_cb + CTL_WORDS + 2 * (size_t)nw); }
+  int n_counts() const { return A * F + (A + 1) + 2; }  // words a host-mediated all-reduce carries
+  int iso_slot() const { return A * F + (A + 1); }
+  int ll_slot() const { return A * F + (A + 1) + 1; }
+  int blk_ent_slot() const { return n_counts(); }
+  int blk_rec_slot() const { return n_counts() + P; }
 
   // ownership (multi-GPU sharding by block)
   std::vector<int> owner_h;  // P entries; default: everything owned by this rank
   DevBuf<int> owner, ent_dest, ent_key, link_key;
   DevBuf<unsigned char> ent_owned, rec_owned;
-  DevBuf<unsigned long long> move_cnt;  // [2*world] counts then [2*world] cursors
+  DevBuf<unsigned long long> move_cnt;  // host-mediated exchange: [2*world] counts then [2*world] cursors
   std::vector<int64_t> h_move_ent, h_move_rec;
   bool in_sweep = false, in_block_sweep = false;
   int block_sampler = 0;
   std::vector<char> block_done;
   DevBuf<int> blk_frozen;
+  bool all_owned = true;  // no shard has been carved out of the replicated state yet
+
+  // peer-to-peer exchange
+  DevBuf<unsigned char> comm_buf;
+  size_t comm_bytes = 0;
+  CommDev comm{};
+  bool comm_ready = false;
+  std::vector<void *> ipc_opened;
+  DevBuf<int> lpt_scratch;
+  DevBuf<double> lpt_dscratch;
+  int rebalance_period = 16;
+  double rebalance_threshold = 1.03;
+  long long barrier_timeout_cycles = 20000000000LL;  // ~10 s at 1.9 GHz
 
   // layout
-  DevBuf<int> iota, blk_sorted, ent_sorted, rec_key, rec_key_sorted, rec_sorted, ent_cnt, rec_cnt;
+  DevBuf<int> iota, blk_sorted, ent_sorted, rec_key, rec_key_sorted, rec_sorted;
   DevBuf<int> ent_ptr, tile_ptr, rec_ptr, cta_ptr, cta_ptr2, tiles;
   // inverted index of the block tables for the pruned PCG-I link kernel (built on demand, once per sweep)
   DevBuf<unsigned long long> inv_key_in, inv_key;
@@ -760,35 +1217,54 @@ struct dbl_ctx {
   size_t inv_tmp_bytes = 0;
   bool inv_valid = false;
   int inv_vbits = 32;
-  DevBuf<int> link_sorted, rec_by_ent, ent_rec_cnt, ent_rec_ptr;
+  DevBuf<int> link_sorted, rec_by_ent, ent_rec_ptr;
   DevBuf<unsigned char> rec_class;  // static cost class of a record (k_rec_class)
   DevBuf<unsigned char> cub_tmp;
   size_t cub_bytes = 0;
   int max_ctas = 0;
+  DevBuf<int> gather_i;  // staging of dbl_download_owned
+  DevBuf<unsigned char> gather_b;
 
-  // summary
-  DevBuf<long long> counts;  // A*F + (A+1) + 2
-  DevBuf<double> loglik;
-  DevBuf<int> status;
-  DevBuf<unsigned long long> pairs;
-  std::vector<long long> h_counts;
-  double h_loglik_part = 0.0;
+  // host copies refreshed by snapshot()
   int64_t h_pairs = 0;
-  int h_owned_ent = -1;  // entities in the blocks this rank owns (= ent_ptr[P]) after the last relayout; -1 = unknown
+  int64_t h_owned_ent = -1, h_owned_rec = -1;  // -1 = not known on the host since the last re-partitioning
 
   int64_t launches = 0;
   double link_ms = 0.0;
   int link_mode = 0;  // 0 auto, 1 generic kernel everywhere, 2 dense TMA kernels everywhere (no pruning)
   double last_sweep_ms = 0.0;
   int64_t link_launches = 0;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_events;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_events, event_pool;
+  size_t pcg2_smem_cfg = 0, match_smem_cfg = 0;  // dynamic shared memory opted in on THIS device
+  bool async_open = false;  // sweeps enqueued by dbl_sweep_async, not yet collected by dbl_sync
 
   void set_error(const std::string &s) { err = s; }
-  int n_counts() const { return A * F + (A + 1) + 2; }
-  int iso_slot() const { return A * F + (A + 1); }
 };
 
 static inline int grid_for(int64_t n, int bs) { return (int)std::max<int64_t>(1, (n + bs - 1) / bs); }
+// grid of a grid-stride kernel over at most n rows
+static inline int grid_rows(int64_t n, int bs) {
+  return (int)std::min<int64_t>(148 * (2048 / bs), std::max<int64_t>(1, (n + bs - 1) / bs));
+}
+
+static RowSet rows_prefix(dbl_ctx *ctx, bool ents) {
+  RowSet r;
+  r.ctl = ctx->ctl();
+  r.sorted = ents ? ctx->ent_sorted.p : ctx->rec_sorted.p;
+  r.owned = nullptr;
+  r.n_all = ents ? ctx->E : ctx->R;
+  r.count_word = ents ? CTL_OWNED_ENT : CTL_OWNED_REC;
+  return r;
+}
+static RowSet rows_masked(dbl_ctx *ctx, bool ents) {
+  RowSet r;
+  r.ctl = ctx->ctl();
+  r.sorted = nullptr;
+  r.owned = ents ? ctx->ent_owned.p : ctx->rec_owned.p;
+  r.n_all = ents ? ctx->E : ctx->R;
+  r.count_word = ents ? CTL_OWNED_ENT : CTL_OWNED_REC;
+  return r;
+}
 
 static int upload_tree(dbl_ctx *ctx, const dbl_kdtree *t) {
   if (t) {
@@ -901,12 +1377,43 @@ static int upload_model(dbl_ctx *ctx, const dbl_model_desc *d) {
   return upload_tree(ctx, d->tree);
 }
 
+// (re)allocate the control block for the current number of blocks; the global summary and theta survive
+static int alloc_control(dbl_ctx *ctx) {
+  const int A = ctx->A, F = ctx->F;
+  const int nw = ctx->n_counts() + 2 * ctx->P;
+  const size_t words = CTL_WORDS + 2 * (size_t)nw + 2 * (size_t)A * F + 2;
+  if (ctx->cb.p && ctx->nw == nw) return DBL_OK;
+  std::vector<long long> keep_ctl(CTL_WORDS, 0), keep_glob(ctx->n_counts(), 0);
+  std::vector<double> keep_theta(2 * (size_t)A * F, 0.0);
+  const bool had = ctx->cb.p != nullptr;
+  if (had) {
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaMemcpy(keep_ctl.data(), ctx->ctl(), sizeof(long long) * CTL_WORDS, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(keep_glob.data(), ctx->glob(), sizeof(long long) * ctx->n_counts(), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(keep_theta.data(), ctx->theta(), sizeof(double) * 2 * A * F, cudaMemcpyDeviceToHost));
+  }
+  CUDA_TRY(ctx->cb.alloc(words));
+  ctx->cb_words = words;
+  ctx->nw = nw;
+  if (ctx->h_cb) cudaFreeHost(ctx->h_cb);
+  CUDA_TRY(cudaMallocHost((void **)&ctx->h_cb, words * sizeof(long long)));
+  memset(ctx->h_cb, 0, words * sizeof(long long));
+  CUDA_TRY(cudaMemset(ctx->cb.p, 0, words * sizeof(long long)));
+  if (had) {
+    CUDA_TRY(cudaMemcpy(ctx->ctl(), keep_ctl.data(), sizeof(long long) * CTL_WORDS, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(ctx->glob(), keep_glob.data(), sizeof(long long) * ctx->n_counts(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(ctx->theta(), keep_theta.data(), sizeof(double) * 2 * A * F, cudaMemcpyHostToDevice));
+  }
+  return DBL_OK;
+}
+
 extern "C" int dbl_ctx_create(dbl_ctx **out, const dbl_model_desc *d) {
   if (!out || !d || d->num_attrs <= 0 || d->num_attrs > DBL_MAX_ATTRS || d->num_files <= 0 || !d->indexes ||
       !d->alpha || !d->beta)
     return DBL_ERR_INVALID;
   for (int a = 0; a < d->num_attrs; ++a)
     if (!d->indexes[a] || !(d->alpha[a] > 0.0) || !(d->beta[a] > 0.0)) return DBL_ERR_INVALID;  // package.scala:165
+  if (d->world_size > MAX_WORLD || d->rank < 0 || (d->world_size > 0 && d->rank >= d->world_size)) return DBL_ERR_INVALID;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return DBL_ERR_CUDA;  // no CPU fallback
   auto *ctx = new dbl_ctx();
@@ -924,26 +1431,36 @@ extern "C" int dbl_ctx_create(dbl_ctx **out, const dbl_model_desc *d) {
   CUDA_TRY(cudaEventCreate(&ctx->ev1));
   int rc = upload_model(ctx, d);
   if (rc != DBL_OK) return rc;
-  CUDA_TRY(ctx->counts.alloc(ctx->n_counts()));
-  CUDA_TRY(ctx->loglik.alloc(1));
-  CUDA_TRY(ctx->status.alloc(1));
-  CUDA_TRY(ctx->pairs.alloc(1));
-  CUDA_TRY(cudaMemset(ctx->status.p, 0, sizeof(int)));
-  CUDA_TRY(cudaMemset(ctx->pairs.p, 0, sizeof(unsigned long long)));
-  CUDA_TRY(ctx->theta.alloc((size_t)ctx->A * ctx->F));
+  rc = alloc_control(ctx);
+  if (rc != DBL_OK) return rc;
+  CUDA_TRY(ctx->prior.alloc(2 * (size_t)ctx->A + ctx->F));
+  {
+    std::vector<double> pr(2 * (size_t)ctx->A + ctx->F, 0.0);
+    std::copy(ctx->alpha.begin(), ctx->alpha.end(), pr.begin());
+    std::copy(ctx->beta.begin(), ctx->beta.end(), pr.begin() + ctx->A);
+    CUDA_TRY(cudaMemcpy(ctx->prior.p, pr.data(), pr.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
   ctx->h_theta.assign((size_t)ctx->A * ctx->F, 0.0);
-  ctx->h_counts.assign(ctx->n_counts(), 0);
   return DBL_OK;
+}
+
+static void comm_close(dbl_ctx *ctx) {
+  for (void *p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);
+  ctx->ipc_opened.clear();
+  ctx->comm_ready = false;
 }
 
 extern "C" void dbl_ctx_destroy(dbl_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  comm_close(ctx);
   for (auto &pe : ctx->pending_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
+  for (auto &pe : ctx->event_pool) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->h_cb) cudaFreeHost(ctx->h_cb);
   delete ctx;
 }
 extern "C" const char *dbl_last_error(const dbl_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -951,33 +1468,38 @@ extern "C" int64_t dbl_num_records(const dbl_ctx *ctx) { return ctx ? ctx->R : 0
 extern "C" int64_t dbl_num_entities(const dbl_ctx *ctx) { return ctx ? ctx->E : 0; }
 extern "C" int64_t dbl_iteration(const dbl_ctx *ctx) { return ctx ? ctx->iteration : 0; }
 extern "C" int64_t dbl_kernel_launches(const dbl_ctx *ctx) { return ctx ? ctx->launches : 0; }
-extern "C" const char *dbl_version(void) { return "dblink_b200 0.1 (sm_100a)"; }
+extern "C" const char *dbl_version(void) { return "dblink_b200 0.2 (sm_100a)"; }
 
 static int alloc_blocks(dbl_ctx *ctx) {
   const int P = ctx->P;
   if ((int)ctx->owner_h.size() != P) ctx->owner_h.assign(P, ctx->rank);
   CUDA_TRY(ctx->owner.alloc(P));
   CUDA_TRY(cudaMemcpy(ctx->owner.p, ctx->owner_h.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
-  CUDA_TRY(ctx->ent_cnt.alloc(P + 1));
-  CUDA_TRY(ctx->rec_cnt.alloc(P + 1));
   CUDA_TRY(ctx->ent_ptr.alloc(P + 1));
   CUDA_TRY(ctx->tile_ptr.alloc(P + 1));
   CUDA_TRY(ctx->rec_ptr.alloc(P + 1));
   CUDA_TRY(ctx->cta_ptr.alloc(P + 1));
   CUDA_TRY(ctx->cta_ptr2.alloc(P + 1));
+  CUDA_TRY(ctx->lpt_scratch.alloc(2 * (size_t)P));
+  CUDA_TRY(ctx->lpt_dscratch.alloc((size_t)P + MAX_WORLD));
   const size_t max_tiles = (size_t)(ctx->E / TE) + (size_t)P + 1;
   CUDA_TRY(ctx->tiles.alloc(max_tiles * tile_words(ctx->A)));
   ctx->max_ctas = (int)((ctx->R + LINK_WARPS - 1) / LINK_WARPS) + P;
-  return DBL_OK;
+  return alloc_control(ctx);
 }
 
 static int alloc_state(dbl_ctx *ctx, int64_t R, int64_t E) {
   const int A = ctx->A;
   if (R <= 0 || E <= 0 || R > 0x7fffffff || E > 0x7fffffff) { ctx->set_error("bad R/E"); return DBL_ERR_INVALID; }
+  ctx->all_owned = true;
   if (ctx->R == R && ctx->E == E && ctx->x.p && ctx->tiles.p) {  // same shape as the previous state: reuse buffers
     CUDA_TRY(cudaMemsetAsync(ctx->ent_owned.p, 1, E, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(ctx->rec_owned.p, 1, R, ctx->stream));
     return DBL_OK;
+  }
+  if (ctx->comm_ready || ctx->comm_buf.p) {  // the communication buffers were sized for the old state
+    comm_close(ctx);
+    ctx->comm_buf.release();
   }
   ctx->R = R; ctx->E = E;
   CUDA_TRY(ctx->zbytes.alloc((size_t)R * A));
@@ -1011,7 +1533,6 @@ static int alloc_state(dbl_ctx *ctx, int64_t R, int64_t E) {
   { int rc = alloc_blocks(ctx); if (rc) return rc; }
   CUDA_TRY(ctx->link_sorted.alloc(R));
   CUDA_TRY(ctx->rec_by_ent.alloc(R));
-  CUDA_TRY(ctx->ent_rec_cnt.alloc(E + 1));
   CUDA_TRY(ctx->ent_rec_ptr.alloc(E + 1));
   size_t b1 = 0, b2 = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, b1, (const int *)nullptr, (int *)nullptr, (const int *)nullptr,
@@ -1060,57 +1581,91 @@ static int relayout(dbl_ctx *ctx) {
   k_segment_ptr<<<grid_for(R + 1, 256), 256, 0, ctx->stream>>>(R, P, ctx->rec_key_sorted.p, ctx->rec_ptr.p,
                                                                 REC_CLASS_BITS);
   k_block_scan<<<1, 32, 0, ctx->stream>>>(P, ctx->ent_ptr.p, ctx->rec_ptr.p, ctx->tile_ptr.p, ctx->cta_ptr.p,
-                                          LINK_WARPS, ctx->cta_ptr2.p, MATCH_WARPS);
+                                          LINK_WARPS, ctx->cta_ptr2.p, MATCH_WARPS, ctx->ctl());
   CUDA_TRY(cudaMemsetAsync(ctx->tiles.p, 0, ctx->tiles.n * sizeof(int), ctx->stream));
   k_build_tiles<<<grid_for(E, 256), 256, 0, ctx->stream>>>(E, A, ctx->y.p, ctx->entN.p, ctx->blk_sorted.p,
                                                            ctx->ent_sorted.p, ctx->ent_ptr.p, ctx->tile_ptr.p,
                                                            ctx->tiles.p, ctx->perm_dev.p, P, ctx->pack_consts);
   ctx->launches += 11;
   ctx->inv_valid = false;
-  ctx->h_owned_ent = -1;  // ent_ptr[P] changed; fetch_summary (or the index build) reads it back
+  ctx->h_owned_ent = ctx->h_owned_rec = -1;  // changed on the device; snapshot() brings them back
   CUDA_TRY(cudaGetLastError());
   return DBL_OK;
 }
 
-// entity N / block ids / entity+record summary of the current state
-static int refresh_summary(dbl_ctx *ctx, bool draw_z, int sampler) {
+// entity N / block ids / partial summary of the owned rows; in_sweep: prefix mode + distortion draws (GU:324-359)
+static int refresh_summary(dbl_ctx *ctx, bool in_sweep) {
   const int A = ctx->A, F = ctx->F;
-  (void)sampler;
-  CUDA_TRY(cudaMemsetAsync(ctx->counts.p, 0, sizeof(long long) * ctx->n_counts(), ctx->stream));
-  CUDA_TRY(cudaMemsetAsync(ctx->loglik.p, 0, sizeof(double), ctx->stream));
-  k_entity_post<<<grid_for(ctx->E, 256), 256, 0, ctx->stream>>>(ctx->E, A, ctx->y.p, ctx->attrs.p, ctx->tree,
-                                                               ctx->entN.p, ctx->blk.p, ctx->ent_rec_ptr.p,
-                                                               ctx->counts.p, ctx->iso_slot(), ctx->loglik.p, ctx->ent_owned.p);
+  CUDA_TRY(cudaMemsetAsync(ctx->part(), 0, sizeof(long long) * ctx->nw, ctx->stream));
+  EntPostParams ep;
+  ep.rows = in_sweep ? rows_prefix(ctx, true) : rows_masked(ctx, true);
+  ep.A = A; ep.y = ctx->y.p; ep.attrs = ctx->attrs.p; ep.tree = ctx->tree; ep.entN = ctx->entN.p; ep.blk = ctx->blk.p;
+  ep.ent_rec_ptr = ctx->ent_rec_ptr.p; ep.part = ctx->part(); ep.iso_slot = ctx->iso_slot(); ep.ll_slot = ctx->ll_slot();
+  ep.blk_slot = ctx->world > 1 ? ctx->blk_ent_slot() : -1;
+  k_entity_post<<<grid_rows(ctx->E, 256), 256, 0, ctx->stream>>>(ep);
   DistParams dp;
-  dp.A = A; dp.F = F; dp.draw = draw_z ? 1 : 0; dp.seed = ctx->seed; dp.iter = (uint32_t)(ctx->iteration + 1);
-  dp.R = ctx->R; dp.attrs = ctx->attrs.p; dp.x = ctx->x.p; dp.file = ctx->file.p; dp.link = ctx->link.p;
-  dp.y = ctx->y.p; dp.zmask = ctx->zmask.p; dp.theta = ctx->theta.p; dp.counts = ctx->counts.p;
-  dp.loglik = ctx->loglik.p;
-  dp.rec_owned = ctx->rec_owned.p;
-  k_dist<<<grid_for(ctx->R, 256), 256, 0, ctx->stream>>>(dp);
-  ctx->launches += 4;
+  dp.A = A; dp.F = F; dp.draw = in_sweep ? 1 : 0; dp.seed = ctx->seed;
+  dp.rows = in_sweep ? rows_prefix(ctx, false) : rows_masked(ctx, false);
+  dp.attrs = ctx->attrs.p; dp.x = ctx->x.p; dp.file = ctx->file.p; dp.link = ctx->link.p;
+  dp.y = ctx->y.p; dp.blk = ctx->blk.p; dp.zmask = ctx->zmask.p; dp.theta = ctx->theta(); dp.part = ctx->part();
+  dp.ll_slot = ctx->ll_slot();
+  dp.blk_slot = ctx->world > 1 ? ctx->blk_rec_slot() : -1;
+  k_dist<<<grid_rows(ctx->R, 256), 256, 0, ctx->stream>>>(dp);
+  ctx->launches += 3;
   CUDA_TRY(cudaGetLastError());
   return DBL_OK;
 }
 
-static int fetch_summary(dbl_ctx *ctx) {
-  CUDA_TRY(cudaMemcpyAsync(ctx->h_counts.data(), ctx->counts.p, sizeof(long long) * ctx->n_counts(),
-                           cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaMemcpyAsync(&ctx->h_loglik_part, ctx->loglik.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  int st = 0;
-  CUDA_TRY(cudaMemcpyAsync(&st, ctx->status.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  unsigned long long pr = 0;
-  CUDA_TRY(cudaMemcpyAsync(&pr, ctx->pairs.p, sizeof(pr), cudaMemcpyDeviceToHost, ctx->stream));
-  int owned = -1;
-  if (ctx->ent_ptr.p) CUDA_TRY(cudaMemcpyAsync(&owned, ctx->ent_ptr.p + ctx->P, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  ctx->h_pairs = (int64_t)pr;
-  ctx->h_owned_ent = owned;
-  if (st) {
-    ctx->set_error("zero probability mass in a link draw");
-    cudaMemsetAsync(ctx->status.p, 0, sizeof(int), ctx->stream);
-    return DBL_ERR_ZERO_MASS;
+// the partial summary of a context that owns everything IS the global one
+static int adopt_local_summary(dbl_ctx *ctx) {
+  k_reduce_local<<<1, 256, 0, ctx->stream>>>(ctx->nw, ctx->ctl(), ctx->part(), ctx->glob());
+  ctx->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return DBL_OK;
+}
+
+static void recycle_events(dbl_ctx *ctx) {
+  for (auto &pe : ctx->pending_events) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, pe.first, pe.second) == cudaSuccess) {
+      ctx->link_ms += ms;
+      ctx->link_launches += 1;
+    }
+    ctx->event_pool.push_back(pe);
   }
+  ctx->pending_events.clear();
+}
+
+// One device -> host copy of the control block, one synchronisation: iteration, status, owned counts, global
+// summary, theta.  This is the only point where the host waits for the device.
+static int snapshot(dbl_ctx *ctx) {
+  CUDA_TRY(cudaMemcpyAsync(ctx->h_cb, ctx->cb.p, ctx->cb_words * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  recycle_events(ctx);
+  const long long *c = ctx->h_ctl();
+  ctx->iteration = c[CTL_ITER];
+  ctx->h_pairs = c[CTL_PAIRS];
+  ctx->h_owned_ent = c[CTL_OWNED_ENT];
+  ctx->h_owned_rec = c[CTL_OWNED_REC];
+  const long long st = c[CTL_STATUS];
+  if (st) {
+    const bool sharded = !ctx->all_owned;
+    if (!sharded && st == ST_ZERO_MASS) {
+      // the abandoned sweep changed nothing but theta: put the previous values back, the state is the one before it
+      std::copy(ctx->h_theta_dev() + (size_t)ctx->A * ctx->F, ctx->h_theta_dev() + 2 * (size_t)ctx->A * ctx->F, ctx->h_theta.begin());
+      CUDA_TRY(cudaMemcpyAsync(ctx->theta(), ctx->theta_prev(), sizeof(double) * ctx->A * ctx->F, cudaMemcpyDeviceToDevice,
+                               ctx->stream));
+    } else {
+      ctx->has_state = false;  // shards are no longer at the same iteration: the caller has to upload a state again
+    }
+    CUDA_TRY(cudaMemsetAsync(ctx->ctl() + CTL_STATUS, 0, sizeof(long long), ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (st & ST_PEER_TIMEOUT) { ctx->set_error("a peer rank did not reach the exchange barrier (time-out)"); return DBL_ERR_CUDA; }
+    ctx->set_error((st & ST_PEER_ERROR) && !(st & ST_ZERO_MASS) ? "the sweep failed on a peer rank"
+                                                                : "zero probability mass in a link draw");
+    return (st & ST_ZERO_MASS) ? DBL_ERR_ZERO_MASS : DBL_ERR_CUDA;
+  }
+  std::copy(ctx->h_theta_dev(), ctx->h_theta_dev() + (size_t)ctx->A * ctx->F, ctx->h_theta.begin());
   return DBL_OK;
 }
 
@@ -1135,14 +1690,27 @@ static int finish_new_state(dbl_ctx *ctx, bool check_state) {
   CUDA_TRY(cudaMemcpyAsync(hc.data(), ctx->file_cnt.p, sizeof(int) * ctx->F, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   ctx->file_sizes.assign(hc.begin(), hc.end());
+  {
+    std::vector<double> fs(hc.begin(), hc.end());
+    CUDA_TRY(cudaMemcpyAsync(ctx->prior.p + 2 * ctx->A, fs.data(), sizeof(double) * ctx->F, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
   ctx->launches += 2;
+  // iteration / status of the new state
+  {
+    long long head[2] = {ctx->iteration, 0};
+    CUDA_TRY(cudaMemcpyAsync(ctx->ctl(), head, sizeof(head), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
   int rc = build_links_csr(ctx);
   if (rc) return rc;
-  rc = refresh_summary(ctx, false, 0);
+  rc = refresh_summary(ctx, false);
+  if (rc) return rc;
+  rc = adopt_local_summary(ctx);
   if (rc) return rc;
   rc = relayout(ctx);
   if (rc) return rc;
-  rc = fetch_summary(ctx);
+  rc = snapshot(ctx);
   if (rc) return rc;
   ctx->has_state = true;
   return DBL_OK;
@@ -1152,18 +1720,29 @@ extern "C" int dbl_set_partitioner(dbl_ctx *ctx, const dbl_kdtree *tree) {
   if (!ctx) return DBL_ERR_INVALID;
   CUDA_TRY(cudaSetDevice(ctx->device));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (ctx->has_state && !ctx->all_owned) { ctx->set_error("dbl_set_partitioner after dbl_set_block_owners"); return DBL_ERR_STATE; }
   int rc = upload_tree(ctx, tree);
   if (rc) return rc;
-  if (!ctx->has_state) return DBL_OK;
+  if (!ctx->has_state) return alloc_control(ctx);
   rc = alloc_blocks(ctx);
   if (rc) return rc;
-  rc = refresh_summary(ctx, false, 0);  // recomputes block ids (and the unchanged summary)
+  rc = refresh_summary(ctx, false);  // recomputes block ids (and the unchanged summary)
+  if (rc) return rc;
+  rc = adopt_local_summary(ctx);
   if (rc) return rc;
   rc = relayout(ctx);
   if (rc) return rc;
-  return fetch_summary(ctx);
+  return snapshot(ctx);
 }
 extern "C" int32_t dbl_num_partitions(const dbl_ctx *ctx) { return ctx ? ctx->P : 0; }
+
+static int upload_theta(dbl_ctx *ctx) {
+  const size_t n = (size_t)ctx->A * ctx->F;
+  CUDA_TRY(cudaMemcpyAsync(ctx->theta(), ctx->h_theta.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(ctx->theta_prev(), ctx->h_theta.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // h_theta may change before an asynchronous copy has run
+  return DBL_OK;
+}
 
 extern "C" int dbl_state_init(dbl_ctx *ctx, int64_t R, const int32_t *x, const int32_t *file, int64_t pop) {
   if (!ctx || !x || !file) return DBL_ERR_INVALID;
@@ -1181,8 +1760,8 @@ extern "C" int dbl_state_init(dbl_ctx *ctx, int64_t R, const int32_t *x, const i
   for (int a = 0; a < A; ++a)
     for (int f = 0; f < ctx->F; ++f)
       ctx->h_theta[a * ctx->F + f] = ctx->alpha[a] / (ctx->alpha[a] + ctx->beta[a]);  // DistortionProbs.scala:38-40
-  CUDA_TRY(cudaMemcpyAsync(ctx->theta.p, ctx->h_theta.data(), sizeof(double) * A * ctx->F, cudaMemcpyHostToDevice,
-                           ctx->stream));
+  rc = upload_theta(ctx);
+  if (rc) return rc;
   ctx->iteration = 0;
   return finish_new_state(ctx, false);
 }
@@ -1205,11 +1784,10 @@ extern "C" int dbl_state_upload(dbl_ctx *ctx, int64_t R, int64_t E, const int32_
   k_pack_z<<<grid_for(R, 256), 256, 0, ctx->stream>>>(R, A, zb.p, ctx->zmask.p);
   ctx->launches += 2;
   std::copy(theta, theta + (size_t)A * ctx->F, ctx->h_theta.begin());
-  CUDA_TRY(cudaMemcpyAsync(ctx->theta.p, ctx->h_theta.data(), sizeof(double) * A * ctx->F, cudaMemcpyHostToDevice,
-                           ctx->stream));
+  rc = upload_theta(ctx);
+  if (rc) return rc;
   ctx->iteration = iteration;
-  rc = finish_new_state(ctx, true);
-  return rc;
+  return finish_new_state(ctx, true);
 }
 
 extern "C" int dbl_state_download(dbl_ctx *ctx, uint8_t *z, int32_t *link, int32_t *y, double *theta,
@@ -1237,38 +1815,37 @@ extern "C" int dbl_links_download(dbl_ctx *ctx, int32_t *link_out, int32_t *bloc
   return dbl_state_download(ctx, nullptr, link_out, nullptr, nullptr, block_out);
 }
 
-static void drain_link_events(dbl_ctx *ctx) {
-  for (auto &pe : ctx->pending_events) {
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, pe.first, pe.second) == cudaSuccess) {
-      ctx->link_ms += ms;
-      ctx->link_launches += 1;
-    }
-    cudaEventDestroy(pe.first);
-    cudaEventDestroy(pe.second);
-  }
-  ctx->pending_events.clear();
-}
-
 // ---------------------------------------------------------------------------------------------------
 // link kernel dispatch
 // ---------------------------------------------------------------------------------------------------
-#define DBL_DECL(N) int dbl_launch_pcg2_a##N(int ns, int grid, cudaStream_t stream, const LinkParams &lp);
+#define DBL_DECL(N) int dbl_launch_pcg2_a##N(int ns, int grid, cudaStream_t stream, const LinkParams &lp, size_t *cfg);
 DBL_DECL(1) DBL_DECL(2) DBL_DECL(3) DBL_DECL(4) DBL_DECL(5) DBL_DECL(6) DBL_DECL(7) DBL_DECL(8)
 DBL_DECL(9) DBL_DECL(10) DBL_DECL(11) DBL_DECL(12) DBL_DECL(13) DBL_DECL(14) DBL_DECL(15) DBL_DECL(16)
 #undef DBL_DECL
+
+// number of entities in owned blocks, on the host.  Unsharded contexts own everything; otherwise the count lives on
+// the device (the exchange changes it every sweep) and costs one small read-back.
+static int owned_entities_on_host(dbl_ctx *ctx, int64_t *out) {
+  if (ctx->all_owned && !ctx->in_block_sweep) { *out = ctx->E; return DBL_OK; }
+  if (ctx->h_owned_ent < 0) {
+    long long v = 0;
+    CUDA_TRY(cudaMemcpyAsync(&v, ctx->ctl() + CTL_OWNED_ENT, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->h_owned_ent = v;
+  }
+  *out = ctx->h_owned_ent;
+  return DBL_OK;
+}
 
 // (block, attribute, value) -> candidate positions, for k_link_pruned
 static int ensure_inverted_index(dbl_ctx *ctx) {
   if (ctx->inv_valid) return DBL_OK;
   const int64_t cap = ctx->E * ctx->A;
   if (cap > 0x7fffffff) { ctx->set_error("inverted index too large"); return DBL_ERR_INVALID; }
-  if (ctx->h_owned_ent < 0) {  // relayout without a summary fetch since (block-level sweeps)
-    CUDA_TRY(cudaMemcpyAsync(&ctx->h_owned_ent, ctx->ent_ptr.p + ctx->P, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  }
+  int64_t owned = 0;
+  { int rc = owned_entities_on_host(ctx, &owned); if (rc) return rc; }
   // only the entities of owned blocks are indexed: they come first in ent_sorted
-  const int64_t n = (int64_t)ctx->h_owned_ent * ctx->A;
+  const int64_t n = owned * ctx->A;
   if (ctx->inv_key.n != (size_t)cap) {
     CUDA_TRY(ctx->inv_key_in.alloc(cap));
     CUDA_TRY(ctx->inv_key.alloc(cap));
@@ -1285,7 +1862,7 @@ static int ensure_inverted_index(dbl_ctx *ctx) {
   ctx->inv_vbits = bits_for(vmax + 1);
   const int nbits = ctx->inv_vbits + bits_for((int64_t)(ctx->P + 1) * ctx->A);
   if (n > 0) {
-    k_inv_keys<<<grid_for(n, 256), 256, 0, ctx->stream>>>((int64_t)ctx->h_owned_ent, ctx->A, ctx->P, ctx->inv_vbits,
+    k_inv_keys<<<grid_for(n, 256), 256, 0, ctx->stream>>>(owned, ctx->A, ctx->P, ctx->inv_vbits,
                                                           ctx->y.p, ctx->blk_sorted.p, ctx->ent_sorted.p,
                                                           ctx->ent_ptr.p, ctx->perm_dev.p, ctx->inv_key_in.p,
                                                           ctx->inv_pos_in.p);
@@ -1319,15 +1896,17 @@ static int ensure_inverted_index(dbl_ctx *ctx) {
   return DBL_OK;
 }
 
-static int launch_link(dbl_ctx *ctx, int sampler, uint32_t it) {
+static int launch_link(dbl_ctx *ctx, int sampler) {
   const int A = ctx->A;
   LinkParams lp;
   memset(&lp, 0, sizeof(lp));
-  lp.A = A; lp.F = ctx->F; lp.P = ctx->P; lp.sampler = sampler; lp.seed = ctx->seed; lp.iter = it;
+  lp.A = A; lp.F = ctx->F; lp.P = ctx->P; lp.sampler = sampler; lp.seed = ctx->seed; lp.ctl = ctx->ctl();
   lp.attrs = ctx->attrs.p; lp.x = ctx->x.p; lp.file = ctx->file.p; lp.link = ctx->link.p; lp.zmask = ctx->zmask.p;
-  lp.theta = ctx->theta.p; lp.ent_ptr = ctx->ent_ptr.p; lp.tile_ptr = ctx->tile_ptr.p; lp.rec_ptr = ctx->rec_ptr.p;
+  lp.theta = ctx->theta(); lp.ent_ptr = ctx->ent_ptr.p; lp.tile_ptr = ctx->tile_ptr.p; lp.rec_ptr = ctx->rec_ptr.p;
   lp.cta_ptr = ctx->cta_ptr.p; lp.ent_sorted = ctx->ent_sorted.p; lp.rec_sorted = ctx->rec_sorted.p;
-  lp.tiles = ctx->tiles.p; lp.newlink = ctx->newlink.p; lp.status = ctx->status.p; lp.pairs = ctx->pairs.p;
+  lp.tiles = ctx->tiles.p; lp.newlink = ctx->newlink.p;
+  lp.status = reinterpret_cast<unsigned long long *>(ctx->ctl() + CTL_STATUS);
+  lp.pairs = reinterpret_cast<unsigned long long *>(ctx->ctl() + CTL_PAIRS);
   for (int k = 0; k < A; ++k) lp.perm[k] = ctx->perm[k];
   lp.blk_of_link = ctx->blk.p;
   lp.pack_consts = ctx->pack_consts;
@@ -1338,7 +1917,7 @@ static int launch_link(dbl_ctx *ctx, int sampler, uint32_t it) {
       pcg2_smem_bytes(A, ctx->n_str, ctx->hslots) <= 100 * 1024) {
     int rc = -1;
     switch (A) {
-#define DBL_CASE(N) case N: rc = dbl_launch_pcg2_a##N(ctx->n_str, ctx->max_ctas, ctx->stream, lp); break;
+#define DBL_CASE(N) case N: rc = dbl_launch_pcg2_a##N(ctx->n_str, ctx->max_ctas, ctx->stream, lp, &ctx->pcg2_smem_cfg); break;
       DBL_CASE(1) DBL_CASE(2) DBL_CASE(3) DBL_CASE(4) DBL_CASE(5) DBL_CASE(6) DBL_CASE(7) DBL_CASE(8)
       DBL_CASE(9) DBL_CASE(10) DBL_CASE(11) DBL_CASE(12) DBL_CASE(13) DBL_CASE(14) DBL_CASE(15) DBL_CASE(16)
 #undef DBL_CASE
@@ -1349,11 +1928,14 @@ static int launch_link(dbl_ctx *ctx, int sampler, uint32_t it) {
   if (mode == 0 && sampler != DBL_PCG_II) {  // pruned scoring through the inverted index
     int rc = ensure_inverted_index(ctx);
     if (rc) return rc;
+    int64_t owned = 0;
+    rc = owned_entities_on_host(ctx, &owned);
+    if (rc) return rc;
     PrunedParams pp;
     pp.lp = lp;
     pp.inv_key = ctx->inv_key.p;
     pp.inv_pos = ctx->inv_pos.p;
-    pp.inv_n = (long long)ctx->h_owned_ent * ctx->A;
+    pp.inv_n = (long long)owned * ctx->A;
     pp.R = ctx->R;
     pp.vbits = ctx->inv_vbits;
     pp.inv_seg = ctx->inv_seg.p;
@@ -1366,10 +1948,9 @@ static int launch_link(dbl_ctx *ctx, int sampler, uint32_t it) {
     return DBL_OK;
   }
   if (mode != 1 && sampler != DBL_PCG_II && ring <= 160 * 1024) {
-    static size_t configured = 0;
-    if (configured < ring) {
+    if (ctx->match_smem_cfg < ring) {
       CUDA_TRY(cudaFuncSetAttribute(k_link_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring));
-      configured = ring;
+      ctx->match_smem_cfg = ring;
     }
     lp.cta_ptr = ctx->cta_ptr2.p;  // MATCH_WARPS records per CTA
     const int grid = (int)((ctx->R + MATCH_WARPS - 1) / MATCH_WARPS) + ctx->P;
@@ -1380,91 +1961,145 @@ static int launch_link(dbl_ctx *ctx, int sampler, uint32_t it) {
   return DBL_OK;
 }
 
-// theta | summary -> links -> entity values -> N/blocks/distortions/summary of the shard owned by this rank
-// (1) theta | summary of the previous state (State.scala:83, GU:305-320) -- A*F scalars on the host
-static int draw_theta(dbl_ctx *ctx) {
-  const int A = ctx->A, F = ctx->F;
-  const uint32_t it = (uint32_t)(ctx->iteration + 1);
-  std::vector<int64_t> agg((size_t)A * F);
-  for (int i = 0; i < A * F; ++i) agg[i] = ctx->h_counts[i];
-  host_draw_theta(A, F, ctx->alpha.data(), ctx->beta.data(), ctx->seed, agg.data(), ctx->file_sizes.data(), it,
-                  ctx->h_theta.data());
-  CUDA_TRY(cudaMemcpyAsync(ctx->theta.p, ctx->h_theta.data(), sizeof(double) * A * F, cudaMemcpyHostToDevice,
-                           ctx->stream));
+// ---------------------------------------------------------------------------------------------------
+// one application of State.nextState (State.scala:78-99), enqueued on the context's stream without any host
+// synchronisation (PCG-II; the pruned PCG-I kernel of a SHARDED context reads one count back per sweep)
+// ---------------------------------------------------------------------------------------------------
+// (1) theta | summary of the previous state (State.scala:83, GU:305-320)
+static int enqueue_theta(dbl_ctx *ctx) {
+  k_theta<<<1, 128, 0, ctx->stream>>>(ctx->A, ctx->F, ctx->seed, ctx->ctl(), ctx->glob(), ctx->prior.p,
+                                       ctx->prior.p + ctx->A, ctx->prior.p + 2 * ctx->A, ctx->theta(), ctx->theta_prev());
+  ctx->launches += 1;
+  CUDA_TRY(cudaGetLastError());
   return DBL_OK;
 }
 
 // (2)-(4) for the owned entities / records (all of them on an unsharded context): updatePartition, GU:156-211
-static int update_owned(dbl_ctx *ctx, int sampler, bool masked) {
+static int update_owned(dbl_ctx *ctx, int sampler) {
   const int A = ctx->A, F = ctx->F;
-  const uint32_t it = (uint32_t)(ctx->iteration + 1);
   // (2) links
-  cudaEvent_t e0, e1;
-  CUDA_TRY(cudaEventCreate(&e0));
-  CUDA_TRY(cudaEventCreate(&e1));
-  CUDA_TRY(cudaEventRecord(e0, ctx->stream));
-  {
-    int rc = launch_link(ctx, sampler, it);
-    if (rc) return rc;
+  std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+  const bool timed = ctx->pending_events.size() < 256;  // per-launch timing of the first sweeps of a call
+  if (timed) {
+    if (!ctx->event_pool.empty()) { ev = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
+    else { CUDA_TRY(cudaEventCreate(&ev.first)); CUDA_TRY(cudaEventCreate(&ev.second)); }
+    CUDA_TRY(cudaEventRecord(ev.first, ctx->stream));
   }
-  CUDA_TRY(cudaEventRecord(e1, ctx->stream));
-  ctx->pending_events.emplace_back(e0, e1);
+  {
+    int rc = launch_link(ctx, sampler);
+    if (rc) { if (timed) ctx->event_pool.push_back(ev); return rc; }
+  }
+  if (timed) {
+    CUDA_TRY(cudaEventRecord(ev.second, ctx->stream));
+    ctx->pending_events.push_back(ev);
+  }
   ctx->launches += 1;
   CUDA_TRY(cudaGetLastError());
-  if (masked) {  // the link kernel only writes records of owned blocks: keep the others as they were
-    k_merge_links<<<grid_for(ctx->R, 256), 256, 0, ctx->stream>>>(ctx->R, ctx->rec_owned.p, ctx->link.p, ctx->newlink.p);
-    ctx->launches += 1;
-  }
-  std::swap(ctx->link.p, ctx->newlink.p);
+  k_commit_links<<<grid_rows(ctx->R, 256), 256, 0, ctx->stream>>>(rows_prefix(ctx, false), ctx->newlink.p, ctx->link.p);
+  ctx->launches += 1;
   // (3) entity values
   int rc = build_links_csr(ctx);
   if (rc) return rc;
   ValParams vp;
-  vp.A = A; vp.F = F; vp.sampler = sampler; vp.seed = ctx->seed; vp.iter = it; vp.E = ctx->E;
-  vp.attrs = ctx->attrs.p; vp.x = ctx->x.p; vp.file = ctx->file.p; vp.zmask = ctx->zmask.p; vp.theta = ctx->theta.p;
+  vp.A = A; vp.F = F; vp.sampler = sampler; vp.seed = ctx->seed; vp.rows = rows_prefix(ctx, true);
+  vp.attrs = ctx->attrs.p; vp.x = ctx->x.p; vp.file = ctx->file.p; vp.zmask = ctx->zmask.p; vp.theta = ctx->theta();
   vp.ent_rec_ptr = ctx->ent_rec_ptr.p; vp.rec_by_ent = ctx->rec_by_ent.p; vp.y = ctx->y.p;
-  vp.ent_owned = ctx->ent_owned.p;
-  k_values<<<grid_for(ctx->E * A, 128), 128, 0, ctx->stream>>>(vp);
+  k_values<<<grid_rows(ctx->E * A, 128), 128, 0, ctx->stream>>>(vp);
   ctx->launches += 1;
-  // (4) N(e), new block ids, distortions, summary
-  return refresh_summary(ctx, true, sampler);
+  // (4) N(e), new block ids, distortions, partial summary
+  return refresh_summary(ctx, true);
 }
 
-static int sweep_local(dbl_ctx *ctx, int sampler) {
-  int rc = draw_theta(ctx);
-  if (rc) return rc;
-  return update_owned(ctx, sampler, ctx->world > 1);
+// (5) the shuffle (GU:144) + the global summary (SummaryAccumulators.scala:54-63), peer to peer
+static int exchange_p2p(dbl_ctx *ctx) {
+  MoveParams mp;
+  mp.c = ctx->comm; mp.ctl = ctx->ctl(); mp.A = ctx->A; mp.ent_sorted = ctx->ent_sorted.p; mp.rec_sorted = ctx->rec_sorted.p;
+  mp.blk = ctx->blk.p; mp.owner = ctx->owner.p; mp.link = ctx->link.p; mp.y = ctx->y.p; mp.zmask = ctx->zmask.p;
+  mp.ent_dest = ctx->ent_dest.p; mp.ent_owned = ctx->ent_owned.p; mp.rec_owned = ctx->rec_owned.p;
+  k_move_ent<<<grid_rows(ctx->E, 256), 256, 0, ctx->stream>>>(mp);
+  k_move_rec<<<grid_rows(ctx->R, 256), 256, 0, ctx->stream>>>(mp);
+  k_publish_barrier<<<1, 256, 0, ctx->stream>>>(ctx->comm, ctx->ctl(), ctx->part(), ctx->nw, ctx->barrier_timeout_cycles);
+  UnpackParams up;
+  up.c = ctx->comm; up.ctl = ctx->ctl(); up.A = ctx->A; up.attrs = ctx->attrs.p; up.tree = ctx->tree; up.y = ctx->y.p;
+  up.blk = ctx->blk.p; up.link = ctx->link.p; up.entN = ctx->entN.p; up.zmask = ctx->zmask.p;
+  up.ent_owned = ctx->ent_owned.p; up.rec_owned = ctx->rec_owned.p;
+  k_unpack_ent_p2p<<<grid_rows(ctx->E, 256), 256, 0, ctx->stream>>>(up);
+  k_unpack_rec_p2p<<<grid_rows(ctx->R, 256), 256, 0, ctx->stream>>>(up);
+  k_reduce_peers<<<1, 256, 0, ctx->stream>>>(ctx->comm, ctx->ctl(), ctx->nw, ctx->ll_slot(), ctx->glob());
+  ctx->launches += 6;
+  if (ctx->rebalance_period > 0 && ctx->P <= 1024) {
+    k_lpt<<<1, 32, 0, ctx->stream>>>(ctx->P, ctx->world, ctx->blk_ent_slot(), ctx->blk_rec_slot(), ctx->glob(), ctx->ctl(),
+                                     ctx->rebalance_period, ctx->rebalance_threshold, ctx->owner.p, ctx->lpt_scratch.p,
+                                     ctx->lpt_dscratch.p);
+    ctx->launches += 1;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return DBL_OK;
 }
 
-// (5) re-partition + summary fetch (also the sync point that bounds the sweep)
-static int sweep_finish(dbl_ctx *ctx) {
-  int rc = relayout(ctx);
+static int enqueue_sweep(dbl_ctx *ctx, int sampler) {
+  int rc = enqueue_theta(ctx);
   if (rc) return rc;
-  ctx->iteration += 1;
-  return fetch_summary(ctx);
+  rc = update_owned(ctx, sampler);
+  if (rc) return rc;
+  rc = (ctx->world > 1) ? exchange_p2p(ctx) : adopt_local_summary(ctx);
+  if (rc) return rc;
+  rc = relayout(ctx);
+  if (rc) return rc;
+  k_finish<<<1, 32, 0, ctx->stream>>>(ctx->ctl());
+  ctx->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return DBL_OK;
+}
+
+static int check_sweep_args(dbl_ctx *ctx, int sampler, int32_t n_sweeps) {
+  if (sampler < 0 || sampler > 3 || n_sweeps < 0) { ctx->set_error("bad sampler / n_sweeps"); return DBL_ERR_INVALID; }
+  if (!ctx->has_state) { ctx->set_error("dbl_sweep before dbl_state_init/upload"); return DBL_ERR_STATE; }
+  if (ctx->world > 1 && !ctx->comm_ready) {
+    ctx->set_error("dbl_sweep on a sharded context needs dbl_comm_export / dbl_comm_import first "
+                   "(or drive the host-mediated exchange: dbl_sweep_begin / dbl_exchange_* / dbl_sweep_end)");
+    return DBL_ERR_STATE;
+  }
+  if (ctx->world > 1 && ctx->all_owned) { ctx->set_error("dbl_sweep on a sharded context before dbl_set_block_owners"); return DBL_ERR_STATE; }
+  if (ctx->in_sweep) { ctx->set_error("dbl_sweep inside an open sweep"); return DBL_ERR_STATE; }
+  return DBL_OK;
+}
+
+extern "C" int dbl_sweep_async(dbl_ctx *ctx, int sampler, int32_t n_sweeps) {
+  if (!ctx) return DBL_ERR_INVALID;
+  int rc = check_sweep_args(ctx, sampler, n_sweeps);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (!ctx->async_open) CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+  ctx->async_open = true;
+  for (int s = 0; s < n_sweeps; ++s) {
+    rc = enqueue_sweep(ctx, sampler);
+    if (rc) return rc;
+  }
+  return DBL_OK;
+}
+
+extern "C" int dbl_sync(dbl_ctx *ctx) {
+  if (!ctx) return DBL_ERR_INVALID;
+  if (!ctx->has_state) { ctx->set_error("no state"); return DBL_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const bool timed = ctx->async_open;
+  if (timed) CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->async_open = false;
+  int rc = snapshot(ctx);
+  if (timed) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_sweep_ms = ms;
+  }
+  return rc;
 }
 
 extern "C" int dbl_sweep(dbl_ctx *ctx, int sampler, int32_t n_sweeps) {
   if (!ctx) return DBL_ERR_INVALID;
-  if (sampler < 0 || sampler > 3 || n_sweeps < 0) { ctx->set_error("bad sampler / n_sweeps"); return DBL_ERR_INVALID; }
-  if (!ctx->has_state) { ctx->set_error("dbl_sweep before dbl_state_init/upload"); return DBL_ERR_STATE; }
-  if (ctx->world > 1) { ctx->set_error("dbl_sweep on a sharded context: use dbl_sweep_begin/exchange/end"); return DBL_ERR_STATE; }
-  if (ctx->in_sweep) { ctx->set_error("dbl_sweep inside an open sweep"); return DBL_ERR_STATE; }
-  CUDA_TRY(cudaSetDevice(ctx->device));
-  CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-  for (int s = 0; s < n_sweeps; ++s) {
-    int rc = sweep_local(ctx, sampler);
-    if (rc) return rc;
-    rc = sweep_finish(ctx);
-    if (rc) return rc;
-  }
-  CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
-  CUDA_TRY(cudaEventSynchronize(ctx->ev1));
-  float ms = 0.f;
-  CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-  ctx->last_sweep_ms = ms;
-  drain_link_events(ctx);
-  return DBL_OK;
+  if (ctx->async_open) { ctx->set_error("dbl_sweep with asynchronous sweeps pending: call dbl_sync first"); return DBL_ERR_STATE; }
+  int rc = dbl_sweep_async(ctx, sampler, n_sweeps);
+  if (rc) { ctx->async_open = false; return rc; }
+  return dbl_sync(ctx);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1475,10 +2110,10 @@ extern "C" int dbl_block_sweep_begin(dbl_ctx *ctx, int sampler) {
   if (sampler < 0 || sampler > 3) { ctx->set_error("bad sampler"); return DBL_ERR_INVALID; }
   if (!ctx->has_state) { ctx->set_error("no state"); return DBL_ERR_STATE; }
   if (ctx->world > 1) { ctx->set_error("block-level sweeps need an unsharded context"); return DBL_ERR_STATE; }
-  if (ctx->in_sweep) { ctx->set_error("a sweep is already open"); return DBL_ERR_STATE; }
+  if (ctx->in_sweep || ctx->async_open) { ctx->set_error("a sweep is already open"); return DBL_ERR_STATE; }
   CUDA_TRY(cudaSetDevice(ctx->device));
   CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-  int rc = draw_theta(ctx);
+  int rc = enqueue_theta(ctx);
   if (rc) return rc;
   // block membership is fixed for the whole sweep (the shuffle happens after every partition was updated, GU:144)
   CUDA_TRY(ctx->blk_frozen.alloc(ctx->E));
@@ -1502,7 +2137,7 @@ extern "C" int dbl_update_block(dbl_ctx *ctx, int32_t block_id) {
   ctx->launches += 2;
   int rc = relayout(ctx);  // tiles of this block only (everything else sorts into the dummy block)
   if (rc) return rc;
-  rc = update_owned(ctx, ctx->block_sampler, true);
+  rc = update_owned(ctx, ctx->block_sampler);
   if (rc) return rc;
   ctx->block_done[block_id] = 1;
   return DBL_OK;
@@ -1519,17 +2154,19 @@ extern "C" int dbl_block_sweep_end(dbl_ctx *ctx) {
   CUDA_TRY(cudaMemsetAsync(ctx->rec_owned.p, 1, ctx->R, ctx->stream));
   int rc = build_links_csr(ctx);
   if (rc) return rc;
-  rc = refresh_summary(ctx, false, 0);  // summary of the whole state (updateSummaryVariables, GU:219-301)
+  rc = refresh_summary(ctx, false);  // summary of the whole state (updateSummaryVariables, GU:219-301)
   if (rc) return rc;
-  rc = sweep_finish(ctx);               // the shuffle: regroup by the new block ids
+  rc = adopt_local_summary(ctx);
   if (rc) return rc;
+  rc = relayout(ctx);  // the shuffle: regroup by the new block ids
+  if (rc) return rc;
+  k_finish<<<1, 32, 0, ctx->stream>>>(ctx->ctl());
+  ctx->launches += 1;
   CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
-  CUDA_TRY(cudaEventSynchronize(ctx->ev1));
+  rc = snapshot(ctx);
   float ms = 0.f;
-  CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-  ctx->last_sweep_ms = ms;
-  drain_link_events(ctx);
-  return DBL_OK;
+  if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_sweep_ms = ms;
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1548,30 +2185,140 @@ static int apply_ownership(dbl_ctx *ctx) {
 extern "C" int dbl_set_block_owners(dbl_ctx *ctx, const int32_t *owner_of_block) {
   if (!ctx || !owner_of_block) return DBL_ERR_INVALID;
   if (!ctx->has_state) { ctx->set_error("set_block_owners needs a (replicated) state"); return DBL_ERR_STATE; }
+  if (!ctx->all_owned) { ctx->set_error("set_block_owners needs the replicated state: upload / init it again first"); return DBL_ERR_STATE; }
   CUDA_TRY(cudaSetDevice(ctx->device));
   for (int b = 0; b < ctx->P; ++b)
     if (owner_of_block[b] < 0 || owner_of_block[b] >= ctx->world) { ctx->set_error("owner out of range"); return DBL_ERR_INVALID; }
   ctx->owner_h.assign(owner_of_block, owner_of_block + ctx->P);
   CUDA_TRY(cudaMemcpyAsync(ctx->owner.p, ctx->owner_h.data(), sizeof(int) * ctx->P, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   int rc = apply_ownership(ctx);
   if (rc) return rc;
+  ctx->all_owned = (ctx->world <= 1);
   rc = build_links_csr(ctx);
   if (rc) return rc;
-  rc = refresh_summary(ctx, false, 0);
+  rc = refresh_summary(ctx, false);  // partial summary of the shard; the global one (replicated state) stays
   if (rc) return rc;
   rc = relayout(ctx);
   if (rc) return rc;
-  return fetch_summary(ctx);
+  return snapshot(ctx);
 }
 
+extern "C" int dbl_block_owners(dbl_ctx *ctx, int32_t *owner_out) {
+  if (!ctx || !owner_out) return DBL_ERR_INVALID;
+  if (!ctx->owner.p) { ctx->set_error("no state"); return DBL_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  CUDA_TRY(cudaMemcpyAsync(owner_out, ctx->owner.p, sizeof(int) * ctx->P, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return DBL_OK;
+}
+
+extern "C" int dbl_set_rebalance(dbl_ctx *ctx, int32_t period, double threshold) {
+  if (!ctx || period < 0 || !(threshold >= 1.0)) return DBL_ERR_INVALID;
+  ctx->rebalance_period = period;
+  ctx->rebalance_threshold = threshold;
+  return DBL_OK;
+}
+
+// ---- peer-to-peer communicator ------------------------------------------------------------------------------
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" int dbl_comm_export(dbl_ctx *ctx, void *blob_out) {
+  if (!ctx || !blob_out) return DBL_ERR_INVALID;
+  if (!ctx->has_state) { ctx->set_error("dbl_comm_export needs a state (the buffers are sized by it)"); return DBL_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  comm_close(ctx);
+  CommDev &c = ctx->comm;
+  memset(&c, 0, sizeof(c));
+  c.rank = ctx->rank; c.world = ctx->world; c.A = ctx->A; c.nws = ctx->nw + 1;
+  c.cap_e = ctx->E; c.cap_r = ctx->R;
+  c.off_cursor = 256;
+  c.off_slots = 512;
+  c.off_ent = align_up(c.off_slots + 2 * (size_t)c.world * c.nws * 8, 256);
+  c.off_rec = align_up(c.off_ent + 2 * (size_t)c.cap_e * (c.A + 1) * 4, 256);
+  const size_t bytes = align_up(c.off_rec + 2 * (size_t)c.cap_r * 3 * 4, 256);
+  if (ctx->comm_bytes != bytes || !ctx->comm_buf.p) {
+    CUDA_TRY(ctx->comm_buf.alloc(bytes));
+    ctx->comm_bytes = bytes;
+  }
+  CUDA_TRY(cudaMemset(ctx->comm_buf.p, 0, 512 + 2 * (size_t)c.world * c.nws * 8));
+  long long zero = 0;  // barrier epochs restart with the buffers
+  CUDA_TRY(cudaMemcpy(ctx->ctl() + CTL_EPOCH, &zero, sizeof(zero), cudaMemcpyHostToDevice));
+  CommBlob b;
+  memset(&b, 0, sizeof(b));
+  b.magic = COMM_MAGIC; b.rank = ctx->rank; b.world = ctx->world; b.device = ctx->device;
+  b.pid = (int64_t)getpid();
+  b.ptr = (uint64_t)(uintptr_t)ctx->comm_buf.p;
+  b.bytes = bytes; b.E = ctx->E; b.R = ctx->R; b.A = ctx->A; b.nws = c.nws;
+  if (ctx->world > 1 && cudaIpcGetMemHandle(&b.handle, ctx->comm_buf.p) != cudaSuccess) {
+    // no IPC on this system: ranks living in this process still reach the buffer through b.ptr; a rank in another
+    // process will fail in dbl_comm_import and the host layer falls back to the host-mediated exchange
+    cudaGetLastError();
+    memset(&b.handle, 0, sizeof(b.handle));
+  }
+  memcpy(blob_out, &b, sizeof(b));
+  return DBL_OK;
+}
+
+extern "C" int dbl_comm_import(dbl_ctx *ctx, const void *blobs, int32_t world) {
+  if (!ctx || !blobs) return DBL_ERR_INVALID;
+  if (world != ctx->world) { ctx->set_error("dbl_comm_import: world size differs from the context's"); return DBL_ERR_INVALID; }
+  if (!ctx->comm_buf.p) { ctx->set_error("dbl_comm_import before dbl_comm_export"); return DBL_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const CommBlob *bl = static_cast<const CommBlob *>(blobs);
+  for (int r = 0; r < world; ++r) {
+    CommBlob b;
+    memcpy(&b, &bl[r], sizeof(b));
+    if (b.magic != COMM_MAGIC || b.rank != r || b.world != world || b.E != ctx->E || b.R != ctx->R || b.A != ctx->A ||
+        b.nws != ctx->comm.nws || b.bytes != ctx->comm_bytes) {
+      ctx->set_error("dbl_comm_import: blob " + std::to_string(r) + " does not describe a matching rank");
+      return DBL_ERR_INVALID;
+    }
+    if (r == ctx->rank) {
+      ctx->comm.base[r] = ctx->comm_buf.p;
+    } else if (b.pid == (int64_t)getpid()) {  // several ranks in one process (tests): plain pointers
+      if (b.device != ctx->device) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ctx->set_error("no peer access between the devices"); return DBL_ERR_CUDA; }
+        cudaGetLastError();
+      }
+      ctx->comm.base[r] = reinterpret_cast<unsigned char *>((uintptr_t)b.ptr);
+    } else {
+      void *p = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&p, b.handle, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        ctx->set_error(std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(r) + "): " + cudaGetErrorString(e));
+        comm_close(ctx);
+        return DBL_ERR_CUDA;
+      }
+      ctx->ipc_opened.push_back(p);
+      ctx->comm.base[r] = static_cast<unsigned char *>(p);
+    }
+  }
+  ctx->comm_ready = true;
+  return DBL_OK;
+}
+
+extern "C" int dbl_last_exchange(dbl_ctx *ctx, int64_t *ent_msgs, int64_t *rec_msgs, int64_t *replacements) {
+  if (!ctx || !ctx->h_cb) return DBL_ERR_INVALID;
+  if (ent_msgs) *ent_msgs = ctx->h_ctl()[CTL_MOVED_ENT];
+  if (rec_msgs) *rec_msgs = ctx->h_ctl()[CTL_MOVED_REC];
+  if (replacements) *replacements = ctx->h_ctl()[CTL_REPLACED];
+  return DBL_OK;
+}
+
+// ---- host-mediated exchange ---------------------------------------------------------------------------------
 extern "C" int dbl_sweep_begin(dbl_ctx *ctx, int sampler, int64_t *ent_counts, int64_t *rec_counts) {
   if (!ctx || !ent_counts || !rec_counts) return DBL_ERR_INVALID;
   if (sampler < 0 || sampler > 3) { ctx->set_error("bad sampler"); return DBL_ERR_INVALID; }
   if (!ctx->has_state) { ctx->set_error("no state"); return DBL_ERR_STATE; }
-  if (ctx->in_sweep) { ctx->set_error("dbl_sweep_begin twice"); return DBL_ERR_STATE; }
+  if (ctx->in_sweep || ctx->async_open) { ctx->set_error("dbl_sweep_begin twice"); return DBL_ERR_STATE; }
   CUDA_TRY(cudaSetDevice(ctx->device));
   CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-  int rc = sweep_local(ctx, sampler);
+  int rc = enqueue_theta(ctx);
+  if (rc) return rc;
+  rc = update_owned(ctx, sampler);
   if (rc) return rc;
   const int W = ctx->world;
   CUDA_TRY(cudaMemsetAsync(ctx->move_cnt.p, 0, sizeof(unsigned long long) * 4 * W, ctx->stream));
@@ -1582,15 +2329,18 @@ extern "C" int dbl_sweep_begin(dbl_ctx *ctx, int sampler, int64_t *ent_counts, i
   ctx->launches += 2;
   std::vector<unsigned long long> h(2 * W);
   CUDA_TRY(cudaMemcpyAsync(h.data(), ctx->move_cnt.p, sizeof(unsigned long long) * 2 * W, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  rc = snapshot(ctx);  // also the partial summary of the shard (dbl_partial_summary) and the sweep's status
   ctx->h_move_ent.assign(W, 0);
   ctx->h_move_rec.assign(W, 0);
   for (int d = 0; d < W; ++d) {
     ent_counts[d] = ctx->h_move_ent[d] = (int64_t)h[d];
     rec_counts[d] = ctx->h_move_rec[d] = (int64_t)h[W + d];
   }
+  if (rc) {  // abandoned: nothing leaves this rank, but the caller still runs the collective calls of the sweep
+    for (int d = 0; d < W; ++d) ent_counts[d] = rec_counts[d] = ctx->h_move_ent[d] = ctx->h_move_rec[d] = 0;
+  }
   ctx->in_sweep = true;
-  return DBL_OK;
+  return rc;
 }
 
 extern "C" int dbl_exchange_pack(dbl_ctx *ctx, void *ent_buf_dev, void *rec_buf_dev) {
@@ -1639,35 +2389,44 @@ extern "C" int dbl_exchange_unpack(dbl_ctx *ctx, const void *ent_buf_dev, int64_
   return DBL_OK;
 }
 
-extern "C" int dbl_sweep_end(dbl_ctx *ctx) {
-  if (!ctx) return DBL_ERR_INVALID;
+// global_counts = the all-reduced words of dbl_partial_summary (drives the next theta draw); failed != 0: some rank
+// reported an error for this sweep, so it is abandoned on every rank
+extern "C" int dbl_sweep_end(dbl_ctx *ctx, const int64_t *global_counts, double global_loglik, int32_t failed) {
+  if (!ctx || !global_counts) return DBL_ERR_INVALID;
   if (!ctx->in_sweep) { ctx->set_error("dbl_sweep_end without dbl_sweep_begin"); return DBL_ERR_STATE; }
   CUDA_TRY(cudaSetDevice(ctx->device));
   ctx->in_sweep = false;
-  int rc = sweep_finish(ctx);
+  if (failed) {
+    ctx->has_state = false;
+    ctx->set_error("the sweep failed on a peer rank");
+    return DBL_ERR_CUDA;
+  }
+  std::vector<long long> g(ctx->n_counts());
+  for (int i = 0; i < ctx->n_counts(); ++i) g[i] = global_counts[i];
+  memcpy(&g[ctx->ll_slot()], &global_loglik, sizeof(double));
+  CUDA_TRY(cudaMemcpyAsync(ctx->glob(), g.data(), sizeof(long long) * ctx->n_counts(), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  int rc = relayout(ctx);
   if (rc) return rc;
+  k_finish<<<1, 32, 0, ctx->stream>>>(ctx->ctl());
+  ctx->launches += 1;
   CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
-  CUDA_TRY(cudaEventSynchronize(ctx->ev1));
+  rc = snapshot(ctx);
   float ms = 0.f;
-  CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-  ctx->last_sweep_ms = ms;
-  drain_link_events(ctx);
-  return DBL_OK;
+  if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_sweep_ms = ms;
+  return rc;
 }
 
+// partial summary of the shard after dbl_sweep_begin / dbl_set_block_owners (host copy, no device work)
 extern "C" int dbl_partial_summary(dbl_ctx *ctx, int64_t *counts, double *loglik) {
   if (!ctx || !counts || !loglik) return DBL_ERR_INVALID;
-  for (int i = 0; i < ctx->n_counts(); ++i) counts[i] = ctx->h_counts[i];
-  *loglik = ctx->h_loglik_part;
-  return DBL_OK;
-}
-extern "C" int dbl_set_global_summary(dbl_ctx *ctx, const int64_t *counts, double loglik) {
-  if (!ctx || !counts) return DBL_ERR_INVALID;
-  for (int i = 0; i < ctx->n_counts(); ++i) ctx->h_counts[i] = counts[i];
-  ctx->h_loglik_part = loglik;
+  for (int i = 0; i < ctx->n_counts(); ++i) counts[i] = ctx->h_part()[i];
+  counts[ctx->ll_slot()] = 0;
+  memcpy(loglik, &ctx->h_part()[ctx->ll_slot()], sizeof(double));
   return DBL_OK;
 }
 extern "C" int32_t dbl_summary_words(const dbl_ctx *ctx) { return ctx ? ctx->n_counts() : 0; }
+
 extern "C" int dbl_export_owned_dev(dbl_ctx *ctx, void *y_dev, void *blk_dev, void *link_dev, void *z_dev) {
   if (!ctx || !y_dev || !blk_dev || !link_dev || !z_dev) return DBL_ERR_INVALID;
   if (!ctx->has_state) { ctx->set_error("no state"); return DBL_ERR_STATE; }
@@ -1682,6 +2441,41 @@ extern "C" int dbl_export_owned_dev(dbl_ctx *ctx, void *y_dev, void *blk_dev, vo
   return DBL_OK;
 }
 
+// the rows this rank owns, compacted (block-major order): ids + rows.  Host buffers sized for E / R rows.
+extern "C" int dbl_download_owned(dbl_ctx *ctx, int64_t *n_ent, int32_t *ent_ids, int32_t *y, int32_t *block,
+                                  int64_t *n_rec, int32_t *rec_ids, int32_t *link, uint8_t *z) {
+  if (!ctx || !n_ent || !n_rec) return DBL_ERR_INVALID;
+  if (!ctx->has_state) { ctx->set_error("no state"); return DBL_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (ctx->h_owned_ent < 0 || ctx->h_owned_rec < 0) { int rc = snapshot(ctx); if (rc) return rc; }
+  const int64_t ne = ctx->h_owned_ent, nr = ctx->h_owned_rec;
+  const int A = ctx->A;
+  *n_ent = ne; *n_rec = nr;
+  const size_t need_i = (size_t)std::max<int64_t>(ne * (A + 2), nr * 2) + 1;
+  if (ctx->gather_i.n < need_i) CUDA_TRY(ctx->gather_i.alloc(need_i));
+  if (ctx->gather_b.n < (size_t)nr * A + 1) CUDA_TRY(ctx->gather_b.alloc((size_t)nr * A + 1));
+  if (ne > 0 && ent_ids && y && block) {
+    int *ids = ctx->gather_i.p, *yo = ids + ne, *bo = yo + ne * A;
+    k_gather_ent<<<grid_for(ne, 256), 256, 0, ctx->stream>>>(ne, A, ctx->ent_sorted.p, ctx->y.p, ctx->blk.p, ids, yo, bo);
+    CUDA_TRY(cudaMemcpyAsync(ent_ids, ids, sizeof(int) * ne, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(y, yo, sizeof(int) * ne * A, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(block, bo, sizeof(int) * ne, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  if (nr > 0 && rec_ids && link && z) {
+    int *ids = ctx->gather_i.p, *lo = ids + nr;
+    k_gather_rec<<<grid_for(nr, 256), 256, 0, ctx->stream>>>(nr, A, ctx->rec_sorted.p, ctx->link.p, ctx->zmask.p, ids, lo,
+                                                            ctx->gather_b.p);
+    CUDA_TRY(cudaMemcpyAsync(rec_ids, ids, sizeof(int) * nr, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(link, lo, sizeof(int) * nr, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(z, ctx->gather_b.p, (size_t)nr * A, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  ctx->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  return DBL_OK;
+}
+
 extern "C" int dbl_owned_masks(dbl_ctx *ctx, uint8_t *ent_owned, uint8_t *rec_owned) {
   if (!ctx) return DBL_ERR_INVALID;
   if (!ctx->has_state) { ctx->set_error("no state"); return DBL_ERR_STATE; }
@@ -1689,6 +2483,23 @@ extern "C" int dbl_owned_masks(dbl_ctx *ctx, uint8_t *ent_owned, uint8_t *rec_ow
   if (ent_owned) CUDA_TRY(cudaMemcpyAsync(ent_owned, ctx->ent_owned.p, ctx->E, cudaMemcpyDeviceToHost, ctx->stream));
   if (rec_owned) CUDA_TRY(cudaMemcpyAsync(rec_owned, ctx->rec_owned.p, ctx->R, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return DBL_OK;
+}
+
+// fingerprint of the rows this rank owns: hash[0] entities (id, values), hash[1] records (id, link, distortion bits);
+// the sums over ranks mod 2^64 identify the global state whatever the number of ranks or the placement
+extern "C" int dbl_state_hash(dbl_ctx *ctx, uint64_t *hash_out) {
+  if (!ctx || !hash_out) return DBL_ERR_INVALID;
+  if (!ctx->has_state) { ctx->set_error("no state"); return DBL_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  CUDA_TRY(cudaMemsetAsync(ctx->hash_words(), 0, 2 * sizeof(unsigned long long), ctx->stream));
+  k_state_hash<<<grid_rows(std::max(ctx->E, ctx->R), 256), 256, 0, ctx->stream>>>(
+      rows_masked(ctx, true), rows_masked(ctx, false), ctx->A, ctx->y.p, ctx->link.p, ctx->zmask.p, ctx->hash_words());
+  ctx->launches += 1;
+  unsigned long long h[2] = {0, 0};
+  CUDA_TRY(cudaMemcpyAsync(h, ctx->hash_words(), sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  hash_out[0] = h[0]; hash_out[1] = h[1];
   return DBL_OK;
 }
 
@@ -1713,22 +2524,24 @@ extern "C" int dbl_summary(dbl_ctx *ctx, dbl_summary_head *head, int64_t *agg_di
   if (!ctx) return DBL_ERR_INVALID;
   if (!ctx->has_state) { ctx->set_error("no state"); return DBL_ERR_STATE; }
   const int A = ctx->A, F = ctx->F;
+  const long long *g = ctx->h_glob();
   if (head) {
     head->iteration = ctx->iteration;
-    head->num_isolates = ctx->h_counts[ctx->iso_slot()];
-    double ll = ctx->h_loglik_part;
+    head->num_isolates = g[ctx->iso_slot()];
+    double ll;
+    memcpy(&ll, &g[ctx->ll_slot()], sizeof(double));
     for (int a = 0; a < A; ++a)
       for (int f = 0; f < F; ++f) {  // GU:286-293
         const double th = ctx->h_theta[a * F + f];
-        const double nd = (double)ctx->h_counts[a * F + f];
+        const double nd = (double)g[a * F + f];
         ll += (ctx->alpha[a] + nd - 1.0) * std::log(th) +
               (ctx->beta[a] + (double)ctx->file_sizes[f] - nd - 1.0) * std::log(1.0 - th);
       }
     head->log_likelihood = ll;
     head->pairs_scored = ctx->h_pairs;
   }
-  if (agg_dist) for (int i = 0; i < A * F; ++i) agg_dist[i] = ctx->h_counts[i];
-  if (rec_dist) for (int i = 0; i <= A; ++i) rec_dist[i] = ctx->h_counts[A * F + i];
+  if (agg_dist) for (int i = 0; i < A * F; ++i) agg_dist[i] = g[i];
+  if (rec_dist) for (int i = 0; i <= A; ++i) rec_dist[i] = g[A * F + i];
   if (theta) std::copy(ctx->h_theta.begin(), ctx->h_theta.end(), theta);
   return DBL_OK;
 }

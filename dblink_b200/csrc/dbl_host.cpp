@@ -417,58 +417,22 @@ extern "C" int32_t dbl_kdtree_partition_id(const dbl_kdtree *t, const int32_t *y
 }
 
 // ---------------------------------------------------------------------------------------------------
-// updateDistProbs, GU:305-320.  Beta(a,b) = X/(X+Y); X, Y ~ Gamma via Marsaglia & Tsang (2000); normals by
-// Box-Muller; uniforms from Philox stream (phase THETA, id = attr*F + file, sub = call counter).  This runs
-// on the host exactly like the reference runs it on the Spark driver: A*F scalar draws per sweep.
+// updateDistProbs, GU:305-320 on the host (used by the host-mediated exchange path and by tests); the sweep itself
+// draws theta on the device with the same function (draw_theta_one, dbl_internal.h).
 // ---------------------------------------------------------------------------------------------------
-namespace {
-struct ThetaStream {
-  uint64_t seed;
-  uint32_t iter, id, calls;
-  U2 next() { return uniform2(seed, PH_THETA, iter, id, calls++); }
-  double normal() {
-    const U2 u = next();
-    const double rad = std::sqrt(-2.0 * std::log(u.u0));
-    const double ang = 6.283185307179586476925286766559 * u.u1;
-    return rad * std::cos(ang);
-  }
-  double unif() { return next().u0; }
-  double gamma(double shape) {
-    if (shape < 1.0) {
-      const double g = gamma(shape + 1.0);
-      const double u = unif();
-      return g * std::pow(u, 1.0 / shape);
-    }
-    const double d = shape - 1.0 / 3.0;
-    const double c = 1.0 / std::sqrt(9.0 * d);
-    for (;;) {
-      const double xn = normal();
-      double v = 1.0 + c * xn;
-      if (v <= 0.0) continue;
-      v = v * v * v;
-      const double u = unif();
-      const double lhs = std::log(u);
-      double t1 = 0.5 * xn;
-      t1 = t1 * xn;
-      double rhs = t1 + d;
-      rhs = rhs - d * v;
-      rhs = rhs + d * std::log(v);
-      if (lhs < rhs) return d * v;
-    }
-  }
-};
-}  // namespace
-
 void host_draw_theta(int A, int F, const double *alpha, const double *beta, uint64_t seed, const int64_t *agg_dist,
                      const int64_t *file_sizes, uint32_t iter, double *theta_out) {
   for (int a = 0; a < A; ++a)
-    for (int f = 0; f < F; ++f) {
-      const double nd = (double)agg_dist[a * F + f];
-      const double s1 = nd + alpha[a];                         // GU:312
-      const double s2 = (double)file_sizes[f] - nd + beta[a];  // GU:313
-      ThetaStream ts{seed, iter, (uint32_t)(a * F + f), 0};
-      const double gx = ts.gamma(s1);
-      const double gy = ts.gamma(s2);
-      theta_out[a * F + f] = gx / (gx + gy);
-    }
+    for (int f = 0; f < F; ++f)
+      theta_out[a * F + f] = draw_theta_one(seed, iter, (uint32_t)(a * F + f), alpha[a], beta[a],
+                                            (double)agg_dist[a * F + f], (double)file_sizes[f]);
+}
+
+extern "C" double dbl_det_log(double x) { return det_log(x); }
+extern "C" double dbl_det_exp(double x) { return det_exp(x); }
+extern "C" int dbl_draw_theta(int32_t A, int32_t F, const double *alpha, const double *beta, uint64_t seed,
+                              const int64_t *agg_dist, const int64_t *file_sizes, int64_t iteration, double *theta_out) {
+  if (A <= 0 || F <= 0 || !alpha || !beta || !agg_dist || !file_sizes || !theta_out) return DBL_ERR_INVALID;
+  host_draw_theta(A, F, alpha, beta, seed, agg_dist, file_sizes, (uint32_t)iteration, theta_out);
+  return DBL_OK;
 }

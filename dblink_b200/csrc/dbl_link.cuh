@@ -36,10 +36,26 @@ struct AttrDev {
   const unsigned *hmult;
 };
 
+// Control block of a context (device memory, 64-bit words): the sweep is enqueued without host round trips, so
+// everything that changes from sweep to sweep is read from here by the kernels.
+enum : int {
+  CTL_ITER = 0,       // completed sweeps (= iteration of the state); the running sweep draws with CTL_ITER + 1
+  CTL_STATUS = 1,     // 0 ok; bit 0 zero-mass categorical, bit 1 peer time-out, bit 2 a peer reported an error
+  CTL_PAIRS = 2,      // (record, candidate) pairs visited by link kernels since context creation
+  CTL_OWNED_ENT = 3,  // entities / records in the blocks this rank owns (prefix of ent_sorted / rec_sorted)
+  CTL_OWNED_REC = 4,
+  CTL_MOVED_ENT = 5,  // cluster messages sent in the last exchange
+  CTL_MOVED_REC = 6,
+  CTL_EPOCH = 7,      // barriers passed (peer-to-peer exchange)
+  CTL_REPLACED = 8,   // block -> rank placements adopted by the device-side LPT
+  CTL_WORDS = 16
+};
+constexpr long long ST_ZERO_MASS = 1, ST_PEER_TIMEOUT = 2, ST_PEER_ERROR = 4;
+
 struct LinkParams {
   int A, F, P, sampler;
   uint64_t seed;
-  uint32_t iter;
+  const long long *ctl;
   const AttrDev *attrs;
   const int *x, *file, *link;
   const unsigned *zmask;
@@ -47,8 +63,8 @@ struct LinkParams {
   const int *ent_ptr, *tile_ptr, *rec_ptr, *cta_ptr, *ent_sorted, *rec_sorted;
   const int *tiles;
   int *newlink;
-  int *status;
-  unsigned long long *pairs;
+  unsigned long long *status;  // &ctl[CTL_STATUS]
+  unsigned long long *pairs;   // &ctl[CTL_PAIRS]
   // "kernel order" of the attributes: constant attributes first, then the others, each group in ascending
   // attribute id.  Tiles, per-record constants and the multiplication order of the protocol use this order.
   int perm[DBL_MAX_ATTRS];
@@ -84,6 +100,10 @@ __device__ __forceinline__ bool row_find(const AttrDev &at, int v1, int v2, doub
   }
   return false;
 }
+
+__device__ __forceinline__ uint32_t link_iter(const LinkParams &p) { return (uint32_t)(p.ctl[CTL_ITER] + 1); }
+// a failed sweep (zero-mass draw, peer error) is abandoned: every later kernel returns before it changes anything
+__device__ __forceinline__ bool sweep_dead(const long long *ctl) { return ctl[CTL_STATUS] != 0; }
 
 // CTA -> (block, first record) mapping shared by all link kernels
 __device__ __forceinline__ int find_block(const LinkParams &p, int cta) {
@@ -244,15 +264,17 @@ __device__ __forceinline__ double generic_weight(const RecAttr *ra, int A, bool 
   return w;
 }
 
-__device__ __forceinline__ void store_link(const LinkParams &p, int lane, int r, int b, int n, int j) {
+// visited = (record, candidate) pairs this record looked at: the block's entity count in the dense kernels, the
+// length of the posting list walked in the pruned one
+__device__ __forceinline__ void store_link(const LinkParams &p, int lane, int r, int b, long long visited, int j) {
   if (lane == 0) {
     p.newlink[r] = p.ent_sorted[p.ent_ptr[b] + j];
-    atomicAdd(p.pairs, (unsigned long long)n);
+    atomicAdd(p.pairs, (unsigned long long)visited);
   }
 }
 __device__ __forceinline__ void fail_link(const LinkParams &p, int lane, int r) {
   if (lane == 0) {  // reference: IllegalArgumentException("zero probability mass")
-    atomicOr(p.status, 1);
+    atomicOr(p.status, (unsigned long long)ST_ZERO_MASS);
     p.newlink[r] = p.link[r];
   }
 }
@@ -261,7 +283,7 @@ __device__ __forceinline__ void fail_link(const LinkParams &p, int lane, int r) 
 __global__ void __launch_bounds__(LINK_WARPS * 32) k_link_generic(LinkParams p) {
   __shared__ RecAttr s_ra[LINK_WARPS][DBL_MAX_ATTRS];
   const int cta = blockIdx.x;
-  if (cta >= p.cta_ptr[p.P]) return;
+  if (sweep_dead(p.ctl) || cta >= p.cta_ptr[p.P]) return;
   const int b = find_block(p, cta);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ridx = p.rec_ptr[b] + (cta - p.cta_ptr[b]) * LINK_WARPS + warp;
@@ -303,7 +325,7 @@ __global__ void __launch_bounds__(LINK_WARPS * 32) k_link_generic(LinkParams p) 
     }
   }
   if (!(run > 0.0) || isinf(run)) { fail_link(p, lane, r); return; }
-  const U2 u = uniform2(p.seed, PH_LINK, p.iter, (uint32_t)r, 0u);
+  const U2 u = uniform2(p.seed, PH_LINK, link_iter(p), (uint32_t)r, 0u);
   const int j = finish_draw(lane, n, nsteps, spc, nchunks, Q, run, u.u0, wf);
   store_link(p, lane, r, b, n, j);
 }
@@ -403,7 +425,7 @@ __global__ void __launch_bounds__((MATCH_WARPS + 1) * 32) k_link_match(LinkParam
   __shared__ int s_mm_attr[MATCH_WARPS][DBL_MAX_ATTRS];  // must-match attributes, most selective first
   __shared__ int s_mm_x[MATCH_WARPS][DBL_MAX_ATTRS];
   const int cta = blockIdx.x;
-  if (cta >= p.cta_ptr[p.P]) return;
+  if (sweep_dead(p.ctl) || cta >= p.cta_ptr[p.P]) return;
   const int b = find_block(p, cta);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int A = p.A;
@@ -497,7 +519,7 @@ __global__ void __launch_bounds__((MATCH_WARPS + 1) * 32) k_link_match(LinkParam
     const int slot = j % TE;
     return generic_weight(ra, A, false, tile + slot, reinterpret_cast<const double *>(tile + (size_t)A * TE)[slot]);
   };
-  const U2 u = uniform2(p.seed, PH_LINK, p.iter, (uint32_t)r, 0u);
+  const U2 u = uniform2(p.seed, PH_LINK, link_iter(p), (uint32_t)r, 0u);
   const int j = finish_draw(lane, n, nsteps, spc, nchunks, Q, run, u.u0, wf);
   store_link(p, lane, r, b, n, j);
 }
@@ -595,7 +617,7 @@ __global__ void __launch_bounds__(LINK_WARPS * 32) k_link_pruned(PrunedParams pp
   const LinkParams &p = pp.lp;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long ridx = (long long)blockIdx.x * LINK_WARPS + warp;
-  if (ridx >= p.rec_ptr[p.P]) return;  // records of blocks this rank owns come first in rec_sorted
+  if (sweep_dead(p.ctl) || ridx >= p.rec_ptr[p.P]) return;  // records of blocks this rank owns come first in rec_sorted
   const int r = p.rec_sorted[ridx];
   const int b = pp.rec_key_sorted[ridx] >> pp.rec_key_shift;  // the sort key of the record: block id above the cost class
   const int A = p.A;
@@ -741,14 +763,14 @@ __global__ void __launch_bounds__(LINK_WARPS * 32) k_link_pruned(PrunedParams pp
   __syncwarp();
   if (ns == 1) {  // a single candidate with positive weight is drawn whatever the uniform is: skip the search
     if (isinf(s_sw[warp][0])) { fail_link(p, lane, r); return; }
-    store_link(p, lane, r, b, n, s_sj[warp][0]);
+    store_link(p, lane, r, b, phi - plo, s_sj[warp][0]);
     return;
   }
   close_chunks_until(nchunks);
   if (!(run > 0.0) || isinf(run)) { fail_link(p, lane, r); return; }
 
   // ---- pass 2: the same walk restricted to the chosen chunk
-  const U2 u = uniform2(p.seed, PH_LINK, p.iter, (uint32_t)r, 0u);
+  const U2 u = uniform2(p.seed, PH_LINK, link_iter(p), (uint32_t)r, 0u);
   const double t = u.u0 * run;
   unsigned m = __ballot_sync(FULL, lane < nchunks && Q > t);
   const int chunk = m ? (__ffs(m) - 1) : (nchunks - 1);
@@ -819,6 +841,6 @@ __global__ void __launch_bounds__(LINK_WARPS * 32) k_link_pruned(PrunedParams pp
     }
   }
   if (pick < 0) pick = last_pos >= 0 ? last_pos : (chunk * cand_per_chunk + L < n ? chunk * cand_per_chunk + L : n - 1);
-  store_link(p, lane, r, b, n, pick);
+  store_link(p, lane, r, b, phi - plo, pick);
 }
 #endif  // DBL_ENGINE_TU

@@ -136,7 +136,7 @@ template <int A, int NS, int HC, bool PK>
 __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int cta = blockIdx.x;
-  if (cta >= p.cta_ptr[p.P]) return;
+  if (sweep_dead(p.ctl) || cta >= p.cta_ptr[p.P]) return;
   const int b = find_block(p, cta);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = p.ent_ptr[b + 1] - p.ent_ptr[b];
@@ -304,11 +304,11 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkPara
     return pcg2_weight<A, NS, HC, false, PK>(rc, p, tab, ctab, dtab, y, ypack,
                                              reinterpret_cast<const double *>(tile + A * TE)[slot]);
   };
-  const U2 u = uniform2(p.seed, PH_LINK, p.iter, (uint32_t)r, 0u);
+  const U2 u = uniform2(p.seed, PH_LINK, link_iter(p), (uint32_t)r, 0u);
   const int j = finish_draw(lane, n, nsteps, spc, nchunks, Q, run, u.u0, wf);
   store_link(p, lane, r, b, n, j);
 #ifdef DBL_EXP_WAITCLK
-  if (lane == 0 && (cta % 997) == 0 && p.iter == 2)
+  if (lane == 0 && (cta % 997) == 0 && link_iter(p) == 2)
     printf("cta %d warp %d ntiles %d loop %lld wait %lld total %lld\n", cta, warp, ntiles, cloop_, wclk_, clock64() - cstart_);
 #endif
 }
@@ -321,13 +321,13 @@ inline size_t pcg2_smem_bytes(int A, int NS, int H) {
 // launch k_link_pcg2<A, NS, HC> for a runtime NS in [0, A]; HC = 32 (compile-time table size) when the model's
 // tables have 32 slots, else 0 (size read from the parameters); returns cudaError_t as int
 template <int A, int NS, int HC, bool PK>
-int pcg2_launch_one(int grid, cudaStream_t stream, const LinkParams &lp) {
+int pcg2_launch_one(int grid, cudaStream_t stream, const LinkParams &lp, size_t *configured) {
   const size_t smem = pcg2_smem_bytes(A, NS, lp.hslots);
-  static size_t configured = 0;
-  if (configured < smem) {
+  // the opt-in is per device: the cache belongs to the context (one model shape = one instantiation per context)
+  if (*configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(k_link_pcg2<A, NS, HC, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    configured = smem;
+    *configured = smem;
   }
   k_link_pcg2<A, NS, HC, PK><<<grid, (LINK_WARPS + 1) * 32, smem, stream>>>(lp);
   return (int)cudaGetLastError();
@@ -335,16 +335,16 @@ int pcg2_launch_one(int grid, cudaStream_t stream, const LinkParams &lp) {
 
 template <int A, int NS>
 struct Pcg2Launch {
-  static int go(int ns, int grid, cudaStream_t stream, const LinkParams &lp) {
+  static int go(int ns, int grid, cudaStream_t stream, const LinkParams &lp, size_t *cfg) {
     if (ns == NS) {
       // byte-packed constant attributes: 1..4 of them, every vocabulary <= 255 (lp.pack_consts), 32-slot tables
       if constexpr (A - NS >= 1 && A - NS <= 4) {
-        if (lp.pack_consts && lp.hslots == 32) return pcg2_launch_one<A, NS, 32, true>(grid, stream, lp);
+        if (lp.pack_consts && lp.hslots == 32) return pcg2_launch_one<A, NS, 32, true>(grid, stream, lp, cfg);
       }
-      return lp.hslots == 32 ? pcg2_launch_one<A, NS, 32, false>(grid, stream, lp)
-                             : pcg2_launch_one<A, NS, 0, false>(grid, stream, lp);
+      return lp.hslots == 32 ? pcg2_launch_one<A, NS, 32, false>(grid, stream, lp, cfg)
+                             : pcg2_launch_one<A, NS, 0, false>(grid, stream, lp, cfg);
     }
-    if constexpr (NS > 0) return Pcg2Launch<A, NS - 1>::go(ns, grid, stream, lp);
+    if constexpr (NS > 0) return Pcg2Launch<A, NS - 1>::go(ns, grid, stream, lp, cfg);
     return (int)cudaErrorInvalidValue;
   }
 };

@@ -1,23 +1,29 @@
-"""Multi-GPU Gibbs sweep: k-d-tree blocks sharded over ranks, one process per GPU (torch.distributed).
+"""Multi-GPU Gibbs sweep: k-d-tree blocks sharded over ranks, one process per GPU.
 
 Replaces, for the sweep, what Spark does in the reference:
-  - one task per partition (GibbsUpdates.scala:137)            -> blocks placed on ranks by LPT on R_b * E_b
-  - the shuffle `.partitionBy(partitioner)` (GU:144)           -> one all-to-all of the clusters whose new block is
-                                                                  owned by another rank (NCCL over NVLink; gloo in
-                                                                  the CPU tests of this host logic)
-  - accumulators (SummaryAccumulators.scala:54-63)             -> all-reduce of A*F + A + 3 int64 words + 1 double
+  - one task per partition (GibbsUpdates.scala:137)            -> blocks placed on ranks by LPT on R_b * E_b, re-placed
+                                                                  on the device every few sweeps
+  - the shuffle `.partitionBy(partitioner)` (GU:144)           -> clusters whose new block is owned by another rank are
+                                                                  written into that rank's receive buffer over
+                                                                  NVLink/NVSwitch by the kernel that finds them
+  - accumulators (SummaryAccumulators.scala:54-63)             -> every rank sums the partial summaries of all ranks
   - broadcast of theta (State.scala:84)                        -> nothing: every rank draws the same theta from the
                                                                   same counter-based stream
 
-The compute engine is duck-typed (`begin/pack/unpack/end/...`), so the exchange logic below is exercised on CPU
-with the gloo backend by tests/test_distributed.py; on GPUs it drives dblink_b200.GibbsEngine.
+The data plane is INSIDE libdblink_b200.so (`dbl_comm_export / dbl_comm_import`, then plain `dbl_sweep`): the only
+thing this module moves is the 192-byte description of each rank's communication buffer, once.  torch.distributed is
+the out-of-band channel for that handshake and for read-out conveniences (gathering a full state on every rank).
+`exchange="host"` selects the host-mediated fallback for machines without peer access: the library packs / unpacks,
+this module moves the messages with NCCL all-to-alls.  The pure host logic (handshake, host-mediated exchange, merging
+of owned rows, hashing) is exercised on CPU with the gloo backend by tests/test_distributed.py.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
 from . import _lib
-from .engine import GibbsEngine, KDTreePartitioner, SAMPLERS, _check, _p
+from .engine import GibbsEngine, KDTreePartitioner, SAMPLERS, _check, _p, combine_state_hash
 
 
 def lpt_assign(costs, world):
@@ -34,9 +40,18 @@ def lpt_assign(costs, world):
     return owner
 
 
+def gather_blobs(dist, blob, device, torch):
+    """All-gather of the ranks' communication-buffer descriptions (bytes) in rank order."""
+    world = dist.get_world_size()
+    mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(device)
+    out = torch.empty(world * mine.numel(), dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(out, mine)
+    return bytes(out.cpu().numpy().tobytes())
+
+
 def exchange(dist, send_ent, ent_counts, send_rec, rec_counts, ent_words, device, torch):
-    """All-to-all of the packed messages.  send_* are int32 tensors concatenated by destination rank;
-    *_counts are per-destination MESSAGE counts.  Returns (recv_ent, n_ent_msgs, recv_rec, n_rec_msgs)."""
+    """Host-mediated exchange: all-to-all of the packed messages.  send_* are int32 tensors concatenated by
+    destination rank; *_counts are per-destination MESSAGE counts.  Returns (recv_ent, n_ent, recv_rec, n_rec)."""
     world = dist.get_world_size()
     mine = torch.tensor(np.stack([ent_counts, rec_counts], axis=1).reshape(-1), dtype=torch.int64, device=device)
     theirs = torch.empty_like(mine)
@@ -52,23 +67,51 @@ def exchange(dist, send_ent, ent_counts, send_rec, rec_counts, ent_words, device
     return recv_ent, int(in_ent.sum()), recv_rec, int(in_rec.sum())
 
 
-def allreduce_summary(dist, counts, loglik, device, torch):
-    """One all-reduce for the integer summary words and the log-likelihood: the counts travel as float64 (exact
-    below 2^53; they are bounded by records x attributes)."""
-    buf = np.empty(len(counts) + 1, np.float64)
-    buf[:-1] = counts
-    buf[-1] = loglik
+def allreduce_summary(dist, counts, loglik, device, torch, failed=0):
+    """One all-reduce for the integer summary words, the log-likelihood and an error flag: the counts travel as
+    float64 (exact below 2^53; they are bounded by records x attributes).  Returns (counts, loglik, n_failed)."""
+    buf = np.empty(len(counts) + 2, np.float64)
+    buf[:-2] = counts
+    buf[-2] = loglik
+    buf[-1] = float(failed)
     t = torch.from_numpy(buf).to(device)
     dist.all_reduce(t)
     out = t.cpu().numpy()
-    return np.rint(out[:-1]).astype(np.int64), float(out[-1])
+    return np.rint(out[:-2]).astype(np.int64), float(out[-2]), int(round(out[-1]))
+
+
+def merge_owned(parts, R, E, A):
+    """Full state arrays from the ranks' compacted owned rows (`GibbsEngine.download_owned`)."""
+    y = np.zeros((E, A), np.int32)
+    blk = np.zeros(E, np.int32)
+    link = np.zeros(R, np.int32)
+    z = np.zeros((R, A), np.uint8)
+    ne = nr = 0
+    for p in parts:
+        y[p["ent_ids"]] = p["y"]
+        blk[p["ent_ids"]] = p["block"]
+        link[p["rec_ids"]] = p["link"]
+        z[p["rec_ids"]] = p["z"]
+        ne += len(p["ent_ids"])
+        nr += len(p["rec_ids"])
+    if ne != E or nr != R:
+        raise RuntimeError(f"shards do not cover the state: {ne}/{E} entities, {nr}/{R} records")
+    return {"y": y, "block": blk, "link": link, "z": z}
+
+
+def sum_hashes(dist, he, hr, device, torch):
+    """Sum of the ranks' row fingerprints mod 2^64 (two's-complement int64 addition wraps the same way)."""
+    t = torch.from_numpy(np.array([he, hr], np.uint64).view(np.int64).copy()).to(device)
+    dist.all_reduce(t)
+    out = t.cpu().numpy().view(np.uint64)
+    return int(out[0]), int(out[1])
 
 
 class ShardedGibbs:
-    """Same surface as GibbsEngine (init_state / sweep / summary / download_state), block-sharded over the ranks of
-    the default process group."""
+    """Same surface as GibbsEngine (init_state / sweep / summary / links / download_state), block-sharded over the
+    ranks of the default process group."""
 
-    def __init__(self, indexes, alpha, beta, seed=0, num_files=1, levels=0, split_attrs=()):
+    def __init__(self, indexes, alpha, beta, seed=0, num_files=1, levels=0, split_attrs=(), exchange=None):
         import torch
         import torch.distributed as dist
 
@@ -79,9 +122,12 @@ class ShardedGibbs:
         self.eng = GibbsEngine(indexes, alpha, beta, None, seed, num_files, rank=self.rank, world_size=self.world)
         self.A, self.F = self.eng.A, self.eng.F
         self.owner = None
+        self.exchange_mode = exchange or os.environ.get("DBL_EXCHANGE", "p2p")  # "p2p" | "host"
+        self.connected = False
         self._ms = 0.0
         self._stage = {}  # device staging buffers of upload_state
-        self.trace = {}  # host wall-clock ms per phase of the sharded sweep, accumulated (rank-local)
+        self.trace = {}   # host-mediated mode: wall-clock ms per phase of the sweep, accumulated (rank-local)
+        self.last_exchange = (0, 0)
 
     # ---- state ---------------------------------------------------------------------------------------
     def init_state(self, x, file_ids=None, population_size=0):
@@ -97,6 +143,28 @@ class ShardedGibbs:
         ent = np.bincount(blk, minlength=P).astype(np.float64)
         rec = np.bincount(blk[link], minlength=P).astype(np.float64)
         self.set_owners(lpt_assign(ent * rec, self.world))
+        self.connect()
+
+    def connect(self):
+        """The handshake of the peer-to-peer data plane: export this rank's buffer, all-gather the descriptions, map
+        the peers.  Falls back to the host-mediated exchange when peers cannot be mapped."""
+        if self.exchange_mode != "p2p":
+            return
+        L, h = _lib.load(), self.eng._h
+        blob = (C.c_uint8 * _lib.COMM_BLOB_BYTES)()
+        _check(L.dbl_comm_export(h, blob), "comm_export", h)
+        blobs = gather_blobs(self.dist, bytes(blob), self.device, self.torch)
+        rc = L.dbl_comm_import(h, blobs, self.world)
+        ok = self.torch.tensor([1 if rc == _lib.OK else 0], device=self.device)
+        self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN)
+        if int(ok[0]) == 1:
+            self.connected = True
+        else:  # some rank could not map a peer: everybody uses the host path
+            import warnings
+
+            warnings.warn("dblink_b200: peer-to-peer mapping unavailable (%s); using the host-mediated exchange"
+                          % L.dbl_last_error(h).decode())
+            self.exchange_mode = "host"
 
     def _gather_upload(self, name, a, dtype):
         """Full device copy of the host array `a` (identical on every rank): each rank copies 1/world of it over
@@ -133,55 +201,79 @@ class ShardedGibbs:
         self.torch.cuda.current_stream().synchronize()  # the engine copies from these buffers on its own stream
         self.eng.upload_state_device(x.shape[0], y.shape[0], dx.data_ptr(), df.data_ptr(), dz.data_ptr(),
                                      dl.data_ptr(), dy.data_ptr(), theta, iteration)
-        self.set_owners(self.owner)
+        self.set_owners(self.block_owners())
 
     def set_owners(self, owner):
         owner = np.ascontiguousarray(owner, dtype=np.int32)
         self.owner = owner
         _check(_lib.load().dbl_set_block_owners(self.eng._h, _p(owner, _lib.i32p)), "set_block_owners", self.eng._h)
-        self._sync_summary()
 
-    def _sync_summary(self):
-        L = _lib.load()
-        n = L.dbl_summary_words(self.eng._h)
-        counts = np.zeros(n, np.int64)
-        ll = C.c_double(0.0)
-        _check(L.dbl_partial_summary(self.eng._h, _p(counts, _lib.i64p), C.byref(ll)), "partial_summary", self.eng._h)
-        g, gll = allreduce_summary(self.dist, counts, ll.value, self.device, self.torch)
-        g = np.ascontiguousarray(g, dtype=np.int64)
-        _check(L.dbl_set_global_summary(self.eng._h, _p(g, _lib.i64p), gll), "set_global_summary", self.eng._h)
+    def block_owners(self):
+        """Current block -> rank table (the device-side LPT may have changed it since `set_owners`)."""
+        out = np.zeros(self.eng.num_partitions, np.int32)
+        _check(_lib.load().dbl_block_owners(self.eng._h, _p(out, _lib.i32p)), "block_owners", self.eng._h)
+        return out
+
+    def set_rebalance(self, period, threshold=1.03):
+        _check(_lib.load().dbl_set_rebalance(self.eng._h, int(period), float(threshold)), "set_rebalance", self.eng._h)
 
     # ---- transition ----------------------------------------------------------------------------------
     def sweep(self, sampler="PCG-I", n=1):
-        torch, dist, L, h = self.torch, self.dist, _lib.load(), self.eng._h
         s = SAMPLERS[sampler] if isinstance(sampler, str) else int(sampler)
+        if self.connected:
+            L, h = _lib.load(), self.eng._h
+            _check(L.dbl_sweep(h, s, int(n)), "sweep", h)  # the whole transition, exchange included, on the devices
+            self._ms = self.eng.last_sweep_ms()
+            e, r = C.c_int64(0), C.c_int64(0)
+            L.dbl_last_exchange(h, C.byref(e), C.byref(r), None)
+            self.last_exchange = (e.value, r.value)
+            return
+        self._sweep_host_mediated(s, n)
+
+    def _sweep_host_mediated(self, s, n):
+        """Fallback without peer access: the library packs and unpacks, NCCL all-to-alls move the messages.  A failure
+        on one rank (e.g. a categorical without mass) is carried through the collectives of the sweep and raised on
+        EVERY rank afterwards, so nobody is left waiting in a collective."""
+        import time
+
+        torch, dist, L, h = self.torch, self.dist, _lib.load(), self.eng._h
         W, ew = self.world, self.A + 1
         total_ms = 0.0
-        import time
         tr = self.trace
         for _ in range(n):
             ec = np.zeros(W, np.int64)
             rc = np.zeros(W, np.int64)
             t0 = time.perf_counter()
-            _check(L.dbl_sweep_begin(h, s, _p(ec, _lib.i64p), _p(rc, _lib.i64p)), "sweep_begin", h)
+            rc_begin = L.dbl_sweep_begin(h, s, _p(ec, _lib.i64p), _p(rc, _lib.i64p))
+            err = L.dbl_last_error(h).decode() if rc_begin != _lib.OK else ""
             t1 = time.perf_counter()
             send_ent = torch.empty(int(ec.sum()) * ew, dtype=torch.int32, device=self.device)
             send_rec = torch.empty(int(rc.sum()) * 3, dtype=torch.int32, device=self.device)
-            _check(L.dbl_exchange_pack(h, send_ent.data_ptr() if send_ent.numel() else None,
-                                       send_rec.data_ptr() if send_rec.numel() else None), "exchange_pack", h)
+            if rc_begin == _lib.OK:
+                _check(L.dbl_exchange_pack(h, send_ent.data_ptr() if send_ent.numel() else None,
+                                           send_rec.data_ptr() if send_rec.numel() else None), "exchange_pack", h)
             t2 = time.perf_counter()
             recv_ent, ne, recv_rec, nr = exchange(dist, send_ent, ec, send_rec, rc, ew, self.device, torch)
             torch.cuda.synchronize()
             t3 = time.perf_counter()
-            _check(L.dbl_exchange_unpack(h, recv_ent.data_ptr() if ne else None, ne,
-                                         recv_rec.data_ptr() if nr else None, nr), "exchange_unpack", h)
-            _check(L.dbl_sweep_end(h), "sweep_end", h)
+            if rc_begin == _lib.OK:
+                _check(L.dbl_exchange_unpack(h, recv_ent.data_ptr() if ne else None, ne,
+                                             recv_rec.data_ptr() if nr else None, nr), "exchange_unpack", h)
+            nwords = L.dbl_summary_words(h)
+            counts = np.zeros(nwords, np.int64)
+            ll = C.c_double(0.0)
+            L.dbl_partial_summary(h, _p(counts, _lib.i64p), C.byref(ll))
+            g, gll, failed = allreduce_summary(dist, counts, ll.value, self.device, torch, failed=int(rc_begin != _lib.OK))
+            g = np.ascontiguousarray(g, dtype=np.int64)
             t4 = time.perf_counter()
-            total_ms += self.eng.last_sweep_ms()
-            self._sync_summary()
+            rc_end = L.dbl_sweep_end(h, _p(g, _lib.i64p), gll, failed)
+            if rc_begin != _lib.OK:
+                _check(rc_begin, f"sweep_begin ({err})", None)
+            _check(rc_end, "sweep_end", h)
             t5 = time.perf_counter()
-            for k, v in (("begin", t1 - t0), ("pack", t2 - t1), ("exchange", t3 - t2), ("unpack_end", t4 - t3),
-                         ("summary", t5 - t4), ("sweeps", 1e-3)):
+            total_ms += self.eng.last_sweep_ms()
+            for k, v in (("begin", t1 - t0), ("pack", t2 - t1), ("exchange", t3 - t2), ("unpack_summary", t4 - t3),
+                         ("end", t5 - t4), ("sweeps", 1e-3)):
                 tr[k] = tr.get(k, 0.0) + v * 1e3
             self.last_exchange = (int(ec.sum()), int(rc.sum()))
         self._ms = total_ms
@@ -203,6 +295,18 @@ class ShardedGibbs:
     def iteration(self):
         return self.eng.iteration
 
+    @property
+    def num_records(self):
+        return self.eng.num_records
+
+    @property
+    def num_entities(self):
+        return self.eng.num_entities
+
+    @property
+    def num_partitions(self):
+        return self.eng.num_partitions
+
     def owned_masks(self):
         e = self.eng
         em = np.zeros(e.num_entities, np.uint8)
@@ -210,7 +314,24 @@ class ShardedGibbs:
         _check(_lib.load().dbl_owned_masks(e._h, _p(em, _lib.u8p), _p(rm, _lib.u8p)), "owned_masks", e._h)
         return em.astype(bool), rm.astype(bool)
 
-    def download_state(self, out=None):
+    def state_hash(self):
+        """Rank-count-invariant fingerprint of the global state (hex string, identical on every rank)."""
+        he, hr = self.eng.state_hash()
+        he, hr = sum_hashes(self.dist, he, hr, self.device, self.torch)
+        s = self.eng.summary()
+        return combine_state_hash(he, hr, s["theta"], s["iteration"])
+
+    def download_owned(self):
+        """Only this rank's rows (State.save of a distributed state): the device-to-host traffic of the whole job is
+        one copy of the state, not one per rank."""
+        return self.eng.download_owned()
+
+    def links(self):
+        """(link[R], block_of_entity[E]) of the global state on every rank."""
+        d = self.download_state(keys=("link", "block"))
+        return d["link"], d["block"]
+
+    def download_state(self, out=None, keys=("y", "block", "link", "z")):
         """The full state on every rank: each rank exports the rows it owns into device buffers (zeros elsewhere),
         one all-reduce (NCCL) per array sums them, one device-to-host copy brings them back.  `out` may hold
         preallocated (e.g. pinned) host arrays under the keys z, link, y, block; they are filled in place."""
@@ -222,17 +343,19 @@ class ShardedGibbs:
         z = torch.empty(R * A, dtype=torch.uint8, device=self.device)
         _check(_lib.load().dbl_export_owned_dev(e._h, y.data_ptr(), blk.data_ptr(), link.data_ptr(), z.data_ptr()),
                "export_owned", e._h)
-        for t in (y, blk, link, z):
-            dist.all_reduce(t)  # exactly one rank owns each row
+        dev = {"y": (y, (E, A)), "block": (blk, (E,)), "link": (link, (R,)), "z": (z, (R, A))}
+        for k in keys:
+            dist.all_reduce(dev[k][0])  # exactly one rank owns each row
         theta = np.zeros((A, self.F))
         _check(_lib.load().dbl_summary(e._h, None, None, None, _p(theta, _lib.f64p)), "summary", e._h)
         res = {"theta": theta}
-        for k, dev, shape in (("y", y, (E, A)), ("block", blk, (E,)), ("link", link, (R,)), ("z", z, (R, A))):
+        for k in keys:
+            t, shape = dev[k]
             host = out.get(k) if out else None
             if host is None:
-                res[k] = dev.cpu().numpy().reshape(shape)
+                res[k] = t.cpu().numpy().reshape(shape)
             else:
-                torch.from_numpy(host.reshape(-1)).copy_(dev, non_blocking=True)
+                torch.from_numpy(host.reshape(-1)).copy_(t, non_blocking=True)
                 res[k] = host
         torch.cuda.current_stream().synchronize()
         if out and out.get("theta") is not None:

@@ -334,6 +334,34 @@ class GibbsEngine:
         s = SAMPLERS[sampler] if isinstance(sampler, str) else int(sampler)
         _check(_lib.load().dbl_sweep(self._h, s, int(n)), "sweep", self._h)
 
+    def sweep_async(self, sampler="PCG-I", n=1):
+        """Enqueue n sweeps without waiting (nothing in a sweep needs the host); `sync()` collects them."""
+        s = SAMPLERS[sampler] if isinstance(sampler, str) else int(sampler)
+        _check(_lib.load().dbl_sweep_async(self._h, s, int(n)), "sweep_async", self._h)
+
+    def sync(self):
+        _check(_lib.load().dbl_sync(self._h), "sync", self._h)
+
+    def state_hash(self):
+        """(entities, records): order-independent 64-bit fingerprints of the rows this context owns; summed over
+        ranks mod 2^64 they identify the global state for any number of ranks (`combine_state_hash`)."""
+        h = np.zeros(2, np.uint64)
+        _check(_lib.load().dbl_state_hash(self._h, _p(h, _lib.u64p)), "state_hash", self._h)
+        return int(h[0]), int(h[1])
+
+    def download_owned(self):
+        """The rows this context owns, compacted: {ent_ids, y, block, rec_ids, link, z}."""
+        R, E, A = self.num_records, self.num_entities, self.A
+        ne, nr = C.c_int64(0), C.c_int64(0)
+        eid, y, blk = np.zeros(E, np.int32), np.zeros((E, A), np.int32), np.zeros(E, np.int32)
+        rid, link, z = np.zeros(R, np.int32), np.zeros(R, np.int32), np.zeros((R, A), np.uint8)
+        _check(_lib.load().dbl_download_owned(self._h, C.byref(ne), _p(eid, _lib.i32p), _p(y, _lib.i32p),
+                                              _p(blk, _lib.i32p), C.byref(nr), _p(rid, _lib.i32p), _p(link, _lib.i32p),
+                                              _p(z, _lib.u8p)), "download_owned", self._h)
+        ne, nr = ne.value, nr.value
+        return {"ent_ids": eid[:ne], "y": y[:ne], "block": blk[:ne], "rec_ids": rid[:nr], "link": link[:nr],
+                "z": z[:nr]}
+
     def sweep_by_block(self, sampler="PCG-I", order=None):
         """One application of State.nextState driven block by block, the way the reference runs one task per
         partition (GibbsUpdates.updatePartition, GU:156-211).  `order` = the order the blocks are updated in
@@ -370,3 +398,14 @@ class GibbsEngine:
         n = C.c_int64(0)
         ms = _lib.load().dbl_link_kernel_ms(self._h, C.byref(n))
         return ms, n.value
+
+
+def combine_state_hash(ent_hash, rec_hash, theta, iteration):
+    """One hex string for a whole state: the (summed) row fingerprints, theta's bits and the iteration."""
+    import hashlib
+
+    h = hashlib.blake2b(digest_size=8)
+    h.update(np.array([ent_hash % (1 << 64), rec_hash % (1 << 64)], np.uint64).tobytes())
+    h.update(np.ascontiguousarray(theta, np.float64).tobytes())
+    h.update(np.int64(iteration).tobytes())
+    return h.hexdigest()

@@ -55,6 +55,69 @@ class Project:
         base = os.getcwd()
         return cls(hocon.parse_file(path), base)
 
+    # ---- description (what Run.main writes to run.txt, Run.scala:38-43) ----------------------------
+    def mk_string(self):
+        """Project.mkString (Project.scala:58-96)."""
+        def sim(fn):
+            if fn.name == "ConstantSimilarityFn":
+                return "ConstantSimilarityFn"
+            return f"LevenshteinSimilarityFn(threshold={fn.threshold}, maxSimilarity={fn.max_similarity})"
+
+        L = ["Data settings", "-------------", f"  * Using data files located at '{self.data_path}'",
+             f"  * The record identifier attribute is '{self.rec_id_attribute}'",
+             f"  * The file identifier attribute is '{self.file_id_attribute}'" if self.file_id_attribute
+             else "  * There is no file identifier",
+             f"  * The entity identifier attribute is '{self.ent_id_attribute}'" if self.ent_id_attribute
+             else "  * There is no entity identifier",
+             "  * The matching attributes are " + ", ".join(f"'{a.name}'" for a in self.matching_attributes), "",
+             "Hyperparameter settings", "-----------------------"]
+        for i, a in enumerate(self.matching_attributes):
+            L.append(f"  * '{a.name}' (id={i}) with {sim(a.similarity_fn)} and "
+                     f"BetaShapeParameters(alpha={a.alpha}, beta={a.beta})")
+        L += [f"  * Size of latent population is {self.population_size}", "",
+              "Partition function settings", "---------------------------"]
+        if self.num_levels == 0:
+            L.append("  * KDTreePartitioner(numLevels=0)")
+        else:
+            L.append(f"  * KDTreePartitioner(numLevels={self.num_levels}, attributeIds="
+                     f"[{','.join(str(i) for i in self.partition_attribute_ids)}])")
+        L += ["", "Project settings", "----------------", f"  * Using randomSeed={self.random_seed}",
+              f"  * Using expectedMaxClusterSize={self.expected_max_cluster_size}",
+              f"  * Saving Markov chain and complete final state to '{self.output_path}'",
+              "  * Sweeps run on the CUDA device of this process (libdblink_b200); there are no Spark checkpoints"]
+        return "\n".join(L) + "\n"
+
+    def steps_mk_string(self):
+        """ProjectSteps.mkString (ProjectSteps.scala:38-45) with the step descriptions of ProjectStep.scala."""
+        L = ["Scheduled steps", "---------------"]
+        braces = lambda xs: "{" + ", ".join(f"'{x}'" for x in xs) + "}"
+        for name, prm in self.steps():
+            if name == "sample":
+                src = "saved state" if prm["resume"] else "new initial state"
+                L.append(f"  * SampleStep: Evolving the chain from {src} with sampleSize={prm['sample_size']}, "
+                         f"burninInterval={prm['burnin_interval']}, thinningInterval={prm['thinning_interval']} and "
+                         f"sampler={prm['sampler']}")
+            elif name == "summarize":
+                L.append(f"  * SummarizeStep: Calculating summary quantities {braces(prm['quantities'])} along the "
+                         f"chain for iterations >= {prm['lower_iteration_cutoff']}")
+            elif name == "evaluate":
+                if prm["use_existing_smpc"]:
+                    L.append(f"  * EvaluateStep: Evaluating saved sMPC clusters using {braces(prm['metrics'])} metrics")
+                else:
+                    L.append(f"  * EvaluateStep: Evaluating sMPC clusters (computed from the chain for iterations >= "
+                             f"{prm['lower_iteration_cutoff']}) using {braces(prm['metrics'])} metrics")
+            else:
+                L.append("  * CopyFilesStep: Copying {" + ", ".join(prm["file_names"]) + "} to destination "
+                         + prm["destination_path"])
+        return "\n".join(L)
+
+    def write_run_txt(self):
+        """run.txt under outputPath: the project and its scheduled steps (Run.scala:38-43)."""
+        os.makedirs(self.output_path, exist_ok=True)
+        with open(os.path.join(self.output_path, "run.txt"), "w") as fh:
+            fh.write(self.mk_string())
+            fh.write("\n" + self.steps_mk_string())
+
     # ---- data ------------------------------------------------------------------------------------
     def load(self):
         if self._loaded is None:
@@ -104,7 +167,9 @@ class Project:
         d = self.load()
         return state_io.model_fingerprint(d["cache"].indexes, d["x"], d["file"],
                                           [a.alpha for a in self.matching_attributes],
-                                          [a.beta for a in self.matching_attributes])
+                                          [a.beta for a in self.matching_attributes],
+                                          extra=(int(self.random_seed), int(self.population_size or 0),
+                                                 int(self.num_levels), tuple(self.partition_attribute_ids)))
 
     def generate_initial_state(self):
         """Project.generateInitialState (:130-145) -> a GibbsEngine at iteration 0."""
@@ -119,7 +184,9 @@ class Project:
     def saved_state(self):
         """Project.savedState (:113-128): the engine restored from `state.npz` under outputPath, or None.  The
         partition function is re-fitted on the deterministic initial entity values, exactly as the original run
-        fitted it, so the resumed chain continues as if it had never stopped."""
+        fitted it, so the resumed chain continues as if it had never stopped; the fingerprint covers the data, the
+        tables, the priors, randomSeed, populationSize and the partitioner settings, so a state saved under a
+        different configuration is refused instead of being continued with another key / partition function."""
         if not state_io.saved_state_exists(self.output_path):
             return None
         st = state_io.load_state(self.output_path, self.fingerprint())
@@ -197,8 +264,12 @@ class Project:
                     raise ValueError("Ground truth entity ids are required for evaluation")  # ProjectStep.scala:65
                 ch = analysis_arrays.read_chain_arrays(os.path.join(self.output_path, "linkage-chain.parquet"),
                                                        prm["lower_iteration_cutoff"])
-                labels = analysis_arrays.shared_most_probable_clusters(ch)
-                self._save_smpc(analysis_arrays.labels_to_clusters(labels, ch.record_ids))
+                smpc_path = os.path.join(self.output_path, "shared-most-probable-clusters.csv")
+                if prm["use_existing_smpc"] and os.path.exists(smpc_path):  # ProjectStep.scala EvaluateStep
+                    labels = self._read_smpc_labels(smpc_path, ch.record_ids)
+                else:
+                    labels = analysis_arrays.shared_most_probable_clusters(ch)
+                    self._save_smpc(analysis_arrays.labels_to_clusters(labels, ch.record_ids))
                 truth = true_labels(ch.record_ids)
                 text = []
                 for m in prm["metrics"]:
@@ -222,6 +293,20 @@ class Project:
                         if prm["delete_source"]:
                             (shutil.rmtree if os.path.isdir(src) else os.remove)(src)
         return results
+
+    @staticmethod
+    def _read_smpc_labels(path, record_ids):
+        """Labels (aligned with record_ids) from a saved shared-most-probable-clusters.csv: one cluster per line."""
+        pos = {r: i for i, r in enumerate(record_ids.to_pylist())}
+        labels = np.full(len(pos), -1, np.int64)
+        with open(path) as fh:
+            for c, line in enumerate(fh):
+                for rid in (t.strip() for t in line.split(",")):
+                    if rid:
+                        labels[pos[rid]] = c
+        if (labels < 0).any():
+            raise ValueError("shared-most-probable-clusters.csv does not cover every record of the chain")
+        return labels
 
     def _save_smpc(self, clusters):
         with open(os.path.join(self.output_path, "shared-most-probable-clusters.csv"), "w") as fh:

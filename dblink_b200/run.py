@@ -10,6 +10,7 @@ def main(argv=None):
         print("usage: python -m dblink_b200.run <path to config file>", file=sys.stderr)
         return 2
     proj = Project.from_file(argv[0])
+    proj.write_run_txt()  # Run.scala:38-43
     res = proj.execute()
     for k, v in res.items():
         print(k, v)

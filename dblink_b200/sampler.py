@@ -22,21 +22,27 @@ def sample(engine, record_ids, attribute_names, sample_size, output_path, burnin
         raise ValueError("`writeBufferSize` must be positive.")       # :65
     if sampler not in SUPPORTED_SAMPLERS:
         raise ValueError(f"sampler must be one of {', '.join(SUPPORTED_SAMPLERS)}.")  # ProjectStep.scala:44
-    os.makedirs(output_path, exist_ok=True)
+    writer = getattr(engine, "rank", 0) == 0  # a sharded engine runs on every rank; rank 0 writes the outputs
+    if writer:
+        os.makedirs(output_path, exist_ok=True)
     initial_iteration = engine.iteration
     continue_chain = initial_iteration != 0
     pop = population_size if population_size is not None else engine.num_entities
-    lw = LinkageChainWriter(os.path.join(output_path, "linkage-chain.parquet"), write_buffer_size, continue_chain)
-    dw = DiagnosticsWriter(os.path.join(output_path, "diagnostics.csv"), attribute_names, continue_chain)
+    lw = dw = ids = None
+    if writer:
+        lw = LinkageChainWriter(os.path.join(output_path, "linkage-chain.parquet"), write_buffer_size, continue_chain)
+        dw = DiagnosticsWriter(os.path.join(output_path, "diagnostics.csv"), attribute_names, continue_chain)
 
-    import pyarrow as pa
+        import pyarrow as pa
 
-    ids = pa.array([str(r) for r in record_ids], pa.string())
+        ids = pa.array([str(r) for r in record_ids], pa.string())
 
     def record():
-        link, blk = engine.links()
-        parts = linkage_structure_arrow(link, blk, ids)  # {partition id: ListArray of clusters}
+        link, blk = engine.links()  # sharded: a collective, every rank takes part
         s = engine.summary()
+        if not writer:
+            return
+        parts = linkage_structure_arrow(link, blk, ids)  # {partition id: ListArray of clusters}
         lw.append(s["iteration"], parts)
         dw.write_row(s, pop)
         if on_sample:
@@ -46,12 +52,18 @@ def sample(engine, record_ids, attribute_names, sample_size, output_path, burnin
         record()  # the initial state is a sample (Sampler.scala:84-89)
     count, done = 0, 0
     while count < sample_size:
-        engine.sweep(sampler, 1)
-        done += 1
+        # all the sweeps up to the next recorded iteration in ONE call: they are enqueued back to back on the device
+        # and the host waits once (Sampler.scala:92-115 applies nextState one at a time)
         completed = engine.iteration - initial_iteration
-        if completed >= burnin_interval and (completed - burnin_interval) % thinning_interval == 0:
-            record()
-            count += 1
-    lw.close()
-    dw.close()
+        if completed < burnin_interval:
+            step = burnin_interval - completed
+        else:
+            step = thinning_interval - (completed - burnin_interval) % thinning_interval
+        engine.sweep(sampler, step)
+        done += step
+        record()
+        count += 1
+    if writer:
+        lw.close()
+        dw.close()
     return done

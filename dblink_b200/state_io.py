@@ -13,7 +13,9 @@ import numpy as np
 STATE_FILE = "state.npz"
 
 
-def model_fingerprint(indexes, x, file_ids, alpha, beta):
+def model_fingerprint(indexes, x, file_ids, alpha, beta, extra=()):
+    """Everything a saved state depends on: the tables, the encoded records, the priors and `extra` (random seed,
+    population size, partitioner levels / attributes -- they fix the Philox key, E and the partition function)."""
     h = hashlib.sha256()
     for ix in indexes:
         t = ix.tables()
@@ -23,6 +25,7 @@ def model_fingerprint(indexes, x, file_ids, alpha, beta):
     h.update(np.ascontiguousarray(file_ids).tobytes())
     h.update(np.asarray(alpha, np.float64).tobytes())
     h.update(np.asarray(beta, np.float64).tobytes())
+    h.update(repr(tuple(extra)).encode())
     return h.hexdigest()
 
 

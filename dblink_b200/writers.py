@@ -49,6 +49,11 @@ def linkage_structure_arrow(link, block_of_entity, record_ids):
         lo, hi = int(cstart[f]), int(cend[e - 1])
         offs = np.r_[cstart[f:e], hi] - lo
         parts[int(b)] = pa.ListArray.from_arrays(pa.array(offs, pa.int32()), values.slice(lo, hi - lo))
+    # a partition that holds only isolated entities still has a row, with an empty linkage structure
+    # (State.getLinkageStructure maps over every partition, State.scala:102-112)
+    for b in np.unique(np.asarray(block_of_entity)):
+        if int(b) not in parts:
+            parts[int(b)] = pa.ListArray.from_arrays(pa.array([0], pa.int32()), pa.array([], pa.string()))
     return parts
 
 

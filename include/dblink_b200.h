@@ -126,7 +126,8 @@ int64_t dbl_iteration(const dbl_ctx *);
 /* n_sweeps applications of the Markov transition operator State.nextState (State.scala:78-99):
  * updateDistProbs (GU:305-320) -> updatePartitions/updatePartition (GU:124-211: link draw per record
  * GU:363-466, entity values GU:731-755, distortions GU:324-359, new partition ids GU:206) ->
- * updateSummaryVariables (GU:219-301).  Everything but the A x F Beta draws runs on the device. */
+ * updateSummaryVariables (GU:219-301).  Everything runs on the device, the A x F Beta draws included; the host waits
+ * once, at the end of the call.  Works on sharded contexts as well (after dbl_comm_import, see below). */
 int dbl_sweep(dbl_ctx *, int sampler, int32_t n_sweeps);
 
 /* The same transition one k-d-tree block at a time, mirroring the reference's per-partition task
@@ -149,40 +150,87 @@ typedef struct {
   int64_t iteration;
   int64_t num_isolates;
   double log_likelihood;
-  int64_t pairs_scored; /* (record, candidate) pairs evaluated by link kernels since ctx creation */
+  int64_t pairs_scored; /* (record, candidate) pairs visited by link kernels since ctx creation: the block's entity
+                           count per record in the dense kernels, the length of the posting list walked in the pruned one */
 } dbl_summary_head;
 int dbl_summary(dbl_ctx *, dbl_summary_head *head, int64_t *agg_dist /*A*F*/, int64_t *rec_dist /*A+1*/,
                 double *theta /*A*F*/);
 
+/* n sweeps enqueued on the context's stream without waiting for them (dbl_sweep = dbl_sweep_async + dbl_sync).
+ * Nothing in a sweep needs the host: theta is drawn on the device, sizes are read from device memory, the exchange
+ * of a sharded context is peer to peer.  dbl_sync waits, refreshes what dbl_summary / dbl_iteration report and
+ * returns the status of the batch.  A sweep that meets a categorical without mass is ABANDONED: the state, theta
+ * and the iteration are those before that sweep, later sweeps of the batch are skipped, DBL_ERR_ZERO_MASS is
+ * returned (the reference fails the task and no new state exists, IndexNonUniformDiscreteDist.scala:78-79). */
+int dbl_sweep_async(dbl_ctx *, int sampler, int32_t n_sweeps);
+int dbl_sync(dbl_ctx *);
+
+/* Order-independent fingerprint of the rows this context owns: hash_out[0] over (entity id, values), hash_out[1]
+ * over (record id, link, distortion bits).  Sums over ranks (mod 2^64) identify the global state for any number of
+ * ranks and any block placement. */
+int dbl_state_hash(dbl_ctx *, uint64_t *hash_out /*2*/);
+
 /* ---------------------------------------------------------------------------------------------------
  * Multi-GPU: one context per rank/GPU (dbl_model_desc.rank / world_size), blocks sharded over ranks.  Replaces
- * the shuffle `.partitionBy(partitioner)` (GU:144), the broadcast of theta (State.scala:84) and the summary
- * accumulators (SummaryAccumulators.scala:54-63).  Every rank initialises the same replicated state
- * (dbl_state_init / dbl_set_partitioner), then dbl_set_block_owners marks which blocks it owns.  One sweep is
+ * the one-task-per-partition fan-out (GU:137), the shuffle `.partitionBy(partitioner)` (GU:144), the broadcast of
+ * theta (State.scala:84) and the summary accumulators (SummaryAccumulators.scala:54-63).  Every rank initialises
+ * the same replicated state (dbl_state_init / dbl_state_upload, dbl_set_partitioner), then dbl_set_block_owners
+ * carves out its shard.  Draws are keyed by global ids, so the chain is identical for any number of ranks.
+ *
+ * Data plane (a) -- peer to peer, inside the library, no host in the sweep:
+ *   dbl_comm_export   allocates this rank's communication buffer and describes it in a DBL_COMM_BLOB_BYTES blob
+ *                     (CUDA IPC handle); the host layer all-gathers the blobs with whatever it has (sockets, MPI,
+ *                     torch.distributed, Spark's driver) -- this is the only thing it ever moves
+ *   dbl_comm_import   maps every peer's buffer over NVLink / NVSwitch
+ *   dbl_sweep / dbl_sweep_async then run the whole transition on the device: clusters whose new block belongs to
+ *   another rank are written straight into that rank's receive buffer by the kernel that finds them, the partial
+ *   summaries go into a slot of every peer, one flag barrier per sweep, theta is drawn redundantly on every rank.
+ *   Block -> rank placement is re-evaluated on the device every `period` sweeps (dbl_set_rebalance) from the
+ *   global block sizes with the LPT rule of partitioning/LPTScheduler.scala:57-76; re-placed blocks migrate as
+ *   ordinary cluster messages.
+ * Data plane (b) -- host-mediated (no peer access, several nodes): per sweep
  *   dbl_sweep_begin        theta | global summary, links, entity values, distortions of the owned shard; counts of
  *                          entity / record messages for every destination rank
  *   dbl_exchange_pack      messages into caller-provided DEVICE buffers, concatenated by destination rank:
  *                          entity message = 1 + A int32 words [e, y_0..y_{A-1}], record message = 3 words
  *                          [r, e, z bit mask]; the host moves them with one all-to-all (NCCL) each
  *   dbl_exchange_unpack    apply what was received
- *   dbl_sweep_end          re-partition the shard, partial summary
- *   dbl_partial_summary -> all-reduce on the host -> dbl_set_global_summary (drives the next theta draw)
- * Draws are keyed by global ids, so the chain is identical for any number of ranks.
+ *   dbl_partial_summary -> all-reduce on the host (with an error flag) -> dbl_sweep_end(global summary)
  * ------------------------------------------------------------------------------------------------- */
 int dbl_set_block_owners(dbl_ctx *, const int32_t *owner_of_block /* numPartitions entries in [0, world) */);
+int dbl_block_owners(dbl_ctx *, int32_t *owner_of_block_out);  /* current table (the device-side LPT may change it) */
+#define DBL_COMM_BLOB_BYTES 192
+int dbl_comm_export(dbl_ctx *, void *blob_out /* DBL_COMM_BLOB_BYTES */);
+int dbl_comm_import(dbl_ctx *, const void *blobs /* world * DBL_COMM_BLOB_BYTES, in rank order */, int32_t world);
+/* period = 0 switches the re-placement off; threshold = current makespan / LPT makespan above which the LPT table is
+ * adopted (default: every 16 sweeps, 1.03) */
+int dbl_set_rebalance(dbl_ctx *, int32_t period, double threshold);
+/* cluster messages this rank sent in the last sweep collected by dbl_sync, placements adopted so far */
+int dbl_last_exchange(dbl_ctx *, int64_t *ent_msgs, int64_t *rec_msgs, int64_t *replacements);
 int dbl_sweep_begin(dbl_ctx *, int sampler, int64_t *ent_msgs_per_dest /*world*/, int64_t *rec_msgs_per_dest /*world*/);
 int dbl_exchange_pack(dbl_ctx *, void *ent_buf_dev, void *rec_buf_dev);
 int dbl_exchange_unpack(dbl_ctx *, const void *ent_buf_dev, int64_t n_ent_msgs, const void *rec_buf_dev,
                         int64_t n_rec_msgs);
-int dbl_sweep_end(dbl_ctx *);
 int32_t dbl_summary_words(const dbl_ctx *); /* A*F + (A+1) + 2 */
 int dbl_partial_summary(dbl_ctx *, int64_t *counts /*dbl_summary_words*/, double *loglik_without_prior);
-int dbl_set_global_summary(dbl_ctx *, const int64_t *counts, double loglik_without_prior);
+int dbl_sweep_end(dbl_ctx *, const int64_t *global_counts, double global_loglik, int32_t failed_somewhere);
 /* the rows this rank owns (zeros elsewhere) into caller-provided DEVICE buffers: y int32[E*A], block int32[E],
  * link int32[R], z uint8[R*A]; summing them over ranks (all-reduce) gives the full state on every rank */
 int dbl_export_owned_dev(dbl_ctx *, void *y_dev, void *block_dev, void *link_dev, void *z_dev);
+/* only the rows this rank owns, compacted, to the HOST: ids + rows (buffers sized for E / R rows); together the
+ * ranks' rows are the state (State.save of a distributed state, State.scala:122-150) */
+int dbl_download_owned(dbl_ctx *, int64_t *n_ent, int32_t *ent_ids, int32_t *y, int32_t *block_of_entity,
+                       int64_t *n_rec, int32_t *rec_ids, int32_t *link, uint8_t *z);
 /* which entities / records this rank currently owns (host byte arrays of E and R entries) */
 int dbl_owned_masks(dbl_ctx *, uint8_t *ent_owned, uint8_t *rec_owned);
+
+/* The protocol functions of the theta draw, exposed so that they can be checked without a GPU:
+ * log / exp built from individually rounded binary64 operations, and updateDistProbs (GU:305-320) itself. */
+double dbl_det_log(double x);
+double dbl_det_exp(double x);
+int dbl_draw_theta(int32_t num_attrs, int32_t num_files, const double *alpha, const double *beta, uint64_t seed,
+                   const int64_t *agg_dist /*A*F*/, const int64_t *file_sizes /*F*/, int64_t iteration,
+                   double *theta_out /*A*F*/);
 
 /* count of kernels launched by this context since creation (bench.py's gpu_launches) */
 int64_t dbl_kernel_launches(const dbl_ctx *);

@@ -17,6 +17,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 /* ------------------------------------------------------------------------------------------ */
 /* RNG protocol: Philox4x32-10 (Salmon et al., SC'11), counter = (id, sub, iteration, phase),   */
@@ -670,25 +671,85 @@ void orc_state_summary(const orc_state *s, orc_summary_head *head, int64_t *agg_
 /* ------------------------------------------------------------------------------------------ */
 /* theta draw -- updateDistProbs, GU:305-320.  The reference draws Beta variates from           */
 /* commons-math3 on the driver MersenneTwister; the protocol keeps the distribution and fixes    */
-/* the algorithm: Beta = X/(X+Y), X,Y Gamma by Marsaglia-Tsang, normals by Box-Muller, all       */
-/* uniforms from the Philox stream (phase THETA, id = a*F+f, sub = call counter).                */
+/* the algorithm: Beta = X/(X+Y), X,Y Gamma by Marsaglia-Tsang, normals by the polar method,     */
+/* all uniforms from the Philox stream (phase THETA, id = a*F+f, sub = call counter).            */
+/* log and exp are PROTOCOL functions, not libm: the product draws theta on the  */
+/* device, and only individually rounded + - * / (and sqrt) are bit-reproducible across CPU and  */
+/* GPU.  Recipe: log x = k ln2 + 2s + s R(s^2) with x = 2^k m, m in (sqrt(1/2), sqrt(2)],        */
+/* s = (m-1)/(m+1), R(z) = sum_{i=1..11} 2/(2i+1) z^i (Horner from i = 11);                      */
+/* exp x = 2^k sum_{n=0..14} r^n/n! with k = floor(x/ln2 + 1/2), r = (x - k ln2_hi) - k ln2_lo.  */
 /* ------------------------------------------------------------------------------------------ */
+
+static const double LN2_HI = 0x1.62e42p-1;            /* ln 2 rounded to 21 significant bits */
+static const double LN2_LO = 0x1.fdf473de6af28p-22;   /* ln 2 - LN2_HI */
+
+static double u64_as_double(uint64_t b) { double d; memcpy(&d, &b, sizeof d); return d; }
+static uint64_t double_as_u64(double d) { uint64_t b; memcpy(&b, &d, sizeof b); return b; }
+
+double orc_det_log(double x) {
+  static const double c[11] = { /* 2/3, 2/5, ..., 2/23 */
+    2.0 / 3.0, 2.0 / 5.0, 2.0 / 7.0, 2.0 / 9.0, 2.0 / 11.0, 2.0 / 13.0,
+    2.0 / 15.0, 2.0 / 17.0, 2.0 / 19.0, 2.0 / 21.0, 2.0 / 23.0 };
+  int k = 0;
+  uint64_t b = double_as_u64(x);
+  if (((b >> 52) & 0x7ff) == 0) { x = x * 0x1p54; k = -54; b = double_as_u64(x); }
+  k += (int)((b >> 52) & 0x7ff) - 1023;
+  double m = u64_as_double((b & 0xfffffffffffffULL) | 0x3ff0000000000000ULL);
+  if (m > 0x1.6a09e667f3bcdp+0) { m = m * 0.5; k += 1; }
+  double f = m - 1.0;
+  double s = f / (2.0 + f);
+  double z = s * s;
+  double R = c[10];
+  for (int i = 9; i >= 0; --i) { R = R * z; R = R + c[i]; }
+  R = R * z;
+  double dk = (double)k;
+  double t = s * R;
+  t = 2.0 * s + t;
+  t = t + dk * LN2_LO;
+  return dk * LN2_HI + t;
+}
+
+double orc_det_exp(double x) {
+  if (x > 709.0) return INFINITY;
+  if (x < -745.0) return 0.0;
+  double t = x * 0x1.71547652b82fep+0 + 0.5;   /* 1/ln 2 */
+  long long ki = (long long)t;
+  if ((double)ki > t) ki -= 1;
+  double kf = (double)ki;
+  double r = x - kf * LN2_HI;
+  r = r - kf * LN2_LO;
+  double fact = 87178291200.0;                 /* 14! */
+  double p = 1.0 / fact;
+  for (int n = 13; n >= 0; --n) {              /* p = p r + 1/n! */
+    fact = fact / (double)(n + 1);
+    p = p * r;
+    p = p + 1.0 / fact;
+  }
+  if (ki < -1000) { p = p * u64_as_double((uint64_t)(1023 - 1000) << 52); ki += 1000; }
+  return p * u64_as_double((uint64_t)(1023 + ki) << 52);
+}
 
 typedef struct { uint64_t seed; uint32_t iter, id, calls; } theta_stream;
 static void ts_next(theta_stream *t, double u[2]) { orc_uniform2(t->seed, ORC_PHASE_THETA, t->iter, t->id, t->calls++, u); }
 static double ts_normal(theta_stream *t) {
-  double u[2];
-  ts_next(t, u);
-  double rad = sqrt(-2.0 * log(u[0]));
-  double ang = 6.283185307179586476925286766559 * u[1];
-  return rad * cos(ang);
+  for (;;) {
+    double u[2];
+    ts_next(t, u);
+    double v1 = 2.0 * u[0] - 1.0, v2 = 2.0 * u[1] - 1.0;
+    double s = v1 * v1;
+    s = s + v2 * v2;
+    if (s >= 1.0 || s == 0.0) continue;
+    double q = -2.0 * orc_det_log(s);
+    q = q / s;
+    return v1 * sqrt(q);
+  }
 }
 static double ts_uniform(theta_stream *t) { double u[2]; ts_next(t, u); return u[0]; }
 static double ts_gamma(theta_stream *t, double shape) {
   if (shape < 1.0) {
     double g = ts_gamma(t, shape + 1.0);
     double u = ts_uniform(t);
-    return g * pow(u, 1.0 / shape);
+    return g * orc_det_exp(orc_det_log(u) / shape);
   }
   double d = shape - 1.0 / 3.0;
   double c = 1.0 / sqrt(9.0 * d);
@@ -698,12 +759,12 @@ static double ts_gamma(theta_stream *t, double shape) {
     if (v <= 0.0) continue;
     v = v * v * v;
     double u = ts_uniform(t);
-    double lhs = log(u);
+    double lhs = orc_det_log(u);
     double t1 = 0.5 * xn;
     t1 = t1 * xn;
     double rhs = t1 + d;
     rhs = rhs - d * v;
-    rhs = rhs + d * log(v);
+    rhs = rhs + d * orc_det_log(v);
     if (lhs < rhs) return d * v;
   }
 }
@@ -1174,12 +1235,147 @@ static void *link_worker(void *arg) {
   return NULL;
 }
 
+/* phases (3)-(5) of a sweep over the entities [e0,e1) / records [r0,r1): independent rows, so any split over
+   threads gives the same state (every draw has its own counter) */
+typedef struct {
+  orc_state *s;
+  int sampler, phase, tid, nthreads;
+  uint32_t it;
+  const int64_t *ptr, *rec;
+  int32_t *ynew;
+} rest_job;
+
+static void rest_values(rest_job *jb, int64_t e0, int64_t e1) {
+  orc_state *s = jb->s;
+  const orc_model *m = s->m;
+  const int A = m->A;
+  for (int64_t e = e0; e < e1; ++e)
+    for (int a = 0; a < A; ++a) {
+      double u[2];
+      orc_uniform2(m->seed, ORC_PHASE_VALUE, jb->it, (uint32_t)e, (uint32_t)a, u);
+      jb->ynew[e * A + a] = value_draw(s, jb->rec + jb->ptr[e], jb->ptr[e + 1] - jb->ptr[e], a, jb->sampler, u[0], u[1]);
+    }
+}
+
+static void rest_dist(rest_job *jb, int64_t r0, int64_t r1) {
+  orc_state *s = jb->s;
+  const orc_model *m = s->m;
+  const int A = m->A, F = m->F;
+  for (int64_t r = r0; r < r1; ++r)
+    for (int a = 0; a < A; ++a) {
+      const orc_index *ix = m->idx[a];
+      int32_t xv = s->x[r * A + a];
+      double th = s->theta[a * F + s->file[r]];
+      double u[2];
+      orc_uniform2(m->seed, ORC_PHASE_DIST, jb->it, (uint32_t)r, (uint32_t)a, u);
+      uint8_t znew;
+      if (xv < 0) znew = (uint8_t)(u[0] < th);
+      else {
+        int32_t yv = s->y[(int64_t)s->link[r] * A + a];
+        if (xv != yv) znew = 1;
+        else {
+          double pr1 = th * ix->phi[xv];
+          if (!ix->is_const) {
+            double ediag = 1.0;
+            row_find(ix, xv, xv, &ediag);
+            pr1 = pr1 * ix->norm[xv];
+            pr1 = pr1 * ediag;
+          }
+          double pr0 = 1.0 - th;
+          double den = pr1 + pr0;
+          double p = (den != 0.0) ? pr1 / den : 0.0;
+          znew = (uint8_t)(u[0] < p);
+        }
+      }
+      s->z[r * A + a] = znew;
+    }
+}
+
+static void rest_blocks(rest_job *jb, int64_t e0, int64_t e1) {
+  orc_state *s = jb->s;
+  const orc_model *m = s->m;
+  for (int64_t e = e0; e < e1; ++e) s->blk[e] = m->tree ? orc_kdtree_leaf(m->tree, s->y + e * m->A) : 0;
+}
+
+static void *rest_worker(void *arg) {
+  rest_job *jb = (rest_job *)arg;
+  const int64_t n = (jb->phase == 1) ? jb->s->R : jb->s->E;
+  const int64_t lo = n * jb->tid / jb->nthreads, hi = n * (jb->tid + 1) / jb->nthreads;
+  if (jb->phase == 0) rest_values(jb, lo, hi);
+  else if (jb->phase == 1) rest_dist(jb, lo, hi);
+  else rest_blocks(jb, lo, hi);
+  return NULL;
+}
+
+static void rest_run(rest_job *proto, int phase, int nthreads) {
+  rest_job jobs[256];
+  pthread_t th[256];
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 256) nthreads = 256;
+  for (int t = 0; t < nthreads; ++t) {
+    jobs[t] = *proto;
+    jobs[t].phase = phase; jobs[t].tid = t; jobs[t].nthreads = nthreads;
+    if (nthreads == 1) rest_worker(&jobs[t]);
+    else pthread_create(&th[t], NULL, rest_worker, &jobs[t]);
+  }
+  if (nthreads > 1) for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
+}
+
+static double wall_s(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+/* (3) entity values GU:731-755, (4) distortions with the new y GU:205-210,324-359, (5) re-route GU:206;
+   sec[0..2] = wall seconds of the three phases (may be NULL) */
+static void sweep_rest(orc_state *s, int sampler, uint32_t it, int nthreads, double *sec) {
+  const int A = s->m->A;
+  int64_t *ptr, *rec;
+  double t0 = wall_s();
+  build_links_csr(s, &ptr, &rec);
+  int32_t *ynew = (int32_t *)malloc(sizeof(int32_t) * (size_t)(s->E * A + 1));
+  rest_job jb = {s, sampler, 0, 0, 1, it, ptr, rec, ynew};
+  rest_run(&jb, 0, nthreads);
+  memcpy(s->y, ynew, sizeof(int32_t) * (size_t)(s->E * A));
+  free(ynew); free(ptr); free(rec);
+  double t1 = wall_s();
+  rest_run(&jb, 1, nthreads);
+  double t2 = wall_s();
+  rest_run(&jb, 2, nthreads);
+  double t3 = wall_s();
+  if (sec) { sec[0] = t1 - t0; sec[1] = t2 - t1; sec[2] = t3 - t2; }
+}
+
+/* bench only: phases (3)-(5) + the summary pass (GU:219-301) of one sweep on `nthreads` threads, from the current
+   links; sec[0..3] = values, distortions, re-route, summary.  Mutates the state like a sweep would. */
+void orc_rest_of_sweep_timed(orc_state *s, int sampler, int nthreads, double *sec) {
+  const int A = s->m->A, F = s->m->F;
+  sweep_rest(s, sampler, (uint32_t)(s->iteration + 1), nthreads, sec);
+  double t0 = wall_s();
+  orc_summary_head h;
+  int64_t *agg = (int64_t *)malloc(sizeof(int64_t) * (size_t)(A * F));
+  int64_t *rd = (int64_t *)malloc(sizeof(int64_t) * (size_t)(A + 1));
+  orc_state_summary(s, &h, agg, rd);
+  free(agg); free(rd);
+  if (sec) sec[3] = wall_s() - t0;
+  s->iteration += 1;
+}
+
 int orc_state_sweep(orc_state *s, int sampler) {
   const orc_model *m = s->m;
   int A = m->A, F = m->F;
   int status = 0;
   uint32_t it = (uint32_t)(s->iteration + 1);
+  int nthreads = 1;
+  {
+    const char *ev = getenv("ORC_THREADS");
+    if (ev && atoi(ev) > 1) nthreads = atoi(ev);
+    if (nthreads > 256) nthreads = 256;
+  }
   /* (1) theta from the previous state's summary (State.scala:83, GU:305-320) */
+  double *theta_old = (double *)malloc(sizeof(double) * (size_t)(A * F));
+  memcpy(theta_old, s->theta, sizeof(double) * (size_t)(A * F));
   {
     orc_summary_head h;
     int64_t *agg = (int64_t *)malloc(sizeof(int64_t) * (size_t)(A * F));
@@ -1208,10 +1404,6 @@ int orc_state_sweep(orc_state *s, int sampler) {
   {
     /* the draws of different records are independent (own counter each): ORC_THREADS > 1 splits the records over
        threads so that full-size states can be checked in seconds; the result does not depend on the split */
-    int nthreads = 1;
-    const char *ev = getenv("ORC_THREADS");
-    if (ev && atoi(ev) > 1) nthreads = atoi(ev);
-    if (nthreads > 256) nthreads = 256;
     link_job jobs[256];
     pthread_t th[256];
     for (int t = 0; t < nthreads; ++t) {
@@ -1227,55 +1419,20 @@ int orc_state_sweep(orc_state *s, int sampler) {
     }
   }
   free(entN); free(bent); free(bptr);
+  if (status) {
+    /* a categorical without mass fails the reference's task (IndexNonUniformDiscreteDist.scala:78-79): no new
+       state exists afterwards -- the sweep is abandoned and the state is the one before the call */
+    memcpy(s->theta, theta_old, sizeof(double) * (size_t)(A * F));
+    free(theta_old); free(newlink);
+    return status;
+  }
+  free(theta_old);
   memcpy(s->link, newlink, sizeof(int32_t) * (size_t)s->R);
   free(newlink);
-  /* (3) entity values (GU:731-755) */
-  {
-    int64_t *ptr, *rec;
-    build_links_csr(s, &ptr, &rec);
-    int32_t *ynew = (int32_t *)malloc(sizeof(int32_t) * (size_t)(s->E * A + 1));
-    for (int64_t e = 0; e < s->E; ++e)
-      for (int a = 0; a < A; ++a) {
-        double u[2];
-        orc_uniform2(m->seed, ORC_PHASE_VALUE, it, (uint32_t)e, (uint32_t)a, u);
-        ynew[e * A + a] = value_draw(s, rec + ptr[e], ptr[e + 1] - ptr[e], a, sampler, u[0], u[1]);
-      }
-    memcpy(s->y, ynew, sizeof(int32_t) * (size_t)(s->E * A));
-    free(ynew); free(ptr); free(rec);
-  }
-  /* (4) distortions with the new y (GU:205-210, 324-359) */
-  for (int64_t r = 0; r < s->R; ++r)
-    for (int a = 0; a < A; ++a) {
-      const orc_index *ix = m->idx[a];
-      int32_t xv = s->x[r * A + a];
-      double th = s->theta[a * F + s->file[r]];
-      double u[2];
-      orc_uniform2(m->seed, ORC_PHASE_DIST, it, (uint32_t)r, (uint32_t)a, u);
-      uint8_t znew;
-      if (xv < 0) znew = (uint8_t)(u[0] < th);
-      else {
-        int32_t yv = s->y[(int64_t)s->link[r] * A + a];
-        if (xv != yv) znew = 1;
-        else {
-          double pr1 = th * ix->phi[xv];
-          if (!ix->is_const) {
-            double ediag = 1.0;
-            row_find(ix, xv, xv, &ediag);
-            pr1 = pr1 * ix->norm[xv];
-            pr1 = pr1 * ediag;
-          }
-          double pr0 = 1.0 - th;
-          double den = pr1 + pr0;
-          double p = (den != 0.0) ? pr1 / den : 0.0;
-          znew = (uint8_t)(u[0] < p);
-        }
-      }
-      s->z[r * A + a] = znew;
-    }
-  /* (5) re-route (GU:206) */
-  for (int64_t e = 0; e < s->E; ++e) s->blk[e] = m->tree ? orc_kdtree_leaf(m->tree, s->y + e * A) : 0;
+  /* (3)-(5): entity values, distortions, re-route */
+  sweep_rest(s, sampler, it, nthreads, NULL);
   s->iteration += 1;
-  return status;
+  return 0;
 }
 
 /* ------------------------------------------------------------------------------------------ */

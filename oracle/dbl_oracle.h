@@ -109,6 +109,12 @@ void orc_state_summary(const orc_state *, orc_summary_head *head, int64_t *agg_d
 
 /* one sweep: theta -> links -> values -> distortions -> blocks (State.scala:78-99). 0 on success. */
 int orc_state_sweep(orc_state *, int sampler);
+/* bench only: phases (3)-(5) and the summary pass of one sweep from the current links on nthreads threads;
+   sec[0..3] = wall seconds of values / distortions / re-route / summary */
+void orc_rest_of_sweep_timed(orc_state *, int sampler, int nthreads, double *sec);
+/* protocol log / exp of the theta draw */
+double orc_det_log(double x);
+double orc_det_exp(double x);
 /* only the theta draw for the next iteration (GU:305-320) */
 void orc_draw_theta(const orc_model *, const int64_t *agg_dist, const int64_t *file_sizes, uint32_t iter,
                     double *theta_out);

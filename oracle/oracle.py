@@ -21,20 +21,44 @@ c_u8p = C.POINTER(C.c_uint8)
 c_dp = C.POINTER(C.c_double)
 
 
-def build(force=False):
+def build(force=False, native=False):
+    """liboracle.so (portable flags).  native=True: the -march=native build of the same sources, made on the machine
+    that runs it (bench.py's CPU legs); returns the portable library when that build is not possible."""
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("dbl_oracle.c", "dbl_oracle.h", "dbl_refsweep.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("dbl_oracle.c", "dbl_oracle.h", "dbl_oracle_priv.h", "dbl_refsweep.c", "Makefile")]
     srcs = [s for s in srcs if os.path.exists(s)]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    if native:
+        try:
+            subprocess.run(["make", "-C", _HERE, "-s", "native"], check=True, capture_output=True)
+            nso = os.path.join(_HERE, "_native", "liboracle.so")
+            if os.path.exists(nso):
+                return nso
+        except Exception:
+            pass
     return so
+
+
+BUILD_FLAGS = {"portable": "-O3 -march=x86-64-v3 -ffp-contract=off", "native": "-O3 -march=native -ffp-contract=off"}
+_NATIVE = False
+
+
+def use_native():
+    """bench.py only: load the -march=native build (must be called before the first lib())."""
+    global _NATIVE
+    _NATIVE = True
+
+
+def flags():
+    return BUILD_FLAGS["native" if (_LIB is not None and "_native" in str(_LIB._name)) else "portable"]
 
 
 def lib():
     global _LIB
     if _LIB is not None:
         return _LIB
-    L = C.CDLL(build())
+    L = C.CDLL(build(native=_NATIVE))
     vp = C.c_void_p
 
     def sig(name, res, *args):
@@ -79,6 +103,9 @@ def lib():
     sig("orc_state_summary", None, vp, C.c_void_p, c_i64p, c_i64p)
     sig("orc_state_sweep", C.c_int, vp, C.c_int)
     sig("orc_draw_theta", None, vp, c_i64p, c_i64p, C.c_uint32, c_dp)
+    sig("orc_det_log", C.c_double, C.c_double)
+    sig("orc_det_exp", C.c_double, C.c_double)
+    sig("orc_rest_of_sweep_timed", None, vp, C.c_int, C.c_int, c_dp)
     sig("orc_draw_index", C.c_int, c_dp, C.c_int64, C.c_double, C.POINTER(C.c_int))
     sig("orc_invcdf", C.c_int, c_dp, C.c_int, C.c_double)
     sig("orc_ref_link_weights", None, vp, C.c_int64, C.c_int, c_i32p, C.c_int64, c_dp)

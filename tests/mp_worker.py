@@ -17,7 +17,7 @@ def cpu_mode():
     import torch
     import torch.distributed as dist
 
-    from dblink_b200.distributed import allreduce_summary, exchange, lpt_assign
+    from dblink_b200.distributed import allreduce_summary, exchange, gather_blobs, lpt_assign, merge_owned, sum_hashes
 
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -39,9 +39,33 @@ def cpu_mode():
     gotr = recv_rec.numpy().reshape(-1, 3)
     expr = [[s * 1000 + rank * 100 + i, rank, s] for s in range(world) for i in range(2 * (s + rank))]
     assert gotr.tolist() == expr
-    counts, ll = allreduce_summary(dist, np.arange(5, dtype=np.int64) * (rank + 1), 1.5 * (rank + 1), dev, torch)
+    counts, ll, failed = allreduce_summary(dist, np.arange(5, dtype=np.int64) * (rank + 1), 1.5 * (rank + 1), dev, torch,
+                                           failed=int(rank == 1))
     tot = sum(r + 1 for r in range(world))
     assert counts.tolist() == (np.arange(5) * tot).tolist() and abs(ll - 1.5 * tot) < 1e-12
+    assert failed == 1  # an error on one rank is seen by every rank after the collective
+    # the handshake of the peer-to-peer data plane: fixed-size descriptions, gathered in rank order
+    blob = bytes([rank] * 192)
+    blobs = gather_blobs(dist, blob, dev, torch)
+    assert len(blobs) == 192 * world and all(blobs[192 * r:192 * (r + 1)] == bytes([r] * 192) for r in range(world))
+    # row fingerprints add up mod 2^64 on every rank
+    big = (1 << 64) - 5
+    he, hr = sum_hashes(dist, big if rank == 0 else 7, 11 * (rank + 1), dev, torch)
+    exp_e = (big + 7 * (world - 1)) % (1 << 64)
+    assert he == exp_e and hr == 11 * sum(r + 1 for r in range(world))
+    # owned rows of every rank -> the full state
+    R, E, A = 10, 8, 3
+    full_y = np.arange(E * A, dtype=np.int32).reshape(E, A)
+    full_l = (np.arange(R, dtype=np.int32) * 3) % E
+    full_z = (np.arange(R * A).reshape(R, A) % 2).astype(np.uint8)
+    parts = []
+    for r in range(world):
+        e = np.arange(r, E, world)
+        rr = np.arange(r, R, world)
+        parts.append({"ent_ids": e, "y": full_y[e], "block": e % 4, "rec_ids": rr, "link": full_l[rr], "z": full_z[rr]})
+    m = merge_owned(parts, R, E, A)
+    assert np.array_equal(m["y"], full_y) and np.array_equal(m["link"], full_l) and np.array_equal(m["z"], full_z)
+    assert np.array_equal(m["block"], np.arange(E) % 4)
     owner = lpt_assign([9, 1, 8, 2, 7, 3, 3, 3], world)
     loads = np.bincount(owner, weights=[9, 1, 8, 2, 7, 3, 3, 3], minlength=world)
     assert loads.max() - loads.min() <= 3 and set(owner.tolist()) == set(range(world))
