@@ -65,6 +65,8 @@ SIGNATURES = {
     "dbl_kdtree_set_len": (C.c_int32, [vp]),
     "dbl_kdtree_export": (C.c_int, [vp, i32p, i32p, i32p, i32p, i32p, i32p]),
     "dbl_kdtree_partition_id": (C.c_int32, [vp, i32p]),
+    "dbl_set_device": (C.c_int, [C.c_int32]),
+    "dbl_device_count": (C.c_int32, []),
     "dbl_ctx_create": (C.c_int, [C.POINTER(vp), C.POINTER(ModelDesc)]),
     "dbl_ctx_destroy": (None, [vp]),
     "dbl_last_error": (C.c_char_p, [vp]),

@@ -1407,6 +1407,13 @@ static int alloc_control(dbl_ctx *ctx) {
   return DBL_OK;
 }
 
+// for hosts without CUDA bindings of their own (a JVM through JNI): the device of the contexts this thread creates
+extern "C" int dbl_set_device(int32_t device) { return cudaSetDevice(device) == cudaSuccess ? DBL_OK : DBL_ERR_CUDA; }
+extern "C" int32_t dbl_device_count(void) {
+  int n = 0;
+  return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
 extern "C" int dbl_ctx_create(dbl_ctx **out, const dbl_model_desc *d) {
   if (!out || !d || d->num_attrs <= 0 || d->num_attrs > DBL_MAX_ATTRS || d->num_files <= 0 || !d->indexes ||
       !d->alpha || !d->beta)

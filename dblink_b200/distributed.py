@@ -362,3 +362,129 @@ class ShardedGibbs:
             out["theta"][...] = theta
             res["theta"] = out["theta"]
         return res
+
+
+class LocalShards:
+    """The same sharded chain driven from ONE process: one context per rank, one host thread per context while a
+    sweep runs (a JVM host would do the same: one thread per GPU, all through the C ABI).  `devices[r]` is the CUDA
+    device of rank r; several ranks may share a device (the tests shard a chain over 2-3 contexts of a single GPU and
+    still go through the complete exchange: remote cursors, message buffers, flag barrier, summary slots)."""
+
+    def __init__(self, indexes, alpha, beta, seed=0, num_files=1, levels=0, split_attrs=(), world=2, devices=None):
+        self.world = world
+        self.devices = list(devices) if devices is not None else [0] * world
+        self.levels, self.split_attrs = levels, list(split_attrs)
+        L = _lib.load()
+        self.engines = []
+        for r in range(world):
+            _check(L.dbl_set_device(self.devices[r]), "set_device")
+            self.engines.append(GibbsEngine(indexes, alpha, beta, None, seed, num_files, rank=r, world_size=world))
+        self.A, self.F = self.engines[0].A, self.engines[0].F
+
+    def _each(self, fn):
+        """fn(rank, engine) on one thread per rank (ctypes releases the GIL inside the library)."""
+        import threading
+
+        errs = [None] * self.world
+
+        def run(r):
+            try:
+                fn(r, self.engines[r])
+            except BaseException as e:  # noqa: BLE001 -- re-raised on the calling thread
+                errs[r] = e
+
+        th = [threading.Thread(target=run, args=(r,)) for r in range(self.world)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        for e in errs:
+            if e is not None:
+                raise e
+
+    def init_state(self, x, file_ids=None, population_size=0, owner=None):
+        e0 = self.engines[0]
+        for e in self.engines:
+            e.init_state(x, file_ids, population_size)
+        y0 = e0.download_state()["y"]
+        self.partitioners = []
+        for e in self.engines:
+            part = KDTreePartitioner(self.levels, self.split_attrs).fit(y0)
+            e.set_partitioner(part)
+            self.partitioners.append(part)
+        if owner is None:
+            link, blk = e0.links()
+            P = e0.num_partitions
+            ent = np.bincount(blk, minlength=P).astype(np.float64)
+            rec = np.bincount(blk[link], minlength=P).astype(np.float64)
+            owner = lpt_assign(ent * rec, self.world)
+        self.set_owners(owner)
+        self.connect()
+
+    def upload_state(self, x, file_ids, z, link, y, theta, iteration=0):
+        owner = self.block_owners()
+        for e in self.engines:
+            e.upload_state(x, file_ids, z, link, y, theta, iteration)
+        self.set_owners(owner)
+
+    def set_owners(self, owner):
+        owner = np.ascontiguousarray(owner, dtype=np.int32)
+        for e in self.engines:
+            _check(_lib.load().dbl_set_block_owners(e._h, _p(owner, _lib.i32p)), "set_block_owners", e._h)
+
+    def block_owners(self):
+        e = self.engines[0]
+        out = np.zeros(e.num_partitions, np.int32)
+        _check(_lib.load().dbl_block_owners(e._h, _p(out, _lib.i32p)), "block_owners", e._h)
+        return out
+
+    def set_rebalance(self, period, threshold=1.03):
+        for e in self.engines:
+            _check(_lib.load().dbl_set_rebalance(e._h, int(period), float(threshold)), "set_rebalance", e._h)
+
+    def connect(self):
+        L = _lib.load()
+        blobs = b""
+        for e in self.engines:
+            blob = (C.c_uint8 * _lib.COMM_BLOB_BYTES)()
+            _check(L.dbl_comm_export(e._h, blob), "comm_export", e._h)
+            blobs += bytes(blob)
+        for e in self.engines:
+            _check(L.dbl_comm_import(e._h, blobs, self.world), "comm_import", e._h)
+
+    def sweep(self, sampler="PCG-I", n=1):
+        self._each(lambda r, e: e.sweep(sampler, n))
+
+    @property
+    def iteration(self):
+        return self.engines[0].iteration
+
+    def summary(self):
+        return self.engines[0].summary()
+
+    def last_exchange(self):
+        out = []
+        for e in self.engines:
+            a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+            _lib.load().dbl_last_exchange(e._h, C.byref(a), C.byref(b), C.byref(c))
+            out.append((a.value, b.value, c.value))
+        return out
+
+    def download_state(self):
+        e0 = self.engines[0]
+        parts = [e.download_owned() for e in self.engines]
+        d = merge_owned(parts, e0.num_records, e0.num_entities, self.A)
+        d["theta"] = e0.summary()["theta"]
+        return d
+
+    def state_hash(self):
+        he = hr = 0
+        for e in self.engines:
+            a, b = e.state_hash()
+            he, hr = (he + a) % (1 << 64), (hr + b) % (1 << 64)
+        s = self.summary()
+        return combine_state_hash(he, hr, s["theta"], s["iteration"])
+
+    def close(self):
+        for e in self.engines:
+            e.close()

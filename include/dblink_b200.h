@@ -94,6 +94,10 @@ typedef struct {
   int32_t rank, world_size;          /* block shard owned by this context: blocks b with owner[b]==rank   */
 } dbl_model_desc;
 
+/* The CUDA device of the contexts the calling thread creates next (cudaSetDevice), and how many there are: for
+ * hosts without CUDA bindings of their own (one JVM driving several GPUs, one thread per context). */
+int dbl_set_device(int32_t device);
+int32_t dbl_device_count(void);
 int dbl_ctx_create(dbl_ctx **out, const dbl_model_desc *desc);
 void dbl_ctx_destroy(dbl_ctx *);
 const char *dbl_last_error(const dbl_ctx *); /* never NULL; "" when no error */

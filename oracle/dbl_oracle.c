@@ -1206,9 +1206,36 @@ typedef struct {
   int64_t maxn;
   const int64_t *bptr;
   const int32_t *bent;
-  const double *entN;
+  const double *entN;     /* N(e) of bent[i] (block order) */
+  const int32_t *ysorted; /* entity rows in block order: row i = entity bent[i] */
+  const int64_t *rorder;  /* records grouped by block: consecutive records score the same (cache-resident) table */
   int32_t *newlink;
 } link_job;
+
+/* PCG-II weight with the record's sparse similarity rows scattered into dense per-attribute tables (0.0 = not
+   similar): the same multiplications in the same order as protocol_weight, one load instead of a binary search per
+   (candidate, attribute).  Only the link phase of whole sweeps uses it (full-size parity tests need the speed);
+   orc_link_weights keeps the plain form and tests/test_oracle_distribution.py compares the two. */
+typedef struct { int n1, n2, n3; int a1[64], a2[64], a3[64]; } kind_lists; /* attributes of kind 1 / 2 / 3, ascending */
+
+static double protocol_weight_pcg2_dense(const orc_model *m, const rec_attr_t *ra, const kind_lists *kl,
+                                         double *const *dense, const int32_t *ye, double nprod) {
+  double c = 1.0;
+  for (int i = 0; i < kl->n1; ++i) { const int a = kl->a1[i]; if (ye[a] == ra[a].x) c = c * ra[a].rmatch; }
+  double w = nprod * c;
+  double d = 1.0;
+  for (int i = 0; i < kl->n2; ++i) { const int a = kl->a2[i]; if (ye[a] == ra[a].x) d = d * ra[a].rmatch; }
+  w = w * d;
+  for (int i = 0; i < kl->n2; ++i) {
+    const int a = kl->a2[i];
+    if (ye[a] != ra[a].x) {
+      const double e = dense[a][ye[a]];
+      if (e != 0.0) w = w * e;
+    }
+  }
+  for (int i = 0; i < kl->n3; ++i) { const int a = kl->a3[i]; w = w * m->idx[a]->invnorm[ye[a]]; }
+  return w;
+}
 
 /* link update of the records tid, tid + nthreads, ...: every record against every entity of its block */
 static void *link_worker(void *arg) {
@@ -1218,20 +1245,52 @@ static void *link_worker(void *arg) {
   const int A = m->A;
   rec_attr_t *ra = (rec_attr_t *)malloc(sizeof(rec_attr_t) * (size_t)A);
   double *w = (double *)malloc(sizeof(double) * (size_t)(jb->maxn + 1));
-  for (int64_t r = jb->tid; r < s->R; r += jb->nthreads) {
+  double **dense = (double **)calloc((size_t)A, sizeof(double *));
+  const int use_dense = (jb->sampler == ORC_PCG_II) && !getenv("ORC_NO_DENSE");
+  if (use_dense)
+    for (int a = 0; a < A; ++a)
+      if (!m->idx[a]->is_const) dense[a] = (double *)calloc((size_t)m->idx[a]->V + 1, sizeof(double));
+  const int64_t i0 = s->R * jb->tid / jb->nthreads, i1 = s->R * (jb->tid + 1) / jb->nthreads;
+  for (int64_t i = i0; i < i1; ++i) {
+    const int64_t r = jb->rorder[i];
     int b = s->blk[s->link[r]];
     const int32_t *cand = jb->bent + jb->bptr[b];
+    const int32_t *yrows = jb->ysorted + jb->bptr[b] * A;
+    const double *nrows = jb->entN + jb->bptr[b];
     int64_t n = jb->bptr[b + 1] - jb->bptr[b];
     prep_record(s, r, jb->sampler, ra);
-    for (int64_t j = 0; j < n; ++j)
-      w[j] = protocol_weight(s, jb->sampler, ra, s->y + (int64_t)cand[j] * A, jb->entN[cand[j]]);
+    if (use_dense) {
+      kind_lists kl;
+      kl.n1 = kl.n2 = kl.n3 = 0;
+      for (int a = 0; a < A; ++a) {
+        if (ra[a].kind == 1) kl.a1[kl.n1++] = a;
+        else if (ra[a].kind == 2) kl.a2[kl.n2++] = a;
+        else if (ra[a].kind == 3) kl.a3[kl.n3++] = a;
+      }
+      for (int a = 0; a < A; ++a)
+        if (ra[a].kind == 2) {
+          const orc_index *ix = m->idx[a];
+          for (int q = ix->rowptr[ra[a].x]; q < ix->rowptr[ra[a].x + 1]; ++q) dense[a][ix->col[q]] = ix->expsim[q];
+        }
+      for (int64_t j = 0; j < n; ++j)
+        w[j] = protocol_weight_pcg2_dense(m, ra, &kl, dense, yrows + j * A, nrows[j]);
+      for (int a = 0; a < A; ++a)
+        if (ra[a].kind == 2) {
+          const orc_index *ix = m->idx[a];
+          for (int q = ix->rowptr[ra[a].x]; q < ix->rowptr[ra[a].x + 1]; ++q) dense[a][ix->col[q]] = 0.0;
+        }
+    } else {
+      for (int64_t j = 0; j < n; ++j)
+        w[j] = protocol_weight(s, jb->sampler, ra, yrows + j * A, nrows[j]);
+    }
     double u[2];
     orc_uniform2(m->seed, ORC_PHASE_LINK, jb->it, (uint32_t)r, 0, u);
     int st;
     int j = orc_draw_index(w, n, u[0], &st);
     if (st) { jb->status = 1; jb->newlink[r] = s->link[r]; } else jb->newlink[r] = cand[j];
   }
-  free(w); free(ra);
+  for (int a = 0; a < A; ++a) free(dense[a]);
+  free(dense); free(w); free(ra);
   return NULL;
 }
 
@@ -1396,8 +1455,21 @@ int orc_state_sweep(orc_state *s, int sampler) {
     for (int64_t e = 0; e < s->E; ++e) bent[fill[s->blk[e]]++] = (int32_t)e; /* ascending id inside a block */
     free(fill);
   }
+  /* block-ordered copies of what a record scans (same values, contiguous) and the records grouped by block */
   double *entN = (double *)malloc(sizeof(double) * (size_t)(s->E + 1));
-  for (int64_t e = 0; e < s->E; ++e) entN[e] = entity_norm_product(s, s->y + e * A);
+  int32_t *ysorted = (int32_t *)malloc(sizeof(int32_t) * (size_t)(s->E * A + 1));
+  for (int64_t i = 0; i < s->E; ++i) {
+    memcpy(ysorted + i * A, s->y + (int64_t)bent[i] * A, sizeof(int32_t) * (size_t)A);
+    entN[i] = entity_norm_product(s, s->y + (int64_t)bent[i] * A);
+  }
+  int64_t *rorder = (int64_t *)malloc(sizeof(int64_t) * (size_t)(s->R + 1));
+  {
+    int64_t *rfill = (int64_t *)calloc((size_t)nblk + 1, sizeof(int64_t));
+    for (int64_t r = 0; r < s->R; ++r) rfill[s->blk[s->link[r]] + 1]++;
+    for (int b = 0; b < nblk; ++b) rfill[b + 1] += rfill[b];
+    for (int64_t r = 0; r < s->R; ++r) rorder[rfill[s->blk[s->link[r]]]++] = r;
+    free(rfill);
+  }
   int32_t *newlink = (int32_t *)malloc(sizeof(int32_t) * (size_t)(s->R + 1));
   int64_t maxn = 0;
   for (int b = 0; b < nblk; ++b) if (bptr[b + 1] - bptr[b] > maxn) maxn = bptr[b + 1] - bptr[b];
@@ -1409,7 +1481,8 @@ int orc_state_sweep(orc_state *s, int sampler) {
     for (int t = 0; t < nthreads; ++t) {
       link_job *jb = &jobs[t];
       jb->s = s; jb->sampler = sampler; jb->it = it; jb->tid = t; jb->nthreads = nthreads; jb->maxn = maxn;
-      jb->bptr = bptr; jb->bent = bent; jb->entN = entN; jb->newlink = newlink; jb->status = 0;
+      jb->bptr = bptr; jb->bent = bent; jb->entN = entN; jb->ysorted = ysorted; jb->rorder = rorder;
+      jb->newlink = newlink; jb->status = 0;
       if (nthreads == 1) link_worker(jb);
       else pthread_create(&th[t], NULL, link_worker, jb);
     }
@@ -1418,7 +1491,7 @@ int orc_state_sweep(orc_state *s, int sampler) {
       status |= jobs[t].status;
     }
   }
-  free(entN); free(bent); free(bptr);
+  free(entN); free(ysorted); free(rorder); free(bent); free(bptr);
   if (status) {
     /* a categorical without mass fails the reference's task (IndexNonUniformDiscreteDist.scala:78-79): no new
        state exists afterwards -- the sweep is abandoned and the state is the one before the call */

@@ -331,6 +331,8 @@ class State:
         st = 0
         for _ in range(n):
             st |= lib().orc_state_sweep(self.h, sampler)
+            if st:  # an abandoned sweep leaves the state as it was: later sweeps would fail the same way
+                break
         return st
 
     def link_weights(self, r, sampler, cand, literal=False):

@@ -94,3 +94,56 @@ def random_state(rng, x, E, Vs, theta_scale=0.05):
             else:
                 z[r, a] = rng.random() < 0.2
     return y, link, z
+
+
+def _mix64(z):
+    z = np.asarray(z, np.uint64)
+    with np.errstate(over="ignore"):
+        z = z + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def state_hash_numpy(y, link, z):
+    """(entities, records): the row fingerprints dbl_state_hash computes on the device, restated with numpy from host
+    arrays (e.g. the ORACLE's state): sum over rows of a mixed hash of (row id, row contents), mod 2^64."""
+    y = np.asarray(y)
+    E, A = y.shape
+    h = _mix64(np.uint64(0xE000000000000000) ^ np.arange(E, dtype=np.uint64))
+    for a in range(A):
+        h = _mix64(h ^ y[:, a].astype(np.uint32).astype(np.uint64))
+    with np.errstate(over="ignore"):
+        he = int(np.add.reduce(h, dtype=np.uint64))
+    R = len(link)
+    zm = np.zeros(R, np.uint64)
+    for a in range(A):
+        zm |= np.asarray(z)[:, a].astype(np.uint64) << np.uint64(a)
+    g = _mix64(np.uint64(0xA000000000000000) ^ np.arange(R, dtype=np.uint64))
+    g = _mix64(g ^ np.asarray(link).astype(np.uint32).astype(np.uint64))
+    g = _mix64(g ^ zm)
+    with np.errstate(over="ignore"):
+        hr = int(np.add.reduce(g, dtype=np.uint64))
+    return he, hr
+
+
+def host_threads(cap=256):
+    """CPU threads this process may really use: the scheduler affinity mask, cut by a cgroup CPU quota when there is
+    one (a container that shows 128 CPUs may be allowed 8)."""
+    import math
+    import os
+
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]  # cgroup v2
+        if q != "max":
+            n = min(n, max(1, math.ceil(int(q) / int(p))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, math.ceil(q / p)))
+        except Exception:
+            pass
+    return max(1, min(cap, n))

@@ -95,9 +95,14 @@ def gpu_mode():
     x, file = rc.transform_records(g["values"], g["files"])
     alpha = [a.alpha for a in g["attributes"]]
     beta = [a.beta for a in g["attributes"]]
-    for sampler in ("PCG-II", "PCG-I", "Gibbs"):
-        eng = ShardedGibbs(rc.indexes, alpha, beta, seed=99, num_files=len(rc.file_ids), levels=3, split_attrs=(2, 3))
+    # the peer-to-peer data plane (CUDA IPC between the rank processes) for every sampler, and the host-mediated
+    # fallback (NCCL all-to-alls driven from here) once
+    for sampler, mode in (("PCG-II", "p2p"), ("PCG-I", "p2p"), ("Gibbs", "p2p"), ("PCG-II", "host")):
+        eng = ShardedGibbs(rc.indexes, alpha, beta, seed=99, num_files=len(rc.file_ids), levels=3, split_attrs=(2, 3),
+                           exchange=mode)
         eng.init_state(x, file)
+        if mode == "p2p" and world > 1:
+            assert eng.connected, "peer mapping failed: the sharded sweep would fall back to the host path"
         m, st, tree, ox, ofile = oracle_setup(O, g, 99, 3, (2, 3))
         moved = 0
         for it in range(5):
@@ -125,6 +130,11 @@ def gpu_mode():
         dist.all_reduce(t)
         if world > 1:
             assert int(t[0]) > 0, "the test should move clusters between ranks"
+        # rank-count-invariant fingerprint == the one of the oracle's state
+        from helpers import state_hash_numpy
+        from dblink_b200.engine import combine_state_hash
+
+        assert eng.state_hash() == combine_state_hash(*state_hash_numpy(st.y, st.link, st.z), st.theta, st.iteration)
         eng.eng.close()
     dist.barrier()
     dist.destroy_process_group()
@@ -132,5 +142,44 @@ def gpu_mode():
         print(f"gpu sharded chain == oracle chain on {world} ranks")
 
 
+def sample_mode():
+    """Sampler.sample end to end on a sharded engine: every rank sweeps, rank 0 writes the outputs."""
+    import tempfile
+
+    import torch
+    import torch.distributed as dist
+
+    from helpers import synth_problem
+    import dblink_b200 as D
+    from dblink_b200 import sampler as chain
+    from dblink_b200.distributed import ShardedGibbs
+
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    g = synth_problem(seed=6, R=900, n_files=2)
+    rc = D.RecordsCache.build(g["values"], g["files"], g["attributes"])
+    x, file = rc.transform_records(g["values"], g["files"])
+    eng = ShardedGibbs(rc.indexes, [a.alpha for a in g["attributes"]], [a.beta for a in g["attributes"]], seed=3,
+                       num_files=len(rc.file_ids), levels=2, split_attrs=(2, 3))
+    eng.init_state(x, file)
+    out = [tempfile.mkdtemp() if rank == 0 else None]
+    dist.broadcast_object_list(out, src=0)
+    n = chain.sample(eng, [f"r{i}" for i in range(len(x))], [a.name for a in g["attributes"]], 5, out[0],
+                     burnin_interval=2, thinning_interval=3, sampler="PCG-I")
+    assert n == 2 + 4 * 3 and eng.iteration == n
+    dist.barrier()
+    if rank == 0:
+        import pyarrow.parquet as pq
+
+        t = pq.read_table(os.path.join(out[0], "linkage-chain.parquet")).to_pandas()
+        assert sorted(set(t["iteration"])) == [2, 5, 8, 11, 14]
+        rows = open(os.path.join(out[0], "diagnostics.csv")).read().strip().splitlines()
+        assert len(rows) == 1 + 5
+        print(f"sharded sample ok on {world} ranks")
+    dist.destroy_process_group()
+
+
 if __name__ == "__main__":
-    {"cpu": cpu_mode, "gpu": gpu_mode}[sys.argv[1]]()
+    {"cpu": cpu_mode, "gpu": gpu_mode, "sample": sample_mode}[sys.argv[1]]()

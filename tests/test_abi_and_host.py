@@ -211,3 +211,33 @@ def test_every_entry_point_is_documented():
     fns = sorted(set(re.findall(r"\b(dbl_[a-z_0-9]+)\s*\(", header)))
     assert len(fns) >= 50
     assert [f for f in fns if f not in doc] == []
+
+
+def test_theta_draw_of_the_product_equals_the_oracle_bit_for_bit(oracle):
+    """updateDistProbs through the product's C ABI (host build of the function the device runs) against the oracle's
+    own restatement: protocol log / exp and the whole Beta draw, shapes below and above 1"""
+    import ctypes as C
+
+    from dblink_b200 import _lib
+
+    L, OL = _lib.load(), oracle.lib()
+    rng = np.random.default_rng(5)
+    for x in np.r_[rng.uniform(0, 1, 3000), 10.0 ** rng.uniform(-320, 300, 3000)]:
+        assert L.dbl_det_log(float(x)) == OL.orc_det_log(float(x))
+    for x in rng.uniform(-760, 720, 6000):
+        assert L.dbl_det_exp(float(x)) == OL.orc_det_exp(float(x))
+    ix = oracle.Index.build({"a": 1.0, "b": 2.0}, True)
+    alpha, beta = np.array([0.5, 0.5, 10.0, 3.0]), np.array([50.0, 2.0, 1000.0, 1.0])
+    m = oracle.Model([ix] * 4, alpha.tolist(), beta.tolist(), None, 0xC0FFEE12345, F=3)
+    fs = np.array([200, 3000, 1], np.int64)
+    for it in range(1, 400):
+        agg = np.minimum(rng.integers(0, 50, (4, 3)), fs[None, :]).astype(np.int64)
+        if it % 3 == 0:
+            agg[:2] = 0  # shape < 1
+        ref = oracle.draw_theta(m, agg, fs, it)
+        out = np.zeros((4, 3))
+        rc = L.dbl_draw_theta(4, 3, alpha.ctypes.data_as(_lib.f64p), beta.ctypes.data_as(_lib.f64p), 0xC0FFEE12345,
+                              agg.ctypes.data_as(_lib.i64p), fs.ctypes.data_as(_lib.i64p), it,
+                              out.ctypes.data_as(_lib.f64p))
+        assert rc == 0
+        np.testing.assert_array_equal(out, ref)

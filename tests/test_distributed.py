@@ -48,3 +48,13 @@ def test_sharded_chain_matches_oracle():
         res = run_workers("gpu", min(n, 4), 29741)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "sharded chain == oracle chain" in res.stdout
+
+
+@pytest.mark.gpu
+def test_chain_driver_on_a_sharded_engine():
+    """Sampler.sample over ShardedGibbs (links() / num_entities on the sharded engine, outputs on rank 0 only)"""
+    import torch
+
+    res = run_workers("sample", max(1, min(torch.cuda.device_count(), 2)), 29751)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "sharded sample ok" in res.stdout

@@ -81,10 +81,10 @@ def test_full_size_properties(big, sampler):
         e.close()
 
 
-def test_baseline_config3_bit_parity_with_the_oracle(monkeypatch):
-    """BASELINE.json configs[2] (100k records / 8 string attributes / 16 blocks) against the oracle itself: its link
-    update runs on all host threads (ORC_THREADS; the split does not change the draws), so a block of 6 250
-    entities per record is affordable.  Bit-exact links, values, flags, theta after every sweep."""
+def _full_config_against_oracle(monkeypatch, config, records, levels, split, samplers, seed=2024):
+    """A BASELINE.json configuration at full size, sweep by sweep against the oracle: its link update runs on the
+    host threads this process may use (ORC_THREADS; the split does not change the draws).  Bit-exact links, values,
+    flags, theta, block ids after every sweep, and the state fingerprint bench.py prints (`state_hash`)."""
     import os
     import sys
 
@@ -92,55 +92,50 @@ def test_baseline_config3_bit_parity_with_the_oracle(monkeypatch):
     import bench
     import dblink_b200 as D
     from dblink_b200 import synth
+    from dblink_b200.engine import combine_state_hash
+    from helpers import host_threads, state_hash_numpy
+    from oracle import oracle as O
 
-    monkeypatch.setenv("ORC_THREADS", str(min(128, os.cpu_count() or 1)))
-    enc = synth.generate_encoded(1, 100_000, synth.config_attrs(3), dup=0.10, distortion=0.05, missing=0.01, n_files=1)
+    monkeypatch.setenv("ORC_THREADS", str(host_threads()))
+    enc = synth.generate_encoded(2 if config != 3 else 1, records, synth.config_attrs(config), dup=0.10,
+                                 distortion=0.30 if config == 5 else 0.05, missing=0.01, n_files=1 if config == 3 else 2)
     indexes, x, file, F = synth.build_encoded(enc)
-    eng = D.GibbsEngine(indexes, [a.alpha for a in enc["attributes"]], [a.beta for a in enc["attributes"]], None, 2024, F)
+    eng = D.GibbsEngine(indexes, [a.alpha for a in enc["attributes"]], [a.beta for a in enc["attributes"]], None, seed, F)
     eng.init_state(x, file)
-    part = D.KDTreePartitioner(4, [0, 1, 2, 3]).fit(eng.download_state()["y"])
-    eng.set_partitioner(part)
-    st, tree = bench.cpu_prepare(enc, 4, [0, 1, 2, 3])  # the oracle's own tables, initial state and tree, seed 2024
-    assert tree.n_leaves == eng.num_partitions == 16
+    eng.set_partitioner(D.KDTreePartitioner(levels, split).fit(eng.download_state()["y"]))
+    st, tree = bench.cpu_prepare(enc, levels, split)  # the oracle's own tables, initial state and tree, same seed
+    assert tree.n_leaves == eng.num_partitions == 1 << levels
     d = eng.download_state()
     for k in ("link", "y", "z", "theta", "block"):
         np.testing.assert_array_equal(d[k], getattr(st, k), err_msg="initial " + k)
-    from oracle import oracle as O
-
-    for sampler in ("PCG-II", "PCG-I", "PCG-II"):
+    for sampler in samplers:
         eng.sweep(sampler, 1)
         assert st.sweep(O.SAMPLERS[sampler]) == 0
         d = eng.download_state()
         for k in ("theta", "link", "y", "z", "block"):
             np.testing.assert_array_equal(d[k], getattr(st, k), err_msg=f"{sampler} {k}")
+        s = eng.summary()
+        he, hr = eng.state_hash()
+        assert combine_state_hash(he, hr, s["theta"], s["iteration"]) == \
+            combine_state_hash(*state_hash_numpy(st.y, st.link, st.z), st.theta, st.iteration)
+    eng.close()
+    return d
 
 
-@pytest.mark.skipif(__import__("os").environ.get("DBL_FULLSIZE_ORACLE") != "1",
-                    reason="set DBL_FULLSIZE_ORACLE=1: one PCG-II sweep of the 1M table through the oracle "
-                           "(1.6e10 pairs; about half a minute on 128 host threads)")
+def test_baseline_config3_bit_parity_with_the_oracle(monkeypatch):
+    """BASELINE.json configs[2]: 100k records / 8 string attributes / 16 blocks of 6 250 entities."""
+    _full_config_against_oracle(monkeypatch, 3, 100_000, 4, [0, 1, 2, 3], ("PCG-II", "PCG-I", "PCG-II"))
+
+
 def test_baseline_config4_bit_parity_with_the_oracle(monkeypatch):
-    """BASELINE.json configs[3] (1M / 10 attributes / 64 blocks): one PCG-II and one PCG-I sweep against the oracle
-    with its link phase on all host threads.  Opt-in because of the CPU time."""
-    import os
-    import sys
+    """BASELINE.json configs[3], the configuration bench.py times: 1M records / 10 attributes / 64 blocks.  One
+    PCG-II and one PCG-I sweep; the oracle scores 1.6e10 pairs per sweep on the host threads (tens of seconds)."""
+    _full_config_against_oracle(monkeypatch, 4, 1_000_000, 6, [4, 5, 6, 7, 8, 9], ("PCG-II", "PCG-I"))
 
-    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    import bench
-    import dblink_b200 as D
-    from dblink_b200 import synth
-    from oracle import oracle as O
 
-    monkeypatch.setenv("ORC_THREADS", str(min(256, os.cpu_count() or 1)))
-    enc = synth.generate_encoded(2, 1_000_000, synth.config_attrs(4), dup=0.10, distortion=0.05, missing=0.01, n_files=2)
-    indexes, x, file, F = synth.build_encoded(enc)
-    eng = D.GibbsEngine(indexes, [a.alpha for a in enc["attributes"]], [a.beta for a in enc["attributes"]], None, 2024, F)
-    eng.init_state(x, file)
-    split = [4, 5, 6, 7, 8, 9]
-    eng.set_partitioner(D.KDTreePartitioner(6, split).fit(eng.download_state()["y"]))
-    st, tree = bench.cpu_prepare(enc, 6, split)
-    for sampler in ("PCG-II", "PCG-I"):
-        eng.sweep(sampler, 1)
-        assert st.sweep(O.SAMPLERS[sampler]) == 0
-        d = eng.download_state()
-        for k in ("theta", "link", "y", "z", "block"):
-            np.testing.assert_array_equal(d[k], getattr(st, k), err_msg=f"{sampler} {k}")
+def test_baseline_config5_bit_parity_with_the_oracle(monkeypatch):
+    """BASELINE.json configs[4]: 1M records, distortion 0.30, Zipf(1.5) on the first two split attributes, so the 64
+    k-d leaves are unbalanced and clusters carry many distorted attributes.  One PCG-II and one PCG-I sweep."""
+    d = _full_config_against_oracle(monkeypatch, 5, 1_000_000, 6, [4, 5, 6, 7, 8, 9], ("PCG-II", "PCG-I"))
+    sizes = np.bincount(d["block"], minlength=64)
+    assert sizes.max() > 1.3 * sizes.mean()  # the skew the configuration is about

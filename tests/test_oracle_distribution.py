@@ -177,12 +177,16 @@ def test_threaded_link_phase_gives_the_same_chain(oracle, monkeypatch):
 
     g = synth_problem(seed=9, R=900, n_files=2)
     out = {}
-    for nt in ("1", "3", "8"):
-        monkeypatch.setenv("ORC_THREADS", nt)
+    # "plain": the PCG-II weights through the literal per-pair form (binary search in the sparse rows) instead of the
+    # per-record dense similarity tables the whole-sweep link phase uses for speed -- the same multiplications
+    for nt in ("1", "3", "8", "plain"):
+        monkeypatch.setenv("ORC_THREADS", "2" if nt == "plain" else nt)
+        if nt == "plain":
+            monkeypatch.setenv("ORC_NO_DENSE", "1")
         m, st, tree, ox, ofile = oracle_setup(oracle, g, 77, 2, (2, 3))
         for s in ("PCG-II", "PCG-I", "Gibbs", "Gibbs-Sequential"):
             assert st.sweep(oracle.SAMPLERS[s], 2) == 0
         out[nt] = (st.link.copy(), st.y.copy(), st.z.copy(), st.theta.copy())
-    for nt in ("3", "8"):
+    for nt in ("3", "8", "plain"):
         for a, b in zip(out["1"], out[nt]):
             assert np.array_equal(a, b)

@@ -163,3 +163,35 @@ def test_theta_draw_moments(oracle):
             assert draws[:, a, f].var() == pytest.approx(var, rel=0.15)
     # deterministic in (seed, iteration)
     np.testing.assert_array_equal(oracle.draw_theta(m, agg, fs, 7), oracle.draw_theta(m, agg, fs, 7))
+
+
+def test_theta_draw_is_beta_distributed(oracle):
+    """the protocol's Beta draw (Marsaglia-Tsang gammas, polar normals, protocol log / exp) against the exact Beta cdf,
+    including the shape < 1 branch (alpha = 0.5 with no distorted value: RLdata500's prior)"""
+    from scipy import stats
+
+    ix = oracle.Index.build({"a": 1.0, "b": 2.0}, True)
+    m = oracle.Model([ix, ix, ix], [0.5, 0.5, 10.0], [50.0, 2.0, 1000.0], None, 7, F=1)
+    agg = np.array([[0], [0], [37]], np.int64)
+    fs = np.array([500], np.int64)
+    draws = np.stack([oracle.draw_theta(m, agg, fs, it) for it in range(1, 8001)])[:, :, 0]
+    for a, (al, be) in enumerate([(0.5, 50.0), (0.5, 2.0), (10.0, 1000.0)]):
+        s1, s2 = al + agg[a, 0], be + fs[0] - agg[a, 0]
+        ks = stats.kstest(draws[:, a], stats.beta(s1, s2).cdf)
+        assert ks.pvalue > 1e-3, (a, ks)
+
+
+def test_protocol_log_exp_accuracy(oracle):
+    """DESIGN.md 4.5: log / exp built from individually rounded IEEE operations (bit-reproducible on CPU and GPU);
+    they only have to be GOOD functions: within a few ulp of libm over the ranges the theta draw uses"""
+    L = oracle.lib()
+    rng = np.random.default_rng(0)
+    xs = np.r_[rng.uniform(0, 1, 4000), 10.0 ** rng.uniform(-300, 300, 4000), [1.0, 2.0, 0.5, 1e-310, 5e-324, 1.7976931348623157e308]]
+    for x in xs:
+        got, ref = L.orc_det_log(float(x)), math.log(x)
+        assert abs(got - ref) <= 4 * np.spacing(abs(ref)) + 1e-320, x
+    assert L.orc_det_log(1.0) == 0.0
+    for x in np.r_[rng.uniform(-745, 709, 6000), rng.uniform(-1, 1, 2000), [0.0]]:
+        got, ref = L.orc_det_exp(float(x)), math.exp(x)
+        assert abs(got - ref) <= 4 * np.spacing(ref), x
+    assert L.orc_det_exp(0.0) == 1.0 and L.orc_det_exp(-800.0) == 0.0
