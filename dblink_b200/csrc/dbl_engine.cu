@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cub/cub.cuh>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -190,7 +191,7 @@ __global__ void k_rec_block_keys(int64_t R, const int *__restrict__ link, const 
 }
 // cost class of a record (x is static): bits 7..6 = number of missing non-constant attributes (each one adds a
 // gather per candidate), bits 5..0 = expected number of similar-but-different candidate values per 32-candidate
-// step (how often the warp takes the similarity multiply), from the empirical value frequencies.
+// step (how often the warp takes the rare multiply: equal or similar value), from the empirical value frequencies.
 __global__ void k_rec_class(int64_t R, int A, const AttrDev *__restrict__ attrs, const int *__restrict__ x,
                             unsigned char *__restrict__ cls) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -202,6 +203,7 @@ __global__ void k_rec_class(int64_t R, int A, const AttrDev *__restrict__ attrs,
     if (at.is_const) continue;
     const int xv = x[r * A + a];
     if (xv < 0) { ++miss; continue; }
+    h += at.probs[xv];  // an equal value takes the same path as a similar one (one table, see k_link_pcg2)
     for (int i = at.rowptr[xv]; i < at.rowptr[xv + 1]; ++i)
       if (at.col[i] != xv) h += at.probs[at.col[i]];
   }
@@ -251,7 +253,8 @@ __global__ void k_block_scan(int P, const int *__restrict__ ent_ptr, const int *
 __global__ void k_build_tiles(int64_t E, int A, const int *__restrict__ y, const double *__restrict__ entN,
                               const int *__restrict__ blk_sorted, const int *__restrict__ ent_sorted,
                               const int *__restrict__ ent_ptr, const int *__restrict__ tile_ptr,
-                              int *__restrict__ tiles, const int *__restrict__ perm, int P, int npack) {
+                              int *__restrict__ tiles, const int *__restrict__ perm, int P, int npack,
+                              int *__restrict__ qtiles, int n_str, int qtile_pk) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= E) return;
   const int b = blk_sorted[i];
@@ -265,6 +268,17 @@ __global__ void k_build_tiles(int64_t E, int A, const int *__restrict__ y, const
   unsigned pk = 0;  // constant attributes (kernel positions 0..npack-1), one byte each, for k_link_pcg2
   for (int k = 0; k < npack; ++k) pk |= ((unsigned)y[(int64_t)e * A + perm[k]] & 0xFFu) << (8 * k);
   tile[(size_t)(A + 2) * TE + slot] = (int)pk;
+  // quad tile of the same entity (k_link_pcg2): [group][slot][4]
+  const int nv = qtile_nv(A, n_str, qtile_pk != 0), ng = qtile_groups(nv), qw = qtile_words(nv);
+  int *qt = qtiles + (size_t)(tile_ptr[b] + j / TE) * qw * TE;
+  auto put = [&](int w, int v) { qt[((size_t)(w >> 2) * TE + slot) * 4 + (w & 3)] = v; };
+  if (qtile_pk) {
+    for (int q = 0; q < n_str; ++q) put(q, y[(int64_t)e * A + perm[A - n_str + q]]);
+    put(n_str, (int)pk);
+  } else {
+    for (int k = 0; k < A; ++k) put(k, y[(int64_t)e * A + perm[k]]);
+  }
+  reinterpret_cast<double *>(qt + (size_t)ng * 4 * TE)[slot] = entN[e];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1207,7 +1221,8 @@ struct dbl_ctx {
 
   // layout
   DevBuf<int> iota, blk_sorted, ent_sorted, rec_key, rec_key_sorted, rec_sorted;
-  DevBuf<int> ent_ptr, tile_ptr, rec_ptr, cta_ptr, cta_ptr2, tiles;
+  DevBuf<int> ent_ptr, tile_ptr, rec_ptr, cta_ptr, cta_ptr2, tiles, qtiles;
+  int qtile_pk = 0;  // quad tiles carry the packed constants (PK instantiations of k_link_pcg2)
   // inverted index of the block tables for the pruned PCG-I link kernel (built on demand, once per sweep)
   DevBuf<unsigned long long> inv_key_in, inv_key;
   DevBuf<int> inv_pos_in, inv_pos, inv_seg, inv_vptr;
@@ -1236,7 +1251,22 @@ struct dbl_ctx {
   int64_t link_launches = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_events, event_pool;
   size_t pcg2_smem_cfg = 0, match_smem_cfg = 0;  // dynamic shared memory opted in on THIS device
+  int pcg2_grid = 148 * DBL_PCG2_CTAS_PER_SM;   // persistent CTAs of k_link_pcg2
   bool async_open = false;  // sweeps enqueued by dbl_sweep_async, not yet collected by dbl_sync
+  // CUDA graphs of one sweep (launch-bound problem sizes): key = sampler * 4 + link mode
+  struct SweepGraph { cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
+  std::map<int, SweepGraph> graphs;
+  std::map<int, bool> graph_warm;  // one eager sweep of that kind has run (lazy allocations, shared-memory opt-ins)
+  int graph_mode = 0;              // 0 auto (small problems), 1 never, 2 always
+  bool capturing = false;
+  void drop_graphs() {
+    for (auto &kv : graphs) {
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+      if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
+    }
+    graphs.clear();
+    graph_warm.clear();
+  }
 
   void set_error(const std::string &s) { err = s; }
 };
@@ -1432,6 +1462,11 @@ extern "C" int dbl_ctx_create(dbl_ctx **out, const dbl_model_desc *d) {
   ctx->alpha.assign(d->alpha, d->alpha + ctx->A);
   ctx->beta.assign(d->beta, d->beta + ctx->A);
   cudaGetDevice(&ctx->device);
+  {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device) == cudaSuccess && sms > 0)
+      ctx->pcg2_grid = sms * DBL_PCG2_CTAS_PER_SM;
+  }
   *out = ctx;
   CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&ctx->ev0));
@@ -1462,6 +1497,7 @@ extern "C" void dbl_ctx_destroy(dbl_ctx *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   comm_close(ctx);
+  ctx->drop_graphs();
   for (auto &pe : ctx->pending_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
   for (auto &pe : ctx->event_pool) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -1479,6 +1515,7 @@ extern "C" const char *dbl_version(void) { return "dblink_b200 0.2 (sm_100a)"; }
 
 static int alloc_blocks(dbl_ctx *ctx) {
   const int P = ctx->P;
+  ctx->drop_graphs();  // captured sweeps hold the old buffers / tree
   if ((int)ctx->owner_h.size() != P) ctx->owner_h.assign(P, ctx->rank);
   CUDA_TRY(ctx->owner.alloc(P));
   CUDA_TRY(cudaMemcpy(ctx->owner.p, ctx->owner_h.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
@@ -1491,6 +1528,8 @@ static int alloc_blocks(dbl_ctx *ctx) {
   CUDA_TRY(ctx->lpt_dscratch.alloc((size_t)P + MAX_WORLD));
   const size_t max_tiles = (size_t)(ctx->E / TE) + (size_t)P + 1;
   CUDA_TRY(ctx->tiles.alloc(max_tiles * tile_words(ctx->A)));
+  ctx->qtile_pk = (ctx->pack_consts && ctx->hslots == 32) ? 1 : 0;
+  CUDA_TRY(ctx->qtiles.alloc(max_tiles * qtile_words(qtile_nv(ctx->A, ctx->n_str, ctx->qtile_pk != 0)) * TE));
   ctx->max_ctas = (int)((ctx->R + LINK_WARPS - 1) / LINK_WARPS) + P;
   return alloc_control(ctx);
 }
@@ -1509,6 +1548,7 @@ static int alloc_state(dbl_ctx *ctx, int64_t R, int64_t E) {
     ctx->comm_buf.release();
   }
   ctx->R = R; ctx->E = E;
+  ctx->drop_graphs();
   CUDA_TRY(ctx->zbytes.alloc((size_t)R * A));
   CUDA_TRY(ctx->vflag.alloc(1));
   CUDA_TRY(ctx->file_cnt.alloc(ctx->F));
@@ -1590,9 +1630,11 @@ static int relayout(dbl_ctx *ctx) {
   k_block_scan<<<1, 32, 0, ctx->stream>>>(P, ctx->ent_ptr.p, ctx->rec_ptr.p, ctx->tile_ptr.p, ctx->cta_ptr.p,
                                           LINK_WARPS, ctx->cta_ptr2.p, MATCH_WARPS, ctx->ctl());
   CUDA_TRY(cudaMemsetAsync(ctx->tiles.p, 0, ctx->tiles.n * sizeof(int), ctx->stream));
+  CUDA_TRY(cudaMemsetAsync(ctx->qtiles.p, 0, ctx->qtiles.n * sizeof(int), ctx->stream));
   k_build_tiles<<<grid_for(E, 256), 256, 0, ctx->stream>>>(E, A, ctx->y.p, ctx->entN.p, ctx->blk_sorted.p,
                                                            ctx->ent_sorted.p, ctx->ent_ptr.p, ctx->tile_ptr.p,
-                                                           ctx->tiles.p, ctx->perm_dev.p, P, ctx->pack_consts);
+                                                           ctx->tiles.p, ctx->perm_dev.p, P, ctx->pack_consts,
+                                                           ctx->qtiles.p, ctx->n_str, ctx->qtile_pk);
   ctx->launches += 11;
   ctx->inv_valid = false;
   ctx->h_owned_ent = ctx->h_owned_rec = -1;  // changed on the device; snapshot() brings them back
@@ -1728,6 +1770,7 @@ extern "C" int dbl_set_partitioner(dbl_ctx *ctx, const dbl_kdtree *tree) {
   CUDA_TRY(cudaSetDevice(ctx->device));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   if (ctx->has_state && !ctx->all_owned) { ctx->set_error("dbl_set_partitioner after dbl_set_block_owners"); return DBL_ERR_STATE; }
+  ctx->drop_graphs();
   int rc = upload_tree(ctx, tree);
   if (rc) return rc;
   if (!ctx->has_state) return alloc_control(ctx);
@@ -1903,6 +1946,22 @@ static int ensure_inverted_index(dbl_ctx *ctx) {
   return DBL_OK;
 }
 
+static bool pcg2_kernel_fits(const dbl_ctx *ctx) {
+  return ctx->hslots > 0 && ctx->A <= LINK_MAX_UNROLL_A &&
+         pcg2_smem_bytes(ctx->A, ctx->n_str, ctx->hslots, ctx->qtile_pk != 0) <= 100 * 1024;
+}
+static int dispatch_pcg2(dbl_ctx *ctx, int grid, const LinkParams &lp) {
+  int rc = -1;
+  switch (ctx->A) {
+#define DBL_CASE(N) case N: rc = dbl_launch_pcg2_a##N(ctx->n_str, grid, ctx->stream, lp, &ctx->pcg2_smem_cfg); break;
+    DBL_CASE(1) DBL_CASE(2) DBL_CASE(3) DBL_CASE(4) DBL_CASE(5) DBL_CASE(6) DBL_CASE(7) DBL_CASE(8)
+    DBL_CASE(9) DBL_CASE(10) DBL_CASE(11) DBL_CASE(12) DBL_CASE(13) DBL_CASE(14) DBL_CASE(15) DBL_CASE(16)
+#undef DBL_CASE
+  }
+  if (rc != 0) { ctx->set_error(std::string("k_link_pcg2 launch: ") + cudaGetErrorString((cudaError_t)rc)); return DBL_ERR_CUDA; }
+  return DBL_OK;
+}
+
 static int launch_link(dbl_ctx *ctx, int sampler) {
   const int A = ctx->A;
   LinkParams lp;
@@ -1912,6 +1971,8 @@ static int launch_link(dbl_ctx *ctx, int sampler) {
   lp.theta = ctx->theta(); lp.ent_ptr = ctx->ent_ptr.p; lp.tile_ptr = ctx->tile_ptr.p; lp.rec_ptr = ctx->rec_ptr.p;
   lp.cta_ptr = ctx->cta_ptr.p; lp.ent_sorted = ctx->ent_sorted.p; lp.rec_sorted = ctx->rec_sorted.p;
   lp.tiles = ctx->tiles.p; lp.newlink = ctx->newlink.p;
+  lp.qtiles = ctx->qtiles.p; lp.qtile_pk = ctx->qtile_pk;
+  lp.work = reinterpret_cast<unsigned long long *>(ctx->ctl() + CTL_WORK);
   lp.status = reinterpret_cast<unsigned long long *>(ctx->ctl() + CTL_STATUS);
   lp.pairs = reinterpret_cast<unsigned long long *>(ctx->ctl() + CTL_PAIRS);
   for (int k = 0; k < A; ++k) lp.perm[k] = ctx->perm[k];
@@ -1920,17 +1981,10 @@ static int launch_link(dbl_ctx *ctx, int sampler) {
   const size_t ring = (size_t)LINK_STAGES * tile_words(A) * 4 + 128;
   const int mode = ctx->link_mode;  // 0 auto, 1 force generic
   lp.hslots = ctx->hslots; lp.hshift = ctx->hshift;
-  if (mode != 1 && sampler == DBL_PCG_II && ctx->hslots > 0 && A <= LINK_MAX_UNROLL_A &&
-      pcg2_smem_bytes(A, ctx->n_str, ctx->hslots) <= 100 * 1024) {
-    int rc = -1;
-    switch (A) {
-#define DBL_CASE(N) case N: rc = dbl_launch_pcg2_a##N(ctx->n_str, ctx->max_ctas, ctx->stream, lp, &ctx->pcg2_smem_cfg); break;
-      DBL_CASE(1) DBL_CASE(2) DBL_CASE(3) DBL_CASE(4) DBL_CASE(5) DBL_CASE(6) DBL_CASE(7) DBL_CASE(8)
-      DBL_CASE(9) DBL_CASE(10) DBL_CASE(11) DBL_CASE(12) DBL_CASE(13) DBL_CASE(14) DBL_CASE(15) DBL_CASE(16)
-#undef DBL_CASE
-    }
-    if (rc != 0) { ctx->set_error(std::string("k_link_pcg2 launch: ") + cudaGetErrorString((cudaError_t)rc)); return DBL_ERR_CUDA; }
-    return DBL_OK;
+  if (mode != 1 && sampler == DBL_PCG_II && pcg2_kernel_fits(ctx)) {
+    // persistent CTAs: a few per SM, each takes groups of LINK_WARPS records from the work counter until none is left
+    CUDA_TRY(cudaMemsetAsync(lp.work, 0, sizeof(unsigned long long), ctx->stream));
+    return dispatch_pcg2(ctx, std::min(ctx->max_ctas, ctx->pcg2_grid), lp);
   }
   if (mode == 0 && sampler != DBL_PCG_II) {  // pruned scoring through the inverted index
     int rc = ensure_inverted_index(ctx);
@@ -1986,7 +2040,7 @@ static int update_owned(dbl_ctx *ctx, int sampler) {
   const int A = ctx->A, F = ctx->F;
   // (2) links
   std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
-  const bool timed = ctx->pending_events.size() < 256;  // per-launch timing of the first sweeps of a call
+  const bool timed = !ctx->capturing && ctx->pending_events.size() < 256;  // per-launch timing (eager sweeps only)
   if (timed) {
     if (!ctx->event_pool.empty()) { ev = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
     else { CUDA_TRY(cudaEventCreate(&ev.first)); CUDA_TRY(cudaEventCreate(&ev.second)); }
@@ -2072,6 +2126,55 @@ static int check_sweep_args(dbl_ctx *ctx, int sampler, int32_t n_sweeps) {
   return DBL_OK;
 }
 
+// Launch-bound sizes (RLdata-sized problems: a sweep is ~50 tiny kernels) replay one captured sweep instead of
+// enqueueing it again: nothing in a sweep depends on the host, every varying quantity is read from device memory.
+static bool graph_allowed(const dbl_ctx *ctx, int sampler) {
+  if (ctx->graph_mode == 1) return false;
+  // the pruned link update of a SHARDED context reads the owned-entity count back every sweep (sizes a sort)
+  if (ctx->world > 1 && sampler != DBL_PCG_II && ctx->link_mode == 0) return false;
+  if (ctx->graph_mode == 2) return true;
+  return ctx->R + ctx->E <= 400000;
+}
+
+static int run_sweeps(dbl_ctx *ctx, int sampler, int32_t n_sweeps) {
+  int s = 0;
+  if (n_sweeps >= 2 && graph_allowed(ctx, sampler)) {
+    const int key = sampler * 4 + ctx->link_mode;
+    if (!ctx->graph_warm[key]) {  // first sweep of this kind eagerly: allocations and opt-ins happen outside a capture
+      int rc = enqueue_sweep(ctx, sampler);
+      if (rc) return rc;
+      ctx->graph_warm[key] = true;
+      s = 1;
+    }
+    auto it = ctx->graphs.find(key);
+    if (it == ctx->graphs.end() && n_sweeps - s >= 2) {
+      dbl_ctx::SweepGraph g;
+      const int64_t before = ctx->launches;
+      CUDA_TRY(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+      ctx->capturing = true;
+      int rc = enqueue_sweep(ctx, sampler);
+      ctx->capturing = false;
+      cudaError_t e = cudaStreamEndCapture(ctx->stream, &g.graph);
+      g.launches = ctx->launches - before;
+      ctx->launches = before;
+      if (rc) { if (g.graph) cudaGraphDestroy(g.graph); return rc; }
+      if (e != cudaSuccess) { ctx->set_error(std::string("graph capture: ") + cudaGetErrorString(e)); return DBL_ERR_CUDA; }
+      CUDA_TRY(cudaGraphInstantiate(&g.exec, g.graph, 0));
+      it = ctx->graphs.emplace(key, g).first;
+    }
+    if (it != ctx->graphs.end())
+      for (; s < n_sweeps; ++s) {
+        CUDA_TRY(cudaGraphLaunch(it->second.exec, ctx->stream));
+        ctx->launches += it->second.launches;
+      }
+  }
+  for (; s < n_sweeps; ++s) {
+    int rc = enqueue_sweep(ctx, sampler);
+    if (rc) return rc;
+  }
+  return DBL_OK;
+}
+
 extern "C" int dbl_sweep_async(dbl_ctx *ctx, int sampler, int32_t n_sweeps) {
   if (!ctx) return DBL_ERR_INVALID;
   int rc = check_sweep_args(ctx, sampler, n_sweeps);
@@ -2079,10 +2182,12 @@ extern "C" int dbl_sweep_async(dbl_ctx *ctx, int sampler, int32_t n_sweeps) {
   CUDA_TRY(cudaSetDevice(ctx->device));
   if (!ctx->async_open) CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
   ctx->async_open = true;
-  for (int s = 0; s < n_sweeps; ++s) {
-    rc = enqueue_sweep(ctx, sampler);
-    if (rc) return rc;
-  }
+  return run_sweeps(ctx, sampler, n_sweeps);
+}
+
+extern "C" int dbl_set_graph_mode(dbl_ctx *ctx, int mode) {
+  if (!ctx || mode < 0 || mode > 2) return DBL_ERR_INVALID;
+  ctx->graph_mode = mode;
   return DBL_OK;
 }
 
@@ -2222,8 +2327,42 @@ extern "C" int dbl_block_owners(dbl_ctx *ctx, int32_t *owner_out) {
 
 extern "C" int dbl_set_rebalance(dbl_ctx *ctx, int32_t period, double threshold) {
   if (!ctx || period < 0 || !(threshold >= 1.0)) return DBL_ERR_INVALID;
+  ctx->drop_graphs();
   ctx->rebalance_period = period;
   ctx->rebalance_threshold = threshold;
+  return DBL_OK;
+}
+
+// With lazy module loading (the CUDA default) the FIRST launch of a kernel may synchronise the whole context.  Inside a
+// sharded sweep that is fatal when several ranks share one device (the tests do): rank A waits in the exchange barrier
+// for rank B, whose next launch waits for A's barrier kernel to finish.  So every kernel a sweep can launch is loaded
+// here, before the first sharded sweep (and before any graph capture): by attribute query for our own kernels, by
+// running the (idempotent) layout / index builds once for the CUB kernels they use.
+static int preload_kernels(dbl_ctx *ctx) {
+  cudaFuncAttributes fa;
+#define DBL_LOAD(k) CUDA_TRY(cudaFuncGetAttributes(&fa, k))
+  DBL_LOAD(k_theta); DBL_LOAD(k_commit_links); DBL_LOAD(k_values); DBL_LOAD(k_entity_post); DBL_LOAD(k_dist);
+  DBL_LOAD(k_reduce_local); DBL_LOAD(k_finish); DBL_LOAD(k_move_ent); DBL_LOAD(k_move_rec); DBL_LOAD(k_publish_barrier);
+  DBL_LOAD(k_unpack_ent_p2p); DBL_LOAD(k_unpack_rec_p2p); DBL_LOAD(k_reduce_peers); DBL_LOAD(k_lpt);
+  DBL_LOAD(k_link_generic); DBL_LOAD(k_link_match); DBL_LOAD(k_link_pruned); DBL_LOAD(k_state_hash);
+  DBL_LOAD(k_gather_ent); DBL_LOAD(k_gather_rec); DBL_LOAD(k_export_ent); DBL_LOAD(k_export_rec);
+  DBL_LOAD(k_inv_keys); DBL_LOAD(k_inv_value_ptr); DBL_LOAD(k_inv_segments);
+#undef DBL_LOAD
+  if (pcg2_kernel_fits(ctx)) {
+    LinkParams lp;
+    memset(&lp, 0, sizeof(lp));
+    lp.hslots = ctx->hslots; lp.pack_consts = ctx->pack_consts; lp.qtile_pk = ctx->qtile_pk;
+    int rc = dispatch_pcg2(ctx, 0, lp);  // grid 0 = load only
+    if (rc) return rc;
+  }
+  int rc = build_links_csr(ctx);
+  if (rc) return rc;
+  ctx->inv_valid = false;
+  rc = ensure_inverted_index(ctx);
+  if (rc) return rc;
+  rc = relayout(ctx);
+  if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return DBL_OK;
 }
 
@@ -2236,6 +2375,7 @@ extern "C" int dbl_comm_export(dbl_ctx *ctx, void *blob_out) {
   CUDA_TRY(cudaSetDevice(ctx->device));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   comm_close(ctx);
+  ctx->drop_graphs();
   CommDev &c = ctx->comm;
   memset(&c, 0, sizeof(c));
   c.rank = ctx->rank; c.world = ctx->world; c.A = ctx->A; c.nws = ctx->nw + 1;
@@ -2303,6 +2443,8 @@ extern "C" int dbl_comm_import(dbl_ctx *ctx, const void *blobs, int32_t world) {
       ctx->comm.base[r] = static_cast<unsigned char *>(p);
     }
   }
+  ctx->drop_graphs();
+  if (ctx->has_state) { int rc = preload_kernels(ctx); if (rc) return rc; }
   ctx->comm_ready = true;
   return DBL_OK;
 }
@@ -2512,6 +2654,7 @@ extern "C" int dbl_state_hash(dbl_ctx *ctx, uint64_t *hash_out) {
 
 extern "C" int dbl_set_link_mode(dbl_ctx *ctx, int mode) {
   if (!ctx || mode < 0 || mode > 2) return DBL_ERR_INVALID;
+  ctx->drop_graphs();
   ctx->link_mode = mode;
   return DBL_OK;
 }

@@ -104,16 +104,17 @@ void dbl_index::finish() {
   build_hash();
 }
 
-// Per-row perfect hash tables for expSimOf(x, y), y != x (AttributeIndex.scala:183-186): the link kernel
-// answers "is y similar to x, and how much" with one shared-memory probe.  All rows of an attribute share the
-// table size (a power of two <= 256); each row has its own multiplier found by search.
+// Per-row perfect hash tables for expSimOf(x, y) (AttributeIndex.scala:183-186), the row's own value x included: the
+// link kernel answers "is y equal or similar to x, and what is the factor" with one shared-memory probe (the entry of
+// x itself is replaced per record by the exact-match multiplier).  All rows of an attribute share the table size (a
+// power of two <= 256); each row has its own multiplier found by search.
 void dbl_index::build_hash(int min_slots) {
   hsize = 0;
   hshift = 32;
   hmult.clear(); hkeys.clear(); hvals.clear();
   if (is_const) return;
   int maxlen = 0;
-  for (int v = 0; v < V; ++v) maxlen = std::max(maxlen, rowptr[v + 1] - rowptr[v] - 1);
+  for (int v = 0; v < V; ++v) maxlen = std::max(maxlen, rowptr[v + 1] - rowptr[v] + 1);
   int H = std::max(32, min_slots);
   while (H < maxlen) H <<= 1;  // a perfect hash needs H >= row length; the multiplier search below decides the rest
   for (; H <= 256; H <<= 1) {
@@ -131,6 +132,7 @@ void dbl_index::build_hash(int min_slots) {
         const uint32_t m = 2654435761u * (2 * k + 1);
         std::fill(used.begin(), used.end(), 0);
         bool clash = false;
+        used[((uint32_t)v * m) >> shift] = 1;  // the row's own value always has an entry
         for (int p = rowptr[v]; p < rowptr[v + 1] && !clash; ++p) {
           if (col[p] == v) continue;
           const uint32_t s = ((uint32_t)col[p] * m) >> shift;
@@ -140,8 +142,8 @@ void dbl_index::build_hash(int min_slots) {
         if (!clash) { mult[v] = m; found = true; }
       }
       if (!found) { ok = false; break; }
+      keys[(size_t)v * H + (((uint32_t)v * mult[v]) >> shift)] = v;  // value: the diagonal exp sim (1 when absent)
       for (int p = rowptr[v]; p < rowptr[v + 1]; ++p) {
-        if (col[p] == v) continue;
         const uint32_t s = ((uint32_t)col[p] * mult[v]) >> shift;
         keys[(size_t)v * H + s] = col[p];
         vals[(size_t)v * H + s] = expsim[p];

@@ -25,8 +25,16 @@ constexpr int LINK_STAGES = 4;   // tile ring depth (8 measured: no gain)
 constexpr int LINK_MAX_UNROLL_A = 16;
 constexpr unsigned FULL = 0xffffffffu;
 
-// int32 words per tile: A value rows, the f64 row N(e), one row of byte-packed constant attributes (k_link_pcg2)
+// int32 words per tile: A value rows (attribute-major), the f64 row N(e), one row of byte-packed constant attributes
 __host__ __device__ inline size_t tile_words(int A) { return (size_t)A * TE + 3 * TE; }
+// "Quad tiles" (k_link_pcg2): the words a lane needs about ONE candidate sit in groups of four, group-major
+// ([group][slot][4] int32), so that a warp fetches a group with one conflict-free 128-bit load per lane.  Words of an
+// entity: nv values (packed kernels: the NS non-constant values then the byte-packed constants; else all A values in
+// kernel order) padded to a multiple of four; the f64 row N(e) follows the groups (8 contiguous bytes per lane: a
+// 64-bit load of a word pair inside a 16-byte group would cost twice the wavefronts).
+__host__ __device__ constexpr int qtile_nv(int A, int NS, bool packed) { return packed ? NS + 1 : A; }
+__host__ __device__ constexpr int qtile_groups(int nv) { return (nv + 3) / 4; }
+__host__ __device__ constexpr int qtile_words(int nv) { return qtile_groups(nv) * 4 + 2; }  // per entity
 
 struct AttrDev {
   int V, is_const, kmax, hsize;
@@ -48,6 +56,7 @@ enum : int {
   CTL_MOVED_REC = 6,
   CTL_EPOCH = 7,      // barriers passed (peer-to-peer exchange)
   CTL_REPLACED = 8,   // block -> rank placements adopted by the device-side LPT
+  CTL_WORK = 9,       // work counter of the persistent link kernel
   CTL_WORDS = 16
 };
 constexpr long long ST_ZERO_MASS = 1, ST_PEER_TIMEOUT = 2, ST_PEER_ERROR = 4;
@@ -62,6 +71,9 @@ struct LinkParams {
   const double *theta;
   const int *ent_ptr, *tile_ptr, *rec_ptr, *cta_ptr, *ent_sorted, *rec_sorted;
   const int *tiles;
+  const int *qtiles;         // quad tiles (k_link_pcg2)
+  int qtile_pk;              // quad tiles hold the non-constant values + the byte-packed constants (else all A values)
+  unsigned long long *work;  // k_link_pcg2: next group of records to take (persistent CTAs); zeroed before the launch
   int *newlink;
   unsigned long long *status;  // &ctl[CTL_STATUS]
   unsigned long long *pairs;   // &ctl[CTL_PAIRS]
@@ -238,15 +250,12 @@ __device__ __forceinline__ double generic_weight(const RecAttr *ra, int A, bool 
     for (int a = 0; a < A; ++a)
       if (ra[a].kind == 1 && ycol[a * TE] == ra[a].x) c = c * ra[a].rmatch;
     w = N * c;
-    double d = 1.0;  // and so do the exact matches of the non-constant attributes
-    for (int a = 0; a < A; ++a)
-      if (ra[a].kind == 2 && ycol[a * TE] == ra[a].x) d = d * ra[a].rmatch;
-    w = w * d;
-    for (int a = 0; a < A; ++a) {
+    for (int a = 0; a < A; ++a) {  // non-constant attributes: one factor each, equal (multiplier) or similar (exp sim)
       if (ra[a].kind != 2) continue;
       const int yv = ycol[a * TE];
       double e;
-      if (yv != ra[a].x && rec_row_find(ra[a], yv, e)) w = w * e;
+      if (yv == ra[a].x) w = w * ra[a].rmatch;
+      else if (rec_row_find(ra[a], yv, e)) w = w * e;
     }
     for (int a = 0; a < A; ++a)
       if (ra[a].kind == 3) w = w * ra[a].tab[ycol[a * TE]];
@@ -400,14 +409,16 @@ __device__ __forceinline__ void ring_init(const TileRing &rg, int consumers) {
 // producer: one lane streams ntiles tiles from global
 // RELAXED: the consumers are slow (PCG-II): let the producer sleep.  !RELAXED: the consumers drain tiles faster
 // than the producer can be woken (PCG-I): poll.
+// base = tiles this CTA has already streamed through the ring (persistent CTAs): stages and phases continue
 template <bool RELAXED>
-__device__ __forceinline__ void ring_produce(const TileRing &rg, const int *gsrc, int ntiles) {
+__device__ __forceinline__ void ring_produce(const TileRing &rg, const int *gsrc, int ntiles, int base = 0) {
   const unsigned bytes = (unsigned)rg.tw * 4u;
   for (int t = 0; t < ntiles; ++t) {
-    const int s = t % LINK_STAGES;
-    if (t >= LINK_STAGES) {
-      if (RELAXED) mbar_wait_relaxed(&rg.empty[s], ((t / LINK_STAGES) - 1) & 1);
-      else mbar_wait(&rg.empty[s], ((t / LINK_STAGES) - 1) & 1);
+    const int g = base + t;
+    const int s = g % LINK_STAGES;
+    if (g >= LINK_STAGES) {
+      if (RELAXED) mbar_wait_relaxed(&rg.empty[s], ((g / LINK_STAGES) - 1) & 1);
+      else mbar_wait(&rg.empty[s], ((g / LINK_STAGES) - 1) & 1);
     }
     mbar_arrive_expect_tx(&rg.full[s], bytes);
     tma_load_1d(rg.tiles + (size_t)s * rg.tw, gsrc + (size_t)t * rg.tw, bytes, &rg.full[s]);

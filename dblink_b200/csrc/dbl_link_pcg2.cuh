@@ -3,15 +3,19 @@
 // when the hash tables have 32 slots (else the size is a run-time parameter); PK = the constant attributes arrive
 // byte-packed.
 //
-//  * the block's entity table streams through shared memory in TE-entity tiles moved by TMA bulk copies
-//    (cp.async.bulk.shared::cluster.global + mbarrier ring, one producer warp per CTA);
+//  * persistent CTAs: the grid is a few CTAs per SM; each takes the next group of LINK_WARPS records of some block
+//    from a device-side counter until none is left (no empty CTAs on a shard that owns 1/8 of the records, no tail);
+//  * the block's entity table streams through shared memory in TE-entity "quad tiles" moved by TMA bulk copies
+//    (cp.async.bulk.shared::cluster.global + mbarrier ring, one producer warp per CTA); a quad tile keeps the words
+//    of one entity in groups of four, so a lane fetches everything it needs about its candidate with QW/4 128-bit
+//    shared-memory loads (3 for 6 non-constant attributes + packed constants + N) instead of one load per word;
 //  * each consumer warp owns one record; its constants (value ids, hash multipliers) are registers;
-//  * exact matches: the multipliers of the matching constant attributes and of the matching non-constant
-//    attributes are two products, each fetched from a per-record table in shared memory indexed by
-//    the match mask (16 entries for PK, 2^NS entries for NS <= 8);
-//  * similar-but-different values: the sparse similarity row of each non-constant record attribute is a 32-slot
-//    perfect-hash table in shared memory, one key word per bank, so a probe is one conflict-free wavefront; one
-//    warp vote per step decides whether anybody needs the multiply;
+//  * constant attributes: the product of the exact-match multipliers comes from a 16-entry per-record table indexed
+//    by the byte-wise match mask of the packed values (PK), else from per-attribute compares;
+//  * non-constant attributes: ONE probe per (candidate, attribute) of a 32-slot perfect-hash table in shared memory
+//    (one key word per bank = one conflict-free wavefront) that holds the record's similarity row INCLUDING the
+//    record's own value, whose entry carries the exact-match multiplier of protocol 4.1 -- so "equal" and "similar"
+//    are the same look-up and the multiply is skipped warp-wide by one vote per step when nobody hit (the usual case);
 //  * lane l scores candidate 32*step + l; lane sums / chunk totals / draw as in DESIGN.md section 4.
 #pragma once
 #include "dbl_link.cuh"
@@ -20,7 +24,7 @@
 // for every attribute of the model; 32 = one key per bank = conflict-free probes).
 __device__ __host__ __forceinline__ int pcg2_tab_bytes(int H) { return H * 12; }
 
-// w *= r when y == x (shapes without a product table; ptxas turns any predicated form into DMUL + 2 FSEL)
+// w *= r when y == x (shapes without the packed-constant table; ptxas turns any predicated form into DMUL + 2 FSEL)
 __device__ __forceinline__ void mul_if_eq(double &w, int y, int x, double r) {
   if (y == x) w = w * r;
 }
@@ -34,23 +38,6 @@ struct Pcg2Rec {
   unsigned xpack;                // PK: the record's constant-attribute values, one byte each (0xFF = cannot match)
 };
 
-// up to 8 non-constant attributes: the product of the exact-match multipliers comes from a per-record table indexed
-// by the match mask (2^NS doubles per warp in shared memory)
-__host__ __device__ constexpr bool pcg2_dtab(int NS) { return NS >= 1 && NS <= 8; }
-// Position (in entries) of attribute q's bit in that table.  Not 1 << q: the weights are chosen so that every subset
-// sum is distinct AND the single-attribute entries (by far the most used after entry 0) fall in different
-// shared-memory banks from entry 0 and from each other (position mod 16 all distinct and non-zero); with powers of
-// two, attributes 4 and 5 would sit 128 and 256 bytes from entry 0, i.e. in its banks.
-__host__ __device__ constexpr int pcg2_dtab_weight(int q) {
-  constexpr int w[8] = {1, 2, 4, 8, 19, 38, 75, 149};
-  return w[q];
-}
-__host__ __device__ constexpr int pcg2_dtab_entries(int NS) {
-  int n = 1;
-  for (int q = 0; q < NS; ++q) n += pcg2_dtab_weight(q);
-  return pcg2_dtab(NS) ? n : 0;
-}
-
 // PK kernels: index into the record's table of constant-attribute products from the byte-packed values of a
 // candidate: bit k of the index = (byte k of ypack == byte k of xpack)
 __device__ __forceinline__ unsigned pcg2_const_index(unsigned ypack, unsigned xpack) {
@@ -60,43 +47,63 @@ __device__ __forceinline__ unsigned pcg2_const_index(unsigned ypack, unsigned xp
   return (eq * 0x01020408u) >> 24;                            // gathers bits 0, 8, 16, 24 into bits 0..3
 }
 
-// CONVERGED: every lane of the warp executes the call (main loop), so the rare similar-value multiply is skipped
-// warp-wide with a vote; pass 2 calls it under divergence and must not vote.
-// PK: the A - NS constant attributes (1..4 of them, vocabularies <= 255) travel as one byte-packed word per
-// candidate (ypack) and their product comes from the record's 16-entry table ctab; otherwise y[0..A-NS) are used.
+// one candidate out of a quad tile: values in kernel order (PK: only the non-constant ones + the packed word), N
+template <int A, int NS, bool PK>
+struct Pcg2Cand {
+  int y[A];
+  unsigned ypack;
+  double N;
+};
+template <int A, int NS, bool PK>
+__device__ __forceinline__ void pcg2_load(Pcg2Cand<A, NS, PK> &c, const int *tile, int slot) {
+  constexpr int NV = qtile_nv(A, NS, PK), NG = qtile_groups(NV);
+  int v[NG * 4];
+  const int4 *q = reinterpret_cast<const int4 *>(tile);
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    const int4 t = q[g * TE + slot];
+    v[4 * g] = t.x; v[4 * g + 1] = t.y; v[4 * g + 2] = t.z; v[4 * g + 3] = t.w;
+  }
+  if constexpr (PK) {
+#pragma unroll
+    for (int q2 = 0; q2 < NS; ++q2) c.y[A - NS + q2] = v[q2];
+    c.ypack = (unsigned)v[NS];
+  } else {
+#pragma unroll
+    for (int k = 0; k < A; ++k) c.y[k] = v[k];
+    c.ypack = 0u;
+  }
+  c.N = reinterpret_cast<const double *>(tile + NG * 4 * TE)[slot];
+}
+
+// With skewed (Zipf-like) value frequencies some lane of the warp finds an equal or similar value on almost every
+// step (96 % at BASELINE's 1M configuration), so a warp-wide vote that skips the multiplies does not pay: the
+// multiplies are predicated per lane and the compiler is free to overlap them with the next step's loads.
+// DBL_PCG2_VOTE=1 brings the vote back (CONVERGED = every lane of the warp executes the call, i.e. the main loop).
+#ifndef DBL_PCG2_VOTE
+#define DBL_PCG2_VOTE 0
+#endif
 template <int A, int NS, int HC, bool CONVERGED, bool PK>
 __device__ __forceinline__ double pcg2_weight(const Pcg2Rec<A, NS> &rc, const LinkParams &p, const char *tab,
-                                              const double *ctab, const double *dtab, const int *y, unsigned ypack,
-                                              double N) {
+                                              const double *ctab, const Pcg2Cand<A, NS, PK> &cd) {
   const int hslots = HC ? HC : p.hslots;
   const int hshift = HC ? 27 : p.hshift;
   const int tabb = pcg2_tab_bytes(hslots);
-  double w = N;
+  const int *y = cd.y;
+  double w = cd.N;
   if constexpr (NS < A) {  // protocol 4.1: the constant attributes form their own product c; w = N * c
     double c = 1.0;
     if constexpr (PK) {
-      c = ctab[pcg2_const_index(ypack, rc.xpack)];
+      c = ctab[pcg2_const_index(cd.ypack, rc.xpack)];
     } else {
 #pragma unroll
       for (int k = 0; k < A - NS; ++k) mul_if_eq(c, y[k], rc.x[k], rc.rm[k]);
     }
     w = w * c;
   }
-  if constexpr (NS >= 1) {  // protocol 4.1: so do the exact matches of the non-constant attributes (product d)
-    double d = 1.0;
-    if constexpr (pcg2_dtab(NS)) {
-      unsigned di = 0;  // byte offset into the table: bit q of the index = attribute q matches
-#pragma unroll
-      for (int q = 0; q < NS; ++q) di += (y[A - NS + q] == rc.x[A - NS + q]) ? 8u * pcg2_dtab_weight(q) : 0u;
-      d = *reinterpret_cast<const double *>(reinterpret_cast<const char *>(dtab) + di);
-    } else {
-#pragma unroll
-      for (int k = A - NS; k < A; ++k) mul_if_eq(d, y[k], rc.x[k], rc.rm[k]);
-    }
-    w = w * d;
-  }
-  if (CONVERGED) {
-    // probe all NS tables first (no control flow), then ONE vote: the multiply by a similarity is rare
+  // protocol 4.1: non-constant attributes in kernel order, each contributes at most one factor: the exact-match
+  // multiplier when y == x, exp(similarity) when y is similar to x -- both sit in the record's hash table
+  if (CONVERGED && DBL_PCG2_VOTE) {
     bool hit[NS > 0 ? NS : 1];
     bool any = false;
 #pragma unroll
@@ -132,16 +139,18 @@ __device__ __forceinline__ double pcg2_weight(const Pcg2Rec<A, NS> &rc, const Li
   return w;
 }
 
+#ifndef DBL_PCG2_CTAS_PER_SM
+#define DBL_PCG2_CTAS_PER_SM 3
+#endif
+
 template <int A, int NS, int HC, bool PK>
-__global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkParams p) {
+__global__ void __launch_bounds__((LINK_WARPS + 1) * 32, DBL_PCG2_CTAS_PER_SM) k_link_pcg2(LinkParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const int cta = blockIdx.x;
-  if (sweep_dead(p.ctl) || cta >= p.cta_ptr[p.P]) return;
-  const int b = find_block(p, cta);
+  __shared__ int s_cta;
+  if (sweep_dead(p.ctl)) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = p.ent_ptr[b + 1] - p.ent_ptr[b];
-  const int ntiles = p.tile_ptr[b + 1] - p.tile_ptr[b];
-  constexpr int TW = A * TE + 3 * TE;  // tile_words(A)
+  constexpr int NV = qtile_nv(A, NS, PK);
+  constexpr int TW = qtile_words(NV) * TE;
   constexpr int NC = A - NS;
   TileRing rg;
   rg.tiles = reinterpret_cast<int *>(smem);
@@ -154,180 +163,166 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, 2) k_link_pcg2(LinkPara
   double *ctab = reinterpret_cast<double *>(reinterpret_cast<char *>(smem) + (size_t)LINK_STAGES * TW * 4 + 128 +
                                            (size_t)LINK_WARPS * (NS > 0 ? NS : 1) * pcg2_tab_bytes(HC ? HC : p.hslots)) +
                  warp * 16;  // PK: products of the matching constant attributes, by match mask
-  double *dtab = ctab + (LINK_WARPS - warp) * 16 + warp * pcg2_dtab_entries(NS);  // same for the others
-  const int *gtiles = p.tiles + (size_t)p.tile_ptr[b] * TW;
   ring_init(rg, LINK_WARPS);
+  const int total_ctas = p.cta_ptr[p.P];
+  int tbase = 0;  // tiles this CTA has streamed so far: stage and phase of the ring continue across work items
 
-  if (warp == LINK_WARPS) {  // producer warp
-    if (lane == 0) ring_produce<true>(rg, gtiles, ntiles);
-    return;
-  }
-  const int ridx = p.rec_ptr[b] + (cta - p.cta_ptr[b]) * LINK_WARPS + warp;
-  const bool active = ridx < p.rec_ptr[b + 1];
-  const int r = active ? p.rec_sorted[ridx] : -1;
+  for (;;) {
+    if (threadIdx.x == 0) s_cta = (int)atomicAdd(p.work, 1ull);
+    __syncthreads();
+    const int cta = s_cta;
+    __syncthreads();
+    if (cta >= total_ctas) break;
+    const int b = find_block(p, cta);
+    const int n = p.ent_ptr[b + 1] - p.ent_ptr[b];
+    const int ntiles = p.tile_ptr[b + 1] - p.tile_ptr[b];
+    const int *gtiles = p.qtiles + (size_t)p.tile_ptr[b] * TW;
 
-  // ---- per-record constants: lane k prepares kernel-order attribute k, then everything is broadcast
-  Pcg2Rec<A, NS> rc;
-  {
-    int xv = -1;
-    double rmv = 1.0;
-    unsigned hmv = 0;
-    bool is_m = false;
-    if (active && lane < A) {
-      const int a = p.perm[lane];
-      const AttrDev &at = p.attrs[a];
-      xv = p.x[(int64_t)r * A + a];
-      if (xv < 0) {
-        is_m = !at.is_const;
-      } else {
-        const double th = p.theta[a * p.F + p.file[r]];
-        double d = th * at.phi[xv];
-        if (at.is_const) {
-          rmv = 1.0 + (1.0 - th) / d;
+    if (warp == LINK_WARPS) {  // producer warp
+      if (lane == 0) ring_produce<true>(rg, gtiles, ntiles, tbase);
+      tbase += ntiles;
+      continue;
+    }
+    const int ridx = p.rec_ptr[b] + (cta - p.cta_ptr[b]) * LINK_WARPS + warp;
+    const bool active = ridx < p.rec_ptr[b + 1];
+    const int r = active ? p.rec_sorted[ridx] : -1;
+
+    // ---- per-record constants: lane k prepares kernel-order attribute k, then everything is broadcast
+    Pcg2Rec<A, NS> rc;
+    {
+      int xv = -1;
+      double rmv = 1.0;
+      unsigned hmv = 0;
+      bool is_m = false;
+      if (active && lane < A) {
+        const int a = p.perm[lane];
+        const AttrDev &at = p.attrs[a];
+        xv = p.x[(int64_t)r * A + a];
+        if (xv < 0) {
+          is_m = !at.is_const;
         } else {
-          d = d * at.norm[xv];
-          double ediag = 1.0;
-          row_find(at, xv, xv, ediag);
-          rmv = ediag + (1.0 - th) / d;
-          hmv = at.hmult[xv];
+          const double th = p.theta[a * p.F + p.file[r]];
+          double d = th * at.phi[xv];
+          if (at.is_const) {
+            rmv = 1.0 + (1.0 - th) / d;
+          } else {
+            d = d * at.norm[xv];
+            double ediag = 1.0;
+            row_find(at, xv, xv, ediag);
+            rmv = ediag + (1.0 - th) / d;
+            hmv = at.hmult[xv];
+          }
         }
       }
-    }
-    rmv = (rmv - 1.0) + 1.0;  // protocol: the multiplier is defined through (r - 1) (identity below ~2^53)
-    rc.mmask = __ballot_sync(FULL, is_m);
+      rmv = (rmv - 1.0) + 1.0;  // protocol: the multiplier is defined through (r - 1) (identity below ~2^53)
+      rc.mmask = __ballot_sync(FULL, is_m);
 #pragma unroll
-    for (int k = 0; k < A; ++k) {
-      rc.x[k] = __shfl_sync(FULL, xv, k);
-      rc.rm[k] = shfl_d(rmv, k);
-    }
-#pragma unroll
-    for (int q = 0; q < NS; ++q) rc.hm[q] = __shfl_sync(FULL, hmv, A - NS + q);
-    // hash tables of the record's similarity rows -> shared memory (all-empty table when the value is missing)
-#pragma unroll
-    for (int q = 0; q < NS; ++q) {
-      const AttrDev &at = p.attrs[p.perm[A - NS + q]];
-      const int H = HC ? HC : p.hslots;
-      int *kd = reinterpret_cast<int *>(tab + q * pcg2_tab_bytes(H));
-      double *vd = reinterpret_cast<double *>(tab + q * pcg2_tab_bytes(H) + H * 4);
-      const int xq = rc.x[A - NS + q];
-      for (int i = lane; i < H; i += 32) {
-        kd[i] = (xq >= 0) ? at.hkeys[(size_t)xq * H + i] : -1;
-        vd[i] = (xq >= 0) ? at.hvals[(size_t)xq * H + i] : 1.0;
+      for (int k = 0; k < A; ++k) {
+        rc.x[k] = __shfl_sync(FULL, xv, k);
+        rc.rm[k] = shfl_d(rmv, k);
       }
-    }
-    rc.xpack = 0xFFFFFFFFu;
-    if constexpr (PK) {
-      static_assert(!PK || (NC >= 1 && NC <= 4), "PK packs 1..4 constant attributes");
 #pragma unroll
-      for (int k = 0; k < NC; ++k)
-        rc.xpack = (rc.xpack & ~(0xFFu << (8 * k))) | ((unsigned)(rc.x[k] < 0 ? 0xFF : rc.x[k]) << (8 * k));
-      if (lane < 16) {
-        double c = 1.0;
+      for (int q = 0; q < NS; ++q) rc.hm[q] = __shfl_sync(FULL, hmv, A - NS + q);
+      // hash tables of the record's similarity rows -> shared memory (all-empty table when the value is missing);
+      // the entry of the record's own value gets the exact-match multiplier (it depends on theta of the record's file)
+      const int H = HC ? HC : p.hslots;
+      const int hshift = HC ? 27 : p.hshift;
+#pragma unroll
+      for (int q = 0; q < NS; ++q) {
+        const AttrDev &at = p.attrs[p.perm[A - NS + q]];
+        int *kd = reinterpret_cast<int *>(tab + q * pcg2_tab_bytes(H));
+        double *vd = reinterpret_cast<double *>(tab + q * pcg2_tab_bytes(H) + H * 4);
+        const int xq = rc.x[A - NS + q];
+        const unsigned own = (xq >= 0) ? (((unsigned)xq * rc.hm[q]) >> hshift) : 0xFFFFFFFFu;
+        for (int i = lane; i < H; i += 32) {
+          kd[i] = (xq >= 0) ? at.hkeys[(size_t)xq * H + i] : -1;
+          vd[i] = ((unsigned)i == own) ? rc.rm[A - NS + q] : ((xq >= 0) ? at.hvals[(size_t)xq * H + i] : 1.0);
+        }
+      }
+      rc.xpack = 0xFFFFFFFFu;
+      if constexpr (PK) {
+        static_assert(!PK || (NC >= 1 && NC <= 4), "PK packs 1..4 constant attributes");
 #pragma unroll
         for (int k = 0; k < NC; ++k)
-          if ((lane >> k) & 1) c = c * rc.rm[k];
-        ctab[lane] = c;
-      }
-    }
-    if constexpr (pcg2_dtab(NS)) {
-      for (int idx = lane; idx < (1 << NS); idx += 32) {  // idx = match mask; stored at its weighted position
-        double d = 1.0;
-        int pos = 0;
+          rc.xpack = (rc.xpack & ~(0xFFu << (8 * k))) | ((unsigned)(rc.x[k] < 0 ? 0xFF : rc.x[k]) << (8 * k));
+        if (lane < 16) {
+          double c = 1.0;
 #pragma unroll
-        for (int q = 0; q < NS; ++q)
-          if ((idx >> q) & 1) { d = d * rc.rm[NC + q]; pos += pcg2_dtab_weight(q); }
-        dtab[pos] = d;
+          for (int k = 0; k < NC; ++k)
+            if ((lane >> k) & 1) c = c * rc.rm[k];
+          ctab[lane] = c;
+        }
       }
+      __syncwarp();
     }
-    __syncwarp();
+
+    const int nsteps = ntiles * (TE / 32);          // steps beyond the last candidate add zeros
+    const int tpc = max(1, (ntiles + 31) >> 5);     // a chunk is a whole number of tiles
+    const int spc = (TE / 32) * tpc;
+    const int nchunks = (nsteps + spc - 1) / spc;
+
+    // ---- pass 1 over the TMA-staged tiles
+    double run = 0.0, Q = 0.0, acc = 0.0;
+    int chunk = 0, tile_in_chunk = 0;
+    for (int t = 0; t < ntiles; ++t) {
+      const int g = tbase + t;
+      const int s = g % LINK_STAGES;
+      mbar_wait(&rg.full[s], (g / LINK_STAGES) & 1);
+      if (active) {
+        const int *tile = rg.tiles + (size_t)s * TW;
+#pragma unroll
+        for (int q = 0; q < TE / 32; ++q) {
+          Pcg2Cand<A, NS, PK> cd;
+          pcg2_load<A, NS, PK>(cd, tile, q * 32 + lane);
+          acc = acc + pcg2_weight<A, NS, HC, true, PK>(rc, p, tab, ctab, cd);
+        }
+        if (++tile_in_chunk == tpc || t + 1 == ntiles) {
+          run = run + butterfly_sum(acc);
+          if (lane == chunk) Q = run;
+          ++chunk;
+          acc = 0.0;
+          tile_in_chunk = 0;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&rg.empty[s]);
+    }
+    tbase += ntiles;
+    if (!active) continue;
+    if (!(run > 0.0) || isinf(run)) { fail_link(p, lane, r); continue; }
+
+    // ---- pass 2 from the L2-resident copy of the tiles
+    auto wf = [&](int j) -> double {
+      if (j >= n) return 0.0;
+      Pcg2Cand<A, NS, PK> cd;
+      pcg2_load<A, NS, PK>(cd, gtiles + (size_t)(j / TE) * TW, j % TE);
+      return pcg2_weight<A, NS, HC, false, PK>(rc, p, tab, ctab, cd);
+    };
+    const U2 u = uniform2(p.seed, PH_LINK, link_iter(p), (uint32_t)r, 0u);
+    const int j = finish_draw(lane, n, nsteps, spc, nchunks, Q, run, u.u0, wf);
+    store_link(p, lane, r, b, n, j);
   }
-
-  const int nsteps = ntiles * (TE / 32);          // steps beyond the last candidate add zeros
-  const int tpc = max(1, (ntiles + 31) >> 5);     // a chunk is a whole number of tiles
-  const int spc = (TE / 32) * tpc;
-  const int nchunks = (nsteps + spc - 1) / spc;
-
-  // ---- pass 1 over the TMA-staged tiles
-  double run = 0.0, Q = 0.0, acc = 0.0;
-  int chunk = 0, tile_in_chunk = 0;
-#ifdef DBL_EXP_WAITCLK
-  long long wclk_ = 0;
-  const long long cstart_ = clock64();
-#endif
-  for (int t = 0; t < ntiles; ++t) {
-    const int s = t % LINK_STAGES;
-#ifdef DBL_EXP_WAITCLK
-    const long long c0_ = clock64();
-#endif
-    mbar_wait(&rg.full[s], (t / LINK_STAGES) & 1);
-#ifdef DBL_EXP_WAITCLK
-    wclk_ += clock64() - c0_;
-#endif
-    if (active) {
-      const int *tile = rg.tiles + (size_t)s * TW;
-      const double *tileN = reinterpret_cast<const double *>(tile + A * TE);
-#pragma unroll
-      for (int q = 0; q < TE / 32; ++q) {
-        const int slot = q * 32 + lane;
-        int y[A];
-#pragma unroll
-        for (int k = PK ? NC : 0; k < A; ++k) y[k] = tile[k * TE + slot];
-        const unsigned ypack = PK ? (unsigned)tile[(A + 2) * TE + slot] : 0u;
-        acc = acc + pcg2_weight<A, NS, HC, true, PK>(rc, p, tab, ctab, dtab, y, ypack, tileN[slot]);
-      }
-      if (++tile_in_chunk == tpc || t + 1 == ntiles) {
-        run = run + butterfly_sum(acc);
-        if (lane == chunk) Q = run;
-        ++chunk;
-        acc = 0.0;
-        tile_in_chunk = 0;
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&rg.empty[s]);
-  }
-#ifdef DBL_EXP_WAITCLK
-  const long long cloop_ = clock64() - cstart_;
-#endif
-  if (!active) return;
-  if (!(run > 0.0) || isinf(run)) { fail_link(p, lane, r); return; }
-
-  // ---- pass 2 from the L2-resident copy of the tiles
-  auto wf = [&](int j) -> double {
-    if (j >= n) return 0.0;
-    const int *tile = gtiles + (size_t)(j / TE) * TW;
-    const int slot = j % TE;
-    int y[A];
-#pragma unroll
-    for (int k = PK ? NC : 0; k < A; ++k) y[k] = tile[k * TE + slot];
-    const unsigned ypack = PK ? (unsigned)tile[(A + 2) * TE + slot] : 0u;
-    return pcg2_weight<A, NS, HC, false, PK>(rc, p, tab, ctab, dtab, y, ypack,
-                                             reinterpret_cast<const double *>(tile + A * TE)[slot]);
-  };
-  const U2 u = uniform2(p.seed, PH_LINK, link_iter(p), (uint32_t)r, 0u);
-  const int j = finish_draw(lane, n, nsteps, spc, nchunks, Q, run, u.u0, wf);
-  store_link(p, lane, r, b, n, j);
-#ifdef DBL_EXP_WAITCLK
-  if (lane == 0 && (cta % 997) == 0 && link_iter(p) == 2)
-    printf("cta %d warp %d ntiles %d loop %lld wait %lld total %lld\n", cta, warp, ntiles, cloop_, wclk_, clock64() - cstart_);
-#endif
 }
 
-inline size_t pcg2_smem_bytes(int A, int NS, int H) {
-  return (size_t)LINK_STAGES * tile_words(A) * 4 + 128 + (size_t)LINK_WARPS * (NS > 0 ? NS : 1) * pcg2_tab_bytes(H) +
-         (size_t)LINK_WARPS * (16 + pcg2_dtab_entries(NS)) * sizeof(double);
+inline size_t pcg2_smem_bytes(int A, int NS, int H, bool PK) {
+  return (size_t)LINK_STAGES * qtile_words(qtile_nv(A, NS, PK)) * TE * 4 + 128 +
+         (size_t)LINK_WARPS * (NS > 0 ? NS : 1) * pcg2_tab_bytes(H) + (size_t)LINK_WARPS * 16 * sizeof(double);
 }
 
 // launch k_link_pcg2<A, NS, HC> for a runtime NS in [0, A]; HC = 32 (compile-time table size) when the model's
 // tables have 32 slots, else 0 (size read from the parameters); returns cudaError_t as int
 template <int A, int NS, int HC, bool PK>
 int pcg2_launch_one(int grid, cudaStream_t stream, const LinkParams &lp, size_t *configured) {
-  const size_t smem = pcg2_smem_bytes(A, NS, lp.hslots);
+  const size_t smem = pcg2_smem_bytes(A, NS, lp.hslots, PK);
   // the opt-in is per device: the cache belongs to the context (one model shape = one instantiation per context)
   if (*configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(k_link_pcg2<A, NS, HC, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     *configured = smem;
+  }
+  if (grid <= 0) {  // load the kernel without running it (see preload_kernels in dbl_engine.cu)
+    cudaFuncAttributes fa;
+    return (int)cudaFuncGetAttributes(&fa, k_link_pcg2<A, NS, HC, PK>);
   }
   k_link_pcg2<A, NS, HC, PK><<<grid, (LINK_WARPS + 1) * 32, smem, stream>>>(lp);
   return (int)cudaGetLastError();
@@ -337,9 +332,9 @@ template <int A, int NS>
 struct Pcg2Launch {
   static int go(int ns, int grid, cudaStream_t stream, const LinkParams &lp, size_t *cfg) {
     if (ns == NS) {
-      // byte-packed constant attributes: 1..4 of them, every vocabulary <= 255 (lp.pack_consts), 32-slot tables
+      // byte-packed constant attributes: 1..4 of them, every vocabulary <= 255, 32-slot tables (lp.qtile_pk)
       if constexpr (A - NS >= 1 && A - NS <= 4) {
-        if (lp.pack_consts && lp.hslots == 32) return pcg2_launch_one<A, NS, 32, true>(grid, stream, lp, cfg);
+        if (lp.qtile_pk) return pcg2_launch_one<A, NS, 32, true>(grid, stream, lp, cfg);
       }
       return lp.hslots == 32 ? pcg2_launch_one<A, NS, 32, false>(grid, stream, lp, cfg)
                              : pcg2_launch_one<A, NS, 0, false>(grid, stream, lp, cfg);

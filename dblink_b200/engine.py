@@ -391,6 +391,10 @@ class GibbsEngine:
         """0 = automatic kernel choice, 1 = force the generic fallback link kernel (same draws)."""
         _check(_lib.load().dbl_set_link_mode(self._h, int(mode)), "set_link_mode", self._h)
 
+    def set_graph_mode(self, mode):
+        """0 = automatic (CUDA graph replay of a sweep for launch-bound sizes), 1 = never, 2 = whenever possible."""
+        _check(_lib.load().dbl_set_graph_mode(self._h, int(mode)), "set_graph_mode", self._h)
+
     def last_sweep_ms(self):
         return _lib.load().dbl_last_sweep_ms(self._h)
 

@@ -242,6 +242,10 @@ int64_t dbl_kernel_launches(const dbl_ctx *);
  * per-sweep inverted index), 1 = always the generic fallback kernel, 2 = dense TMA kernels for every sampler.
  * All produce identical draws; this exists so tests can cover every kernel. */
 int dbl_set_link_mode(dbl_ctx *, int mode);
+/* How dbl_sweep / dbl_sweep_async enqueue several sweeps: 0 = automatic (problems small enough to be bound by kernel
+ * launches replay a captured CUDA graph of one sweep), 1 = every sweep enqueued kernel by kernel (and the link kernel
+ * timed per launch, dbl_link_kernel_ms), 2 = graphs whenever possible.  Same chain either way. */
+int dbl_set_graph_mode(dbl_ctx *, int mode);
 /* CUDA-event time (ms) of the last dbl_sweep call, first operation to last operation on the context's stream */
 double dbl_last_sweep_ms(const dbl_ctx *);
 /* CUDA-event time (ms) spent in the link-scoring kernel since the last call; resets the accumulator */

@@ -973,13 +973,11 @@ static double protocol_weight(const orc_state *s, int sampler, const rec_attr_t 
     for (int a = 0; a < A; ++a)
       if (ra[a].kind == 1 && ye[a] == ra[a].x) c = c * ra[a].rmatch;
     w = nprod * c;
-    double d = 1.0; /* and so do the exact matches of the non-constant attributes */
-    for (int a = 0; a < A; ++a)
-      if (ra[a].kind == 2 && ye[a] == ra[a].x) d = d * ra[a].rmatch;
-    w = w * d;
-    for (int a = 0; a < A; ++a) { /* (ii) similar but different values */
+    for (int a = 0; a < A; ++a) { /* (ii) non-constant attributes, one factor each: equal, or similar but different */
       double e;
-      if (ra[a].kind == 2 && ye[a] != ra[a].x && row_find(m->idx[a], ra[a].x, ye[a], &e)) w = w * e;
+      if (ra[a].kind != 2) continue;
+      if (ye[a] == ra[a].x) w = w * ra[a].rmatch;
+      else if (row_find(m->idx[a], ra[a].x, ye[a], &e)) w = w * e;
     }
     for (int a = 0; a < A; ++a) /* (iii) missing record attributes */
       if (ra[a].kind == 3) w = w * m->idx[a]->invnorm[ye[a]];
@@ -1223,12 +1221,10 @@ static double protocol_weight_pcg2_dense(const orc_model *m, const rec_attr_t *r
   double c = 1.0;
   for (int i = 0; i < kl->n1; ++i) { const int a = kl->a1[i]; if (ye[a] == ra[a].x) c = c * ra[a].rmatch; }
   double w = nprod * c;
-  double d = 1.0;
-  for (int i = 0; i < kl->n2; ++i) { const int a = kl->a2[i]; if (ye[a] == ra[a].x) d = d * ra[a].rmatch; }
-  w = w * d;
   for (int i = 0; i < kl->n2; ++i) {
     const int a = kl->a2[i];
-    if (ye[a] != ra[a].x) {
+    if (ye[a] == ra[a].x) w = w * ra[a].rmatch;
+    else {
       const double e = dense[a][ye[a]];
       if (e != 0.0) w = w * e;
     }

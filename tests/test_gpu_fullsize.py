@@ -69,7 +69,10 @@ def test_full_size_properties(big, sampler):
         if it == 0:
             # a record can only link to an entity of the block it was in (GU:137, 192-198)
             assert np.array_equal(blk_before[da["link"]], blk_before[link_before])
-    assert sa["pairs_scored"] == sb["pairs_scored"] > 3e10
+    if sampler == "PCG-II":
+        assert sa["pairs_scored"] == sb["pairs_scored"] > 3e10  # dense scoring: every entity of the block, every record
+    else:  # the pruned kernel reports the postings it walked, the generic one every pair
+        assert sb["pairs_scored"] > 3e10 and 0 < sa["pairs_scored"] < sb["pairs_scored"] / 100
     # determinism: a fresh engine replays the same chain (here through the dense TMA kernels, mode 2)
     c = make()
     c.set_link_mode(2)

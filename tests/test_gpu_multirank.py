@@ -174,3 +174,50 @@ def test_zero_mass_abandons_the_sweep(oracle, sampler):
     for k in ("theta", "link", "y", "z"):
         np.testing.assert_array_equal(d[k], getattr(st, k), err_msg=k)
     eng.close()
+
+
+@pytest.mark.parametrize("sampler", ["PCG-II", "PCG-I", "Gibbs", "Gibbs-Sequential"])
+def test_graph_replay_gives_the_same_chain(oracle, sampler):
+    """several sweeps per call replay ONE captured CUDA graph of a sweep (every per-sweep quantity is read from device
+    memory): same chain as kernel-by-kernel launches, for every link mode"""
+    from helpers import product_setup
+
+    g = synth_problem(seed=15, R=800, n_files=2)
+    m, st, tree, ox, ofile = oracle_setup(oracle, g, 31, 2, (2, 3))
+    engs = []
+    for graph_mode, link_mode in ((2, 0), (1, 0), (2, 2), (2, 1)):
+        eng, rc, x, file = product_setup(g, 31, 2, (2, 3))
+        eng.set_graph_mode(graph_mode)
+        eng.set_link_mode(link_mode)
+        engs.append(eng)
+    for n in (5, 1, 7):  # first call: 1 eager + capture + replays; later calls replay only
+        st.sweep(oracle.SAMPLERS[sampler], n)
+        for eng in engs:
+            eng.sweep(sampler, n)
+            d = eng.download_state()
+            for k in ("theta", "link", "y", "z", "block"):
+                np.testing.assert_array_equal(d[k], getattr(st, k), err_msg=k)
+            s, os_ = eng.summary(), st.summary()
+            assert s["iteration"] == os_["iteration"] and s["num_isolates"] == os_["num_isolates"]
+            np.testing.assert_array_equal(s["agg_dist"], os_["agg_dist"])
+    # a new state of the same shape keeps the graphs; a new partitioner drops them
+    d = engs[0].download_state()
+    engs[0].upload_state(x, file, d["z"], d["link"], d["y"], d["theta"], iteration=engs[0].iteration)
+    engs[0].sweep(sampler, 4)
+    st.sweep(oracle.SAMPLERS[sampler], 4)
+    np.testing.assert_array_equal(engs[0].download_state()["link"], st.link)
+    for eng in engs:
+        eng.close()
+
+
+def test_graph_replay_on_a_sharded_chain(oracle):
+    g = synth_problem(seed=5, R=1500, n_files=2)
+    sh, rc, x, file = make(2, g, 99, 3, (2, 3))
+    for e in sh.engines:
+        e.set_graph_mode(2)
+    m, st, tree, ox, ofile = oracle_setup(oracle, g, 99, 3, (2, 3))
+    for n in (6, 3):
+        sh.sweep("PCG-II", n)
+        st.sweep(oracle.SAMPLERS["PCG-II"], n)
+        assert_same(sh, st)
+    sh.close()
