@@ -107,6 +107,8 @@ SIGNATURES = {
     "dbl_owned_masks": (C.c_int, [vp, u8p, u8p]),
     "dbl_kernel_launches": (C.c_int64, [vp]),
     "dbl_set_link_mode": (C.c_int, [vp, C.c_int]),
+    "dbl_link_kernel": (C.c_int, [vp, C.c_int]),
+    "dbl_index_hash_slots": (C.c_int32, [vp]),
     "dbl_set_graph_mode": (C.c_int, [vp, C.c_int]),
     "dbl_last_sweep_ms": (C.c_double, [vp]),
     "dbl_link_kernel_ms": (C.c_double, [vp, i64p]),

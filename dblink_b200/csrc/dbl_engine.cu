@@ -2652,6 +2652,19 @@ extern "C" int dbl_state_hash(dbl_ctx *ctx, uint64_t *hash_out) {
   return DBL_OK;
 }
 
+// which link kernel a sweep with this sampler launches: 0 k_link_generic, 1 k_link_match, 2 k_link_pruned,
+// 3 k_link_pcg2 (+4 when the constants are byte-packed, +8 when the hash tables have the compile-time 32 slots)
+extern "C" int dbl_link_kernel(const dbl_ctx *ctx, int sampler) {
+  if (!ctx || sampler < 0 || sampler > 3) return DBL_ERR_INVALID;
+  const int mode = ctx->link_mode;
+  if (mode != 1 && sampler == DBL_PCG_II && pcg2_kernel_fits(ctx))
+    return 3 + (ctx->qtile_pk ? 4 : 0) + (ctx->hslots == 32 ? 8 : 0);
+  if (mode == 0 && sampler != DBL_PCG_II) return 2;
+  const size_t ring = (size_t)LINK_STAGES * tile_words(ctx->A) * 4 + 128;
+  if (mode != 1 && sampler != DBL_PCG_II && ring <= 160 * 1024) return 1;
+  return 0;
+}
+
 extern "C" int dbl_set_link_mode(dbl_ctx *ctx, int mode) {
   if (!ctx || mode < 0 || mode > 2) return DBL_ERR_INVALID;
   ctx->drop_graphs();

@@ -438,3 +438,5 @@ extern "C" int dbl_draw_theta(int32_t A, int32_t F, const double *alpha, const d
   host_draw_theta(A, F, alpha, beta, seed, agg_dist, file_sizes, (uint32_t)iteration, theta_out);
   return DBL_OK;
 }
+
+extern "C" int32_t dbl_index_hash_slots(const dbl_index *ix) { return ix ? ix->hsize : 0; }

@@ -18,6 +18,8 @@
 //    are the same look-up and the multiply is skipped warp-wide by one vote per step when nobody hit (the usual case);
 //  * lane l scores candidate 32*step + l; lane sums / chunk totals / draw as in DESIGN.md section 4.
 #pragma once
+#include <type_traits>
+
 #include "dbl_link.cuh"
 
 // Per (record, non-constant attribute): H key words then H f64 values, H = p.hslots (a power of two >= 32, the same
@@ -83,7 +85,7 @@ __device__ __forceinline__ void pcg2_load(Pcg2Cand<A, NS, PK> &c, const int *til
 #ifndef DBL_PCG2_VOTE
 #define DBL_PCG2_VOTE 0
 #endif
-template <int A, int NS, int HC, bool CONVERGED, bool PK>
+template <int A, int NS, int HC, bool CONVERGED, bool PK, bool MISSING = true>
 __device__ __forceinline__ double pcg2_weight(const Pcg2Rec<A, NS> &rc, const LinkParams &p, const char *tab,
                                               const double *ctab, const Pcg2Cand<A, NS, PK> &cd) {
   const int hslots = HC ? HC : p.hslots;
@@ -131,7 +133,7 @@ __device__ __forceinline__ double pcg2_weight(const Pcg2Rec<A, NS> &rc, const Li
         w = w * reinterpret_cast<const double *>(tab + q * tabb + hslots * 4)[slot];
     }
   }
-  if (rc.mmask) {
+  if (MISSING && rc.mmask) {
 #pragma unroll
     for (int q = 0; q < NS; ++q)
       if ((rc.mmask >> (A - NS + q)) & 1u) w = w * p.attrs[p.perm[A - NS + q]].invnorm[y[A - NS + q]];
@@ -261,32 +263,37 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, DBL_PCG2_CTAS_PER_SM) k
     const int spc = (TE / 32) * tpc;
     const int nchunks = (nsteps + spc - 1) / spc;
 
-    // ---- pass 1 over the TMA-staged tiles
+    // ---- pass 1 over the TMA-staged tiles.  Records without a missing non-constant attribute (most of them) take a
+    // loop body without the gather of 1/n(y): straight-line code the compiler can overlap across the steps of a tile
     double run = 0.0, Q = 0.0, acc = 0.0;
     int chunk = 0, tile_in_chunk = 0;
-    for (int t = 0; t < ntiles; ++t) {
-      const int g = tbase + t;
-      const int s = g % LINK_STAGES;
-      mbar_wait(&rg.full[s], (g / LINK_STAGES) & 1);
-      if (active) {
-        const int *tile = rg.tiles + (size_t)s * TW;
+    auto pass1 = [&](auto missing_tag) {
+      constexpr bool MISSING = decltype(missing_tag)::value;
+      for (int t = 0; t < ntiles; ++t) {
+        const int g = tbase + t;
+        const int s = g % LINK_STAGES;
+        mbar_wait(&rg.full[s], (g / LINK_STAGES) & 1);
+        if (active) {
+          const int *tile = rg.tiles + (size_t)s * TW;
 #pragma unroll
-        for (int q = 0; q < TE / 32; ++q) {
-          Pcg2Cand<A, NS, PK> cd;
-          pcg2_load<A, NS, PK>(cd, tile, q * 32 + lane);
-          acc = acc + pcg2_weight<A, NS, HC, true, PK>(rc, p, tab, ctab, cd);
+          for (int q = 0; q < TE / 32; ++q) {
+            Pcg2Cand<A, NS, PK> cd;
+            pcg2_load<A, NS, PK>(cd, tile, q * 32 + lane);
+            acc = acc + pcg2_weight<A, NS, HC, true, PK, MISSING>(rc, p, tab, ctab, cd);
+          }
+          if (++tile_in_chunk == tpc || t + 1 == ntiles) {
+            run = run + butterfly_sum(acc);
+            if (lane == chunk) Q = run;
+            ++chunk;
+            acc = 0.0;
+            tile_in_chunk = 0;
+          }
         }
-        if (++tile_in_chunk == tpc || t + 1 == ntiles) {
-          run = run + butterfly_sum(acc);
-          if (lane == chunk) Q = run;
-          ++chunk;
-          acc = 0.0;
-          tile_in_chunk = 0;
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&rg.empty[s]);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&rg.empty[s]);
-    }
+    };
+    if (rc.mmask) pass1(std::true_type{}); else pass1(std::false_type{});
     tbase += ntiles;
     if (!active) continue;
     if (!(run > 0.0) || isinf(run)) { fail_link(p, lane, r); continue; }

@@ -54,6 +54,7 @@ class AttributeIndex:
         self.is_constant = bool(is_constant)
         L = _lib.load()
         self.num_values = L.dbl_index_num_values(handle)
+        self.hash_slots = L.dbl_index_hash_slots(handle)
         self.nnz = L.dbl_index_nnz(handle)
 
     @classmethod
@@ -390,6 +391,16 @@ class GibbsEngine:
     def set_link_mode(self, mode):
         """0 = automatic kernel choice, 1 = force the generic fallback link kernel (same draws)."""
         _check(_lib.load().dbl_set_link_mode(self._h, int(mode)), "set_link_mode", self._h)
+
+    def link_kernel(self, sampler="PCG-II"):
+        """Name of the link kernel a sweep with this sampler launches."""
+        s = SAMPLERS[sampler] if isinstance(sampler, str) else int(sampler)
+        k = _lib.load().dbl_link_kernel(self._h, s)
+        base = {0: "k_link_generic", 1: "k_link_match", 2: "k_link_pruned", 3: "k_link_pcg2"}[k & 3]
+        if (k & 3) == 3:
+            base += "<A=%d,NS=%d,HC=%s,PK=%d>" % (self.A, sum(not ix.is_constant for ix in self.indexes),
+                                                  "32" if k & 8 else "0", 1 if k & 4 else 0)
+        return base
 
     def set_graph_mode(self, mode):
         """0 = automatic (CUDA graph replay of a sweep for launch-bound sizes), 1 = never, 2 = whenever possible."""

@@ -53,6 +53,9 @@ int dbl_index_from_tables(dbl_index **out, int32_t num_values, int similarity, c
 void dbl_index_free(dbl_index *);
 int32_t dbl_index_num_values(const dbl_index *);                 /* AttributeIndex.numValues                 */
 int32_t dbl_index_nnz(const dbl_index *);
+/* slots of the per-row perfect-hash tables the link kernel probes (32 = the fast instantiations; 0 = none: constant
+ * attribute, or rows too long for a table) */
+int32_t dbl_index_hash_slots(const dbl_index *);
 int32_t dbl_index_value_id(const dbl_index *, const char *value); /* valueIdxOf; -1 when absent              */
 const char *dbl_index_value(const dbl_index *, int32_t value_id);
 /* copies of the tables (arrays sized num_values, num_values+1, nnz, nnz); any pointer may be NULL */
@@ -242,6 +245,10 @@ int64_t dbl_kernel_launches(const dbl_ctx *);
  * per-sweep inverted index), 1 = always the generic fallback kernel, 2 = dense TMA kernels for every sampler.
  * All produce identical draws; this exists so tests can cover every kernel. */
 int dbl_set_link_mode(dbl_ctx *, int mode);
+/* which link kernel a sweep with this sampler launches: 0 generic fallback, 1 dense must-match kernel, 2 index-pruned
+ * kernel, 3 k_link_pcg2 (+4: byte-packed constants, +8: 32-slot tables known at compile time).  A model that falls
+ * back to the generic kernel runs an order of magnitude slower: benches and tests assert what they expect. */
+int dbl_link_kernel(const dbl_ctx *, int sampler);
 /* How dbl_sweep / dbl_sweep_async enqueue several sweeps: 0 = automatic (problems small enough to be bound by kernel
  * launches replay a captured CUDA graph of one sweep), 1 = every sweep enqueued kernel by kernel (and the link kernel
  * timed per launch, dbl_link_kernel_ms), 2 = graphs whenever possible.  Same chain either way. */

@@ -108,6 +108,9 @@ def _full_config_against_oracle(monkeypatch, config, records, levels, split, sam
     eng.set_partitioner(D.KDTreePartitioner(levels, split).fit(eng.download_state()["y"]))
     st, tree = bench.cpu_prepare(enc, levels, split)  # the oracle's own tables, initial state and tree, same seed
     assert tree.n_leaves == eng.num_partitions == 1 << levels
+    # the fast kernels, not a silent fall-back to the generic one (an order of magnitude slower)
+    assert eng.link_kernel("PCG-II").startswith("k_link_pcg2<") and "HC=32" in eng.link_kernel("PCG-II")
+    assert eng.link_kernel("PCG-I") == "k_link_pruned"
     d = eng.download_state()
     for k in ("link", "y", "z", "theta", "block"):
         np.testing.assert_array_equal(d[k], getattr(st, k), err_msg="initial " + k)
