@@ -1170,8 +1170,9 @@ struct dbl_ctx {
   DevBuf<int> vflag, file_cnt;
   DevBuf<unsigned> zmask;
   DevBuf<double> entN;
-  std::vector<double> h_theta;
+  std::vector<double> h_theta, h_file_sizes_d;
   std::vector<int64_t> file_sizes;
+  long long h_head[2] = {0, 0};  // staging of (iteration, status) for a new state
 
   // control block (one allocation, mirrored in pinned host memory by snapshot()):
   //   [CTL_WORDS] ctl | [nw] partial summary | [nw] global summary | [A*F] theta | [A*F] theta_prev | [2] hash
@@ -1718,7 +1719,7 @@ static int snapshot(dbl_ctx *ctx) {
   return DBL_OK;
 }
 
-static int finish_new_state(dbl_ctx *ctx, bool check_state) {
+static int finish_new_state(dbl_ctx *ctx, bool check_state, bool new_records) {
   // range checks on the device, then file sizes (RecordsCache.fileSizes)
   CUDA_TRY(cudaMemsetAsync(ctx->vflag.p, 0, sizeof(int), ctx->stream));
   k_validate<<<grid_for(std::max(ctx->R, ctx->E), 256), 256, 0, ctx->stream>>>(
@@ -1726,39 +1727,41 @@ static int finish_new_state(dbl_ctx *ctx, bool check_state) {
       check_state ? ctx->y.p : nullptr, ctx->vflag.p);
   int bad = 0;
   CUDA_TRY(cudaMemcpyAsync(&bad, ctx->vflag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  std::vector<int> hc(ctx->F);
+  if (new_records) {
+    CUDA_TRY(cudaMemsetAsync(ctx->file_cnt.p, 0, sizeof(int) * ctx->F, ctx->stream));
+    k_hist<<<grid_for(ctx->R, 256), 256, 0, ctx->stream>>>(ctx->R, ctx->file.p, ctx->file_cnt.p);
+    CUDA_TRY(cudaMemcpyAsync(hc.data(), ctx->file_cnt.p, sizeof(int) * ctx->F, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // nothing below may run on out-of-range ids
   if (bad) {
     ctx->has_state = false;
     ctx->set_error(bad & 1 ? "record value id out of range" : bad & 2 ? "file id out of range"
                    : bad & 4 ? "link out of range" : "entity value id out of range");
     return DBL_ERR_INVALID;
   }
-  CUDA_TRY(cudaMemsetAsync(ctx->file_cnt.p, 0, sizeof(int) * ctx->F, ctx->stream));
-  k_hist<<<grid_for(ctx->R, 256), 256, 0, ctx->stream>>>(ctx->R, ctx->file.p, ctx->file_cnt.p);
-  std::vector<int> hc(ctx->F);
-  CUDA_TRY(cudaMemcpyAsync(hc.data(), ctx->file_cnt.p, sizeof(int) * ctx->F, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  ctx->file_sizes.assign(hc.begin(), hc.end());
-  {
-    std::vector<double> fs(hc.begin(), hc.end());
-    CUDA_TRY(cudaMemcpyAsync(ctx->prior.p + 2 * ctx->A, fs.data(), sizeof(double) * ctx->F, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (new_records) {
+    ctx->file_sizes.assign(hc.begin(), hc.end());
+    ctx->h_file_sizes_d.assign(hc.begin(), hc.end());
+    CUDA_TRY(cudaMemcpyAsync(ctx->prior.p + 2 * ctx->A, ctx->h_file_sizes_d.data(), sizeof(double) * ctx->F,
+                             cudaMemcpyHostToDevice, ctx->stream));
   }
   ctx->launches += 2;
   // iteration / status of the new state
-  {
-    long long head[2] = {ctx->iteration, 0};
-    CUDA_TRY(cudaMemcpyAsync(ctx->ctl(), head, sizeof(head), cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  }
+  ctx->h_head[0] = ctx->iteration; ctx->h_head[1] = 0;
+  CUDA_TRY(cudaMemcpyAsync(ctx->ctl(), ctx->h_head, sizeof(ctx->h_head), cudaMemcpyHostToDevice, ctx->stream));
   int rc = build_links_csr(ctx);
   if (rc) return rc;
   rc = refresh_summary(ctx, false);
   if (rc) return rc;
   rc = adopt_local_summary(ctx);
   if (rc) return rc;
-  rc = relayout(ctx);
-  if (rc) return rc;
+  // a sharded context is carved up by dbl_set_block_owners next, which lays the shard out; until then nothing reads
+  // the layout (dbl_set_partitioner builds its own)
+  if (ctx->world <= 1) {
+    rc = relayout(ctx);
+    if (rc) return rc;
+  }
   rc = snapshot(ctx);
   if (rc) return rc;
   ctx->has_state = true;
@@ -1790,8 +1793,7 @@ static int upload_theta(dbl_ctx *ctx) {
   const size_t n = (size_t)ctx->A * ctx->F;
   CUDA_TRY(cudaMemcpyAsync(ctx->theta(), ctx->h_theta.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(cudaMemcpyAsync(ctx->theta_prev(), ctx->h_theta.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // h_theta may change before an asynchronous copy has run
-  return DBL_OK;
+  return DBL_OK;  // h_theta is next written by snapshot(), i.e. after the stream has drained
 }
 
 extern "C" int dbl_state_init(dbl_ctx *ctx, int64_t R, const int32_t *x, const int32_t *file, int64_t pop) {
@@ -1813,21 +1815,28 @@ extern "C" int dbl_state_init(dbl_ctx *ctx, int64_t R, const int32_t *x, const i
   rc = upload_theta(ctx);
   if (rc) return rc;
   ctx->iteration = 0;
-  return finish_new_state(ctx, false);
+  return finish_new_state(ctx, false, true);
 }
 
 extern "C" int dbl_state_upload(dbl_ctx *ctx, int64_t R, int64_t E, const int32_t *x, const int32_t *file,
                                 const uint8_t *z, const int32_t *link, const int32_t *y, const double *theta,
                                 int64_t iteration) {
-  if (!ctx || !x || !file || !z || !link || !y || !theta) return DBL_ERR_INVALID;
+  if (!ctx || !z || !link || !y || !theta || ((x == nullptr) != (file == nullptr))) return DBL_ERR_INVALID;
+  const bool new_records = (x != nullptr);
+  if (!new_records && (!ctx->x.p || ctx->R != R || ctx->E != E)) {
+    ctx->set_error("dbl_state_upload without records: the context holds no records / state of that shape");
+    return DBL_ERR_STATE;
+  }
   CUDA_TRY(cudaSetDevice(ctx->device));
   int rc = alloc_state(ctx, R, E);
   if (rc) return rc;
   const int A = ctx->A;
   DevBuf<uint8_t> &zb = ctx->zbytes;
-  CUDA_TRY(cudaMemcpyAsync(ctx->x.p, x, sizeof(int) * R * A, cudaMemcpyDefault, ctx->stream));
-  k_rec_class<<<grid_for(R, 256), 256, 0, ctx->stream>>>(R, A, ctx->attrs.p, ctx->x.p, ctx->rec_class.p);
-  CUDA_TRY(cudaMemcpyAsync(ctx->file.p, file, sizeof(int) * R, cudaMemcpyDefault, ctx->stream));
+  if (new_records) {
+    CUDA_TRY(cudaMemcpyAsync(ctx->x.p, x, sizeof(int) * R * A, cudaMemcpyDefault, ctx->stream));
+    k_rec_class<<<grid_for(R, 256), 256, 0, ctx->stream>>>(R, A, ctx->attrs.p, ctx->x.p, ctx->rec_class.p);
+    CUDA_TRY(cudaMemcpyAsync(ctx->file.p, file, sizeof(int) * R, cudaMemcpyDefault, ctx->stream));
+  }
   CUDA_TRY(cudaMemcpyAsync(zb.p, z, (size_t)R * A, cudaMemcpyDefault, ctx->stream));
   CUDA_TRY(cudaMemcpyAsync(ctx->link.p, link, sizeof(int) * R, cudaMemcpyDefault, ctx->stream));
   CUDA_TRY(cudaMemcpyAsync(ctx->y.p, y, sizeof(int) * E * A, cudaMemcpyDefault, ctx->stream));
@@ -1837,7 +1846,7 @@ extern "C" int dbl_state_upload(dbl_ctx *ctx, int64_t R, int64_t E, const int32_
   rc = upload_theta(ctx);
   if (rc) return rc;
   ctx->iteration = iteration;
-  return finish_new_state(ctx, true);
+  return finish_new_state(ctx, true, new_records);
 }
 
 extern "C" int dbl_state_download(dbl_ctx *ctx, uint8_t *z, int32_t *link, int32_t *y, double *theta,
@@ -2295,21 +2304,21 @@ static int apply_ownership(dbl_ctx *ctx) {
 }
 
 extern "C" int dbl_set_block_owners(dbl_ctx *ctx, const int32_t *owner_of_block) {
-  if (!ctx || !owner_of_block) return DBL_ERR_INVALID;
+  if (!ctx) return DBL_ERR_INVALID;
   if (!ctx->has_state) { ctx->set_error("set_block_owners needs a (replicated) state"); return DBL_ERR_STATE; }
   if (!ctx->all_owned) { ctx->set_error("set_block_owners needs the replicated state: upload / init it again first"); return DBL_ERR_STATE; }
   CUDA_TRY(cudaSetDevice(ctx->device));
-  for (int b = 0; b < ctx->P; ++b)
-    if (owner_of_block[b] < 0 || owner_of_block[b] >= ctx->world) { ctx->set_error("owner out of range"); return DBL_ERR_INVALID; }
-  ctx->owner_h.assign(owner_of_block, owner_of_block + ctx->P);
-  CUDA_TRY(cudaMemcpyAsync(ctx->owner.p, ctx->owner_h.data(), sizeof(int) * ctx->P, cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (owner_of_block) {  // NULL = the table the context already holds on the device (the device-side LPT may have changed it)
+    for (int b = 0; b < ctx->P; ++b)
+      if (owner_of_block[b] < 0 || owner_of_block[b] >= ctx->world) { ctx->set_error("owner out of range"); return DBL_ERR_INVALID; }
+    ctx->owner_h.assign(owner_of_block, owner_of_block + ctx->P);
+    CUDA_TRY(cudaMemcpyAsync(ctx->owner.p, ctx->owner_h.data(), sizeof(int) * ctx->P, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
   int rc = apply_ownership(ctx);
   if (rc) return rc;
   ctx->all_owned = (ctx->world <= 1);
-  rc = build_links_csr(ctx);
-  if (rc) return rc;
-  rc = refresh_summary(ctx, false);  // partial summary of the shard; the global one (replicated state) stays
+  rc = build_links_csr(ctx);  // of the shard; the global summary (of the replicated state) stays
   if (rc) return rc;
   rc = relayout(ctx);
   if (rc) return rc;
@@ -2595,33 +2604,33 @@ extern "C" int dbl_download_owned(dbl_ctx *ctx, int64_t *n_ent, int32_t *ent_ids
                                   int64_t *n_rec, int32_t *rec_ids, int32_t *link, uint8_t *z) {
   if (!ctx || !n_ent || !n_rec) return DBL_ERR_INVALID;
   if (!ctx->has_state) { ctx->set_error("no state"); return DBL_ERR_STATE; }
+  if (ctx->world > 1 && ctx->all_owned) { ctx->set_error("dbl_download_owned before dbl_set_block_owners"); return DBL_ERR_STATE; }
   CUDA_TRY(cudaSetDevice(ctx->device));
   if (ctx->h_owned_ent < 0 || ctx->h_owned_rec < 0) { int rc = snapshot(ctx); if (rc) return rc; }
   const int64_t ne = ctx->h_owned_ent, nr = ctx->h_owned_rec;
   const int A = ctx->A;
   *n_ent = ne; *n_rec = nr;
-  const size_t need_i = (size_t)std::max<int64_t>(ne * (A + 2), nr * 2) + 1;
+  if (!(ent_ids && y && block) && !(rec_ids && link && z)) return DBL_OK;  // counts only
+  const size_t need_i = (size_t)(ne * (A + 2) + nr * 2) + 1;
   if (ctx->gather_i.n < need_i) CUDA_TRY(ctx->gather_i.alloc(need_i));
   if (ctx->gather_b.n < (size_t)nr * A + 1) CUDA_TRY(ctx->gather_b.alloc((size_t)nr * A + 1));
+  int *eids = ctx->gather_i.p, *yo = eids + ne, *bo = yo + ne * A, *rids = bo + ne, *lo = rids + nr;
   if (ne > 0 && ent_ids && y && block) {
-    int *ids = ctx->gather_i.p, *yo = ids + ne, *bo = yo + ne * A;
-    k_gather_ent<<<grid_for(ne, 256), 256, 0, ctx->stream>>>(ne, A, ctx->ent_sorted.p, ctx->y.p, ctx->blk.p, ids, yo, bo);
-    CUDA_TRY(cudaMemcpyAsync(ent_ids, ids, sizeof(int) * ne, cudaMemcpyDeviceToHost, ctx->stream));
+    k_gather_ent<<<grid_for(ne, 256), 256, 0, ctx->stream>>>(ne, A, ctx->ent_sorted.p, ctx->y.p, ctx->blk.p, eids, yo, bo);
+    CUDA_TRY(cudaMemcpyAsync(ent_ids, eids, sizeof(int) * ne, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(y, yo, sizeof(int) * ne * A, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(block, bo, sizeof(int) * ne, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   }
   if (nr > 0 && rec_ids && link && z) {
-    int *ids = ctx->gather_i.p, *lo = ids + nr;
-    k_gather_rec<<<grid_for(nr, 256), 256, 0, ctx->stream>>>(nr, A, ctx->rec_sorted.p, ctx->link.p, ctx->zmask.p, ids, lo,
+    k_gather_rec<<<grid_for(nr, 256), 256, 0, ctx->stream>>>(nr, A, ctx->rec_sorted.p, ctx->link.p, ctx->zmask.p, rids, lo,
                                                             ctx->gather_b.p);
-    CUDA_TRY(cudaMemcpyAsync(rec_ids, ids, sizeof(int) * nr, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(rec_ids, rids, sizeof(int) * nr, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(link, lo, sizeof(int) * nr, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(z, ctx->gather_b.p, (size_t)nr * A, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   }
   ctx->launches += 2;
   CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return DBL_OK;
 }
 

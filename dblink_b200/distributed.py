@@ -189,19 +189,29 @@ class ShardedGibbs:
         traffic is shared: a rank copies its 1/world slice of each array and the slices are all-gathered."""
         if self.owner is None:
             raise RuntimeError("upload_state needs the partitioner and block placement of init_state first")
-        x = np.asarray(x)
         y = np.asarray(y)
-        if x.ndim != 2 or y.ndim != 2 or x.shape[1] != self.A or y.shape[1] != self.A:
+        if y.ndim != 2 or y.shape[1] != self.A:
             raise ValueError("state arrays do not match the model")
-        dx = self._gather_upload("x", x, np.int32)
-        df = self._gather_upload("file", file_ids, np.int32)
+        # the records never change along a chain: the same host arrays as last time stay on the devices
+        keep = x is None or (x is getattr(self, "_records_src", (None, None))[0] and file_ids is self._records_src[1]
+                             and y.shape[0] == self.eng.num_entities)
+        R = self.eng.num_records if keep else np.asarray(x).shape[0]
+        if not keep:
+            x = np.asarray(x)
+            if x.ndim != 2 or x.shape[1] != self.A:
+                raise ValueError("state arrays do not match the model")
+            dx = self._gather_upload("x", x, np.int32)
+            df = self._gather_upload("file", file_ids, np.int32)
         dz = self._gather_upload("z", z, np.uint8)
         dl = self._gather_upload("link", link, np.int32)
         dy = self._gather_upload("y", y, np.int32)
         self.torch.cuda.current_stream().synchronize()  # the engine copies from these buffers on its own stream
-        self.eng.upload_state_device(x.shape[0], y.shape[0], dx.data_ptr(), df.data_ptr(), dz.data_ptr(),
-                                     dl.data_ptr(), dy.data_ptr(), theta, iteration)
-        self.set_owners(self.block_owners())
+        self.eng.upload_state_device(R, y.shape[0], dx.data_ptr() if not keep else 0, df.data_ptr() if not keep else 0,
+                                     dz.data_ptr(), dl.data_ptr(), dy.data_ptr(), theta, iteration)
+        if not keep:
+            self._records_src = (x, file_ids)
+        # carve the shards out again with the block -> rank table the devices hold (no host round trip)
+        _check(_lib.load().dbl_set_block_owners(self.eng._h, None), "set_block_owners", self.eng._h)
 
     def set_owners(self, owner):
         owner = np.ascontiguousarray(owner, dtype=np.int32)
@@ -321,10 +331,10 @@ class ShardedGibbs:
         s = self.eng.summary()
         return combine_state_hash(he, hr, s["theta"], s["iteration"])
 
-    def download_owned(self):
+    def download_owned(self, out=None):
         """Only this rank's rows (State.save of a distributed state): the device-to-host traffic of the whole job is
-        one copy of the state, not one per rank."""
-        return self.eng.download_owned()
+        one copy of the state, not one per rank.  `out` = an earlier result whose pinned buffers are reused."""
+        return self.eng.download_owned(out)
 
     def links(self):
         """(link[R], block_of_entity[E]) of the global state on every rank."""

@@ -215,6 +215,10 @@ class KDTreePartitioner:
         return out
 
 
+class _OwnedRows(dict):
+    """dict of the owned rows that also carries the host buffers behind them (reused by the next download)."""
+
+
 class GibbsEngine:
     """The Markov chain state on one GPU and its transition operator (State.scala:56-99)."""
 
@@ -263,16 +267,32 @@ class GibbsEngine:
         f = _i32(file_ids if file_ids is not None else np.zeros(x.shape[0], np.int32))
         _check(_lib.load().dbl_state_init(self._h, x.shape[0], _p(x, _lib.i32p), _p(f, _lib.i32p),
                                           int(population_size)), "init_state", self._h)
+        self._records_src = (None, None)
 
     def upload_state(self, x, file_ids, z, link, y, theta, iteration=0):
-        x, f, link, y = _i32(x), _i32(file_ids), _i32(link), _i32(y)
+        """State.read: an arbitrary state.  x = file_ids = None keeps the records already on the device (they never
+        change along a chain); passing the very same host arrays as last time has the same effect."""
+        link, y = _i32(link), _i32(y)
         z = np.ascontiguousarray(z, dtype=np.uint8)
         theta = _f64(theta)
-        if x.shape[1] != self.A or y.shape[1] != self.A or theta.size != self.A * self.F:
+        if y.shape[1] != self.A or theta.size != self.A * self.F:
             raise ValueError("state arrays do not match the model")
-        _check(_lib.load().dbl_state_upload(self._h, x.shape[0], y.shape[0], _p(x, _lib.i32p), _p(f, _lib.i32p),
-                                            _p(z, _lib.u8p), _p(link, _lib.i32p), _p(y, _lib.i32p),
-                                            _p(theta, _lib.f64p), int(iteration)), "upload_state", self._h)
+        keep = x is None or (x is getattr(self, "_records_src", (None, None))[0] and
+                             file_ids is self._records_src[1] and y.shape[0] == self.num_entities)
+        if keep:
+            xp, fp, R = None, None, self.num_records
+            if z.shape[0] != R:
+                raise ValueError("state arrays do not match the records on the device")
+        else:
+            xs, fs = _i32(x), _i32(file_ids)
+            if xs.shape[1] != self.A:
+                raise ValueError("state arrays do not match the model")
+            xp, fp, R = _p(xs, _lib.i32p), _p(fs, _lib.i32p), xs.shape[0]
+        _check(_lib.load().dbl_state_upload(self._h, R, y.shape[0], xp, fp, _p(z, _lib.u8p), _p(link, _lib.i32p),
+                                            _p(y, _lib.i32p), _p(theta, _lib.f64p), int(iteration)), "upload_state",
+               self._h)
+        if not keep:
+            self._records_src = (x, file_ids)
 
     def upload_state_device(self, R, E, x_ptr, file_ptr, z_ptr, link_ptr, y_ptr, theta, iteration=0):
         """upload_state from DEVICE buffers (raw addresses of int32 x[R,A], file[R], uint8 z[R,A], int32 link[R],
@@ -280,7 +300,7 @@ class GibbsEngine:
         theta = _f64(theta)
         if theta.size != self.A * self.F:
             raise ValueError("state arrays do not match the model")
-        cast = lambda p, t: C.cast(C.c_void_p(int(p)), t)
+        cast = lambda p, t: C.cast(C.c_void_p(int(p)), t) if p else None
         _check(_lib.load().dbl_state_upload(self._h, int(R), int(E), cast(x_ptr, _lib.i32p), cast(file_ptr, _lib.i32p),
                                             cast(z_ptr, _lib.u8p), cast(link_ptr, _lib.i32p), cast(y_ptr, _lib.i32p),
                                             _p(theta, _lib.f64p), int(iteration)), "upload_state", self._h)
@@ -350,18 +370,42 @@ class GibbsEngine:
         _check(_lib.load().dbl_state_hash(self._h, _p(h, _lib.u64p)), "state_hash", self._h)
         return int(h[0]), int(h[1])
 
-    def download_owned(self):
-        """The rows this context owns, compacted: {ent_ids, y, block, rec_ids, link, z}."""
-        R, E, A = self.num_records, self.num_entities, self.A
+    def owned_counts(self):
+        """(entities, records) in the blocks this context owns."""
         ne, nr = C.c_int64(0), C.c_int64(0)
-        eid, y, blk = np.zeros(E, np.int32), np.zeros((E, A), np.int32), np.zeros(E, np.int32)
-        rid, link, z = np.zeros(R, np.int32), np.zeros(R, np.int32), np.zeros((R, A), np.uint8)
-        _check(_lib.load().dbl_download_owned(self._h, C.byref(ne), _p(eid, _lib.i32p), _p(y, _lib.i32p),
-                                              _p(blk, _lib.i32p), C.byref(nr), _p(rid, _lib.i32p), _p(link, _lib.i32p),
-                                              _p(z, _lib.u8p)), "download_owned", self._h)
-        ne, nr = ne.value, nr.value
-        return {"ent_ids": eid[:ne], "y": y[:ne], "block": blk[:ne], "rec_ids": rid[:nr], "link": link[:nr],
-                "z": z[:nr]}
+        _check(_lib.load().dbl_download_owned(self._h, C.byref(ne), None, None, None, C.byref(nr), None, None, None),
+               "owned_counts", self._h)
+        return ne.value, nr.value
+
+    def download_owned(self, out=None):
+        """The rows this context owns, compacted: {ent_ids, y, block, rec_ids, link, z}.  `out` = the dict returned by
+        an earlier call: its (pinned) buffers are reused when they are large enough."""
+        A = self.A
+        ne, nr = self.owned_counts()
+        buf = getattr(out, "_buffers", None) if out is not None else None
+        if buf is None or buf["cap_e"] < ne or buf["cap_r"] < nr:
+            cap_e, cap_r = int(ne * 1.25) + 16, int(nr * 1.25) + 16
+
+            def alloc(shape, dtype):
+                try:  # pinned host memory: the copies are plain DMA
+                    import torch
+
+                    return torch.empty(shape, dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True).numpy()
+                except Exception:
+                    return np.empty(shape, dtype)
+
+            buf = {"cap_e": cap_e, "cap_r": cap_r, "eid": alloc(cap_e, np.int32), "y": alloc((cap_e, A), np.int32),
+                   "blk": alloc(cap_e, np.int32), "rid": alloc(cap_r, np.int32), "link": alloc(cap_r, np.int32),
+                   "z": alloc((cap_r, A), np.uint8)}
+        ne2, nr2 = C.c_int64(0), C.c_int64(0)
+        _check(_lib.load().dbl_download_owned(self._h, C.byref(ne2), _p(buf["eid"], _lib.i32p), _p(buf["y"], _lib.i32p),
+                                              _p(buf["blk"], _lib.i32p), C.byref(nr2), _p(buf["rid"], _lib.i32p),
+                                              _p(buf["link"], _lib.i32p), _p(buf["z"], _lib.u8p)),
+               "download_owned", self._h)
+        res = _OwnedRows({"ent_ids": buf["eid"][:ne], "y": buf["y"][:ne], "block": buf["blk"][:ne],
+                          "rec_ids": buf["rid"][:nr], "link": buf["link"][:nr], "z": buf["z"][:nr]})
+        res._buffers = buf
+        return res
 
     def sweep_by_block(self, sampler="PCG-I", order=None):
         """One application of State.nextState driven block by block, the way the reference runs one task per

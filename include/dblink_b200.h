@@ -120,7 +120,9 @@ int dbl_state_init(dbl_ctx *, int64_t num_records, const int32_t *x, const int32
                    int64_t population_size);
 /* Arbitrary state (resume; State.read, State.scala:160-193).  z = R x A bytes, link = R global entity ids,
  * y = E x A value ids, theta = A x F (host).  x, file, z, link, y may be host OR device pointers (unified
- * addressing decides): a multi-GPU caller can stage slices and all-gather them on the device first. */
+ * addressing decides): a multi-GPU caller can stage slices and all-gather them on the device first.
+ * x = file = NULL keeps the records the context already holds (they never change along a chain: the reference
+ * broadcasts its RecordsCache once); R and E must then be those of the state being replaced. */
 int dbl_state_upload(dbl_ctx *, int64_t num_records, int64_t num_entities, const int32_t *x, const int32_t *file,
                      const uint8_t *z, const int32_t *link, const int32_t *y, const double *theta,
                      int64_t iteration);
@@ -204,7 +206,8 @@ int dbl_state_hash(dbl_ctx *, uint64_t *hash_out /*2*/);
  *   dbl_exchange_unpack    apply what was received
  *   dbl_partial_summary -> all-reduce on the host (with an error flag) -> dbl_sweep_end(global summary)
  * ------------------------------------------------------------------------------------------------- */
-int dbl_set_block_owners(dbl_ctx *, const int32_t *owner_of_block /* numPartitions entries in [0, world) */);
+int dbl_set_block_owners(dbl_ctx *, const int32_t *owner_of_block /* numPartitions entries in [0, world); NULL =
+                                                                      the table already on the device */);
 int dbl_block_owners(dbl_ctx *, int32_t *owner_of_block_out);  /* current table (the device-side LPT may change it) */
 #define DBL_COMM_BLOB_BYTES 192
 int dbl_comm_export(dbl_ctx *, void *blob_out /* DBL_COMM_BLOB_BYTES */);

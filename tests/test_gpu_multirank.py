@@ -221,3 +221,29 @@ def test_graph_replay_on_a_sharded_chain(oracle):
         st.sweep(oracle.SAMPLERS["PCG-II"], n)
         assert_same(sh, st)
     sh.close()
+
+
+def test_upload_state_keeps_the_records(oracle):
+    """the records never change along a chain (the reference broadcasts its RecordsCache once): a state upload without
+    them -- x = file = None, or the very same host arrays as before -- leaves them on the device"""
+    from helpers import product_setup
+
+    g = synth_problem(seed=19, R=700, n_files=2)
+    eng, rc, x, file = product_setup(g, 6, 2, (2, 3))
+    m, st, tree, ox, ofile = oracle_setup(oracle, g, 6, 2, (2, 3))
+    eng.sweep("PCG-II", 2)
+    st.sweep(oracle.SAMPLERS["PCG-II"], 2)
+    d = eng.download_state()
+    for how in ("none", "same-arrays", "same-arrays"):
+        if how == "none":
+            eng.upload_state(None, None, d["z"], d["link"], d["y"], d["theta"], iteration=eng.iteration)
+        else:
+            eng.upload_state(x, file, d["z"], d["link"], d["y"], d["theta"], iteration=eng.iteration)
+        eng.sweep("PCG-I", 2)
+        st.sweep(oracle.SAMPLERS["PCG-I"], 2)
+        d = eng.download_state()
+        for k in ("theta", "link", "y", "z", "block"):
+            np.testing.assert_array_equal(d[k], getattr(st, k), err_msg=how + " " + k)
+    with pytest.raises(Exception):  # another population size needs the records again
+        eng.upload_state(None, None, d["z"], d["link"], d["y"][:-1], d["theta"], iteration=0)
+    eng.close()
