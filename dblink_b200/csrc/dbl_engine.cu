@@ -183,12 +183,6 @@ __global__ void k_hist(int64_t n, const int *__restrict__ key, int *__restrict__
 // the link kernel (and its tile ring) advance at the same pace.  The order of records inside a block has no effect
 // on the draws (every record has its own counter-based stream).
 constexpr int REC_CLASS_BITS = 8;
-__global__ void k_rec_block_keys(int64_t R, const int *__restrict__ link, const int *__restrict__ blk,
-                                 const unsigned char *__restrict__ rec_owned,
-                                 const unsigned char *__restrict__ rec_class, int P, int *__restrict__ key) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < R) key[r] = rec_owned[r] ? ((blk[link[r]] << REC_CLASS_BITS) | rec_class[r]) : (P << REC_CLASS_BITS);
-}
 // cost class of a record (x is static): bits 7..6 = number of missing non-constant attributes (each one adds a
 // gather per candidate), bits 5..0 = expected number of similar-but-different candidate values per 32-candidate
 // step (how often the warp takes the rare multiply: equal or similar value), from the empirical value frequencies.
@@ -210,32 +204,69 @@ __global__ void k_rec_class(int64_t R, int A, const AttrDev *__restrict__ attrs,
   const int hq = min(63, (int)(h * 32.0 * 8.0));
   cls[r] = (unsigned char)((min(miss, 3) << 6) | hq);
 }
-__global__ void k_ent_block_keys(int64_t E, const int *__restrict__ blk, const unsigned char *__restrict__ ent_owned,
-                                 int P, int *__restrict__ key) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < E) key[e] = ent_owned[e] ? blk[e] : P;
+// block sort keys of the entities and of the records in one launch
+__global__ void k_block_keys(int64_t E, int64_t R, const int *__restrict__ blk, const int *__restrict__ link,
+                             const unsigned char *__restrict__ ent_owned, const unsigned char *__restrict__ rec_owned,
+                             const unsigned char *__restrict__ rec_class, int P, int *__restrict__ ent_key,
+                             int *__restrict__ rec_key) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < E) ent_key[i] = ent_owned[i] ? blk[i] : P;
+  if (i < R) rec_key[i] = rec_owned[i] ? ((blk[link[i]] << REC_CLASS_BITS) | rec_class[i]) : (P << REC_CLASS_BITS);
 }
 __global__ void k_rec_link_keys(int64_t R, const int *__restrict__ link, const unsigned char *__restrict__ rec_owned,
                                 int E, int *__restrict__ key) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r < R) key[r] = rec_owned[r] ? link[r] : E;
 }
+// the same inside a sweep, fused with the commit of the link draws: the link kernels wrote them to newlink; they
+// become the state only if no categorical of the sweep was without mass (the reference fails the task and no new
+// state exists, IndexNonUniformDiscreteDist.scala:78-79)
+__global__ void k_commit_link_keys(int64_t R, const long long *__restrict__ ctl, const int *__restrict__ newlink,
+                                   int *__restrict__ link, const unsigned char *__restrict__ rec_owned, int E,
+                                   int *__restrict__ key) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  int l = link[r];
+  const bool own = rec_owned[r];
+  if (own && !sweep_dead(ctl)) {
+    l = newlink[r];
+    link[r] = l;
+  }
+  key[r] = own ? l : E;
+}
 // offsets from sorted keys: ptr[k] = first position whose key is >= k, for k = 0..n_keys (keys beyond the data
 // point at n).  One pass over the sorted array; replaces an atomic histogram + scan.
-__global__ void k_segment_ptr(int64_t n, int n_keys, const int *__restrict__ sorted_key, int *__restrict__ ptr,
-                              int shift = 0) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void segment_ptr_at(int64_t i, int64_t n, int n_keys, const int *__restrict__ sorted_key,
+                                               int *__restrict__ ptr, int shift) {
   if (i > n) return;
   const int cur = (i < n) ? min(sorted_key[i] >> shift, n_keys) : n_keys;
   const int prev = (i > 0) ? min(sorted_key[i - 1] >> shift, n_keys) : -1;
   for (int k = prev + 1; k <= cur; ++k) ptr[k] = (int)i;
 }
-// prefix sums over the P blocks (P is 2^numLevels: small); also publishes the owned counts (everything before the
-// dummy block) in the control block -- they size the prefix-mode row kernels of the next sweep
+__global__ void k_segment_ptr(int64_t n, int n_keys, const int *__restrict__ sorted_key, int *__restrict__ ptr,
+                              int shift = 0) {
+  segment_ptr_at((int64_t)blockIdx.x * blockDim.x + threadIdx.x, n, n_keys, sorted_key, ptr, shift);
+}
+// block offsets of the sorted entities and of the sorted records in one launch
+__global__ void k_block_ptrs(int64_t E, int64_t R, int P, const int *__restrict__ blk_sorted, int *__restrict__ ent_ptr,
+                             const int *__restrict__ rec_key_sorted, int *__restrict__ rec_ptr) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  segment_ptr_at(i, E, P, blk_sorted, ent_ptr, 0);
+  segment_ptr_at(i, R, P, rec_key_sorted, rec_ptr, REC_CLASS_BITS);
+}
+// prefix sums over the P blocks (P is 2^numLevels: small); publishes the owned counts (everything before the dummy
+// block) in the control block -- they size the prefix-mode row kernels of the next sweep.  As the last kernel of a
+// sweep it also adopts the partial summary as the global one (single rank: adopt_nw > 0) and counts the sweep
+// (finish), unless the sweep was abandoned.
 __global__ void k_block_scan(int P, const int *__restrict__ ent_ptr, const int *__restrict__ rec_ptr,
                              int *__restrict__ tile_ptr, int *__restrict__ cta_ptr, int warps_per_cta,
-                             int *__restrict__ cta_ptr2, int warps_per_cta2, long long *__restrict__ ctl) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
+                             int *__restrict__ cta_ptr2, int warps_per_cta2, long long *__restrict__ ctl,
+                             int adopt_nw, const unsigned long long *__restrict__ part, long long *__restrict__ glob,
+                             int finish) {
+  const bool dead = sweep_dead(ctl);
+  if (adopt_nw > 0 && !dead)
+    for (int i = threadIdx.x; i < adopt_nw; i += blockDim.x) glob[i] = (long long)part[i];
+  if (threadIdx.x == 0) {
     int t = 0, c = 0, c2 = 0;
     for (int b = 0; b < P; ++b) {
       tile_ptr[b] = t; cta_ptr[b] = c; cta_ptr2[b] = c2;
@@ -247,38 +278,56 @@ __global__ void k_block_scan(int P, const int *__restrict__ ent_ptr, const int *
     tile_ptr[P] = t; cta_ptr[P] = c; cta_ptr2[P] = c2;
     ctl[CTL_OWNED_ENT] = ent_ptr[P];
     ctl[CTL_OWNED_REC] = rec_ptr[P];
+    if (finish && !dead) ctl[CTL_ITER] += 1;
   }
 }
-// tiled, block-sorted copy of the entity table: tile = { int32 y[A][TE]; double N[TE]; uint32 packed_consts[TE] }
-__global__ void k_build_tiles(int64_t E, int A, const int *__restrict__ y, const double *__restrict__ entN,
-                              const int *__restrict__ blk_sorted, const int *__restrict__ ent_sorted,
-                              const int *__restrict__ ent_ptr, const int *__restrict__ tile_ptr,
-                              int *__restrict__ tiles, const int *__restrict__ perm, int P, int npack,
-                              int *__restrict__ qtiles, int n_str, int qtile_pk) {
+// Tiled, block-sorted copies of the entity table, one thread per tile slot (padding slots of a block's last tile are
+// zeroed here: no memset of the whole table).  fmt 1: attribute-major tiles { int32 y[A][TE]; f64 N[TE]; uint32
+// packed_consts[TE] } (k_link_generic / k_link_match / k_link_pruned); fmt 2: quad tiles (k_link_pcg2).
+__global__ void k_build_tiles(int64_t n_slots, int fmt, int A, const int *__restrict__ y, const double *__restrict__ entN,
+                              const int *__restrict__ ent_sorted, const int *__restrict__ ent_ptr,
+                              const int *__restrict__ tile_ptr, int *__restrict__ tiles, const int *__restrict__ perm, int P,
+                              int npack, int *__restrict__ qtiles, int n_str, int qtile_pk) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= E) return;
-  const int b = blk_sorted[i];
-  if (b >= P) return;  // not owned by this rank
-  const int e = ent_sorted[i];
-  const int j = (int)(i - ent_ptr[b]);
-  int *tile = tiles + (size_t)(tile_ptr[b] + j / TE) * tile_words(A);
-  const int slot = j % TE;
-  for (int k = 0; k < A; ++k) tile[k * TE + slot] = y[(int64_t)e * A + perm[k]];  // kernel order
-  reinterpret_cast<double *>(tile + (size_t)A * TE)[slot] = entN[e];
-  unsigned pk = 0;  // constant attributes (kernel positions 0..npack-1), one byte each, for k_link_pcg2
-  for (int k = 0; k < npack; ++k) pk |= ((unsigned)y[(int64_t)e * A + perm[k]] & 0xFFu) << (8 * k);
-  tile[(size_t)(A + 2) * TE + slot] = (int)pk;
-  // quad tile of the same entity (k_link_pcg2): [group][slot][4]
-  const int nv = qtile_nv(A, n_str, qtile_pk != 0), ng = qtile_groups(nv), qw = qtile_words(nv);
-  int *qt = qtiles + (size_t)(tile_ptr[b] + j / TE) * qw * TE;
-  auto put = [&](int w, int v) { qt[((size_t)(w >> 2) * TE + slot) * 4 + (w & 3)] = v; };
-  if (qtile_pk) {
-    for (int q = 0; q < n_str; ++q) put(q, y[(int64_t)e * A + perm[A - n_str + q]]);
-    put(n_str, (int)pk);
-  } else {
-    for (int k = 0; k < A; ++k) put(k, y[(int64_t)e * A + perm[k]]);
+  if (i >= n_slots) return;
+  const int T = (int)(i / TE), slot = (int)(i % TE);
+  if (T >= tile_ptr[P]) return;
+  int lo = 0, hi = P;  // block of tile T: last b with tile_ptr[b] <= T
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (tile_ptr[mid] <= T) lo = mid; else hi = mid;
   }
-  reinterpret_cast<double *>(qt + (size_t)ng * 4 * TE)[slot] = entN[e];
+  const int b = lo;
+  const int j = (T - tile_ptr[b]) * TE + slot;
+  const bool real = j < ent_ptr[b + 1] - ent_ptr[b];
+  const int64_t e = real ? ent_sorted[ent_ptr[b] + j] : 0;
+  unsigned pk = 0;  // constant attributes (kernel positions 0..npack-1), one byte each, for k_link_pcg2
+  if (real)
+    for (int k = 0; k < npack; ++k) pk |= ((unsigned)y[e * A + perm[k]] & 0xFFu) << (8 * k);
+  const double nn = real ? entN[e] : 0.0;
+  if (fmt == 1) {
+    int *tile = tiles + (size_t)T * tile_words(A);
+    for (int k = 0; k < A; ++k) tile[k * TE + slot] = real ? y[e * A + perm[k]] : 0;  // kernel order
+    reinterpret_cast<double *>(tile + (size_t)A * TE)[slot] = nn;
+    tile[(size_t)(A + 2) * TE + slot] = (int)pk;
+  } else {
+    const int nv = qtile_nv(A, n_str, qtile_pk != 0), ng = qtile_groups(nv), qw = qtile_words(nv);
+    int *qt = qtiles + (size_t)T * qw * TE;
+    int v[4];
+    for (int g = 0; g < ng; ++g) {
+      for (int c = 0; c < 4; ++c) {
+        const int w = 4 * g + c;
+        int val = 0;
+        if (real) {
+          if (qtile_pk) val = (w < n_str) ? y[e * A + perm[A - n_str + w]] : (w == n_str ? (int)pk : 0);
+          else val = (w < A) ? y[e * A + perm[w]] : 0;
+        }
+        v[c] = val;
+      }
+      reinterpret_cast<int4 *>(qt)[(size_t)g * TE + slot] = make_int4(v[0], v[1], v[2], v[3]);
+    }
+    reinterpret_cast<double *>(qt + (size_t)ng * 4 * TE)[slot] = nn;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -290,25 +339,16 @@ __global__ void k_build_tiles(int64_t E, int A, const int *__restrict__ y, const
 __global__ void k_theta(int A, int F, uint64_t seed, long long *__restrict__ ctl, const long long *__restrict__ glob,
                         const double *__restrict__ alpha, const double *__restrict__ beta,
                         const double *__restrict__ file_size, double *__restrict__ theta,
-                        double *__restrict__ theta_prev) {
+                        double *__restrict__ theta_prev, unsigned long long *__restrict__ part, int nw) {
   if (sweep_dead(ctl)) return;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) part[i] = 0ull;  // the partial summary of the sweep starts empty
   const uint32_t it = (uint32_t)(ctl[CTL_ITER] + 1);
   for (int i = threadIdx.x; i < A * F; i += blockDim.x) {
     const int a = i / F, f = i % F;
     theta_prev[i] = theta[i];
     theta[i] = draw_theta_one(seed, it, (uint32_t)i, alpha[a], beta[a], (double)glob[i], file_size[f]);
   }
-  if (threadIdx.x == 0) { ctl[CTL_MOVED_ENT] = 0; ctl[CTL_MOVED_REC] = 0; }
-}
-// the link kernels write their draws to newlink; they become the state only if no categorical of the sweep was
-// without mass (the reference fails the task and no new state exists, IndexNonUniformDiscreteDist.scala:78-79)
-__global__ void k_commit_links(RowSet rows, const int *__restrict__ newlink, int *__restrict__ link) {
-  if (rows.dead()) return;
-  const int64_t n = rows.count();
-  GRID_STRIDE(i, n) {
-    const int64_t r = rows.row(i);
-    if (r >= 0) link[r] = newlink[r];
-  }
+  if (threadIdx.x == 0) { ctl[CTL_MOVED_ENT] = 0; ctl[CTL_MOVED_REC] = 0; ctl[CTL_WORK] = 0; }
 }
 // single rank: the partial summary is the global one
 __global__ void k_reduce_local(int nw, const long long *__restrict__ ctl, const unsigned long long *__restrict__ part,
@@ -1224,8 +1264,10 @@ struct dbl_ctx {
   DevBuf<int> iota, blk_sorted, ent_sorted, rec_key, rec_key_sorted, rec_sorted;
   DevBuf<int> ent_ptr, tile_ptr, rec_ptr, cta_ptr, cta_ptr2, tiles, qtiles;
   int qtile_pk = 0;  // quad tiles carry the packed constants (PK instantiations of k_link_pcg2)
+  bool tiles_valid[2] = {false, false};  // attribute-major / quad tiles match the current layout
   // inverted index of the block tables for the pruned PCG-I link kernel (built on demand, once per sweep)
   DevBuf<unsigned long long> inv_key_in, inv_key;
+  DevBuf<unsigned> inv_key32_in, inv_key32;
   DevBuf<int> inv_pos_in, inv_pos, inv_seg, inv_vptr;
   InvDense inv_dense;
   bool inv_use_dense = false;
@@ -1598,10 +1640,14 @@ static int bits_for(int64_t n) {
 }
 
 // CSR entity -> linked records in ascending record id (LinksIndex, GU:84-119)
-static int build_links_csr(dbl_ctx *ctx) {
+static int build_links_csr(dbl_ctx *ctx, bool commit_newlinks = false) {
   const int64_t R = ctx->R, E = ctx->E;
   size_t tb = ctx->cub_bytes;
-  k_rec_link_keys<<<grid_for(R, 256), 256, 0, ctx->stream>>>(R, ctx->link.p, ctx->rec_owned.p, (int)E, ctx->link_key.p);
+  if (commit_newlinks)  // inside a sweep: the draws of the link kernel become the links (unless the sweep was abandoned)
+    k_commit_link_keys<<<grid_for(R, 256), 256, 0, ctx->stream>>>(R, ctx->ctl(), ctx->newlink.p, ctx->link.p,
+                                                                 ctx->rec_owned.p, (int)E, ctx->link_key.p);
+  else
+    k_rec_link_keys<<<grid_for(R, 256), 256, 0, ctx->stream>>>(R, ctx->link.p, ctx->rec_owned.p, (int)E, ctx->link_key.p);
   CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, (const int *)ctx->link_key.p, ctx->link_sorted.p,
                                            (const int *)ctx->iota.p, ctx->rec_by_ent.p, (int)R, 0, bits_for(E + 1),
                                            ctx->stream));
@@ -1610,35 +1656,47 @@ static int build_links_csr(dbl_ctx *ctx) {
   return DBL_OK;
 }
 
-// group entities and records by block, build the tiled entity table (replaces the shuffle, GU:144)
-static int relayout(dbl_ctx *ctx) {
+// group entities and records by block (replaces the shuffle, GU:144); the tiled copies of the entity table are built
+// on demand by ensure_tiles().  end_of_sweep: this is the last step of a sweep -- the scan kernel also adopts the
+// partial summary as the global one (single rank) and counts the sweep.
+static int relayout(dbl_ctx *ctx, bool end_of_sweep = false) {
   const int64_t R = ctx->R, E = ctx->E;
-  const int A = ctx->A, P = ctx->P;
+  const int P = ctx->P;
   const int pb = bits_for(P + 1);
   size_t tb = ctx->cub_bytes;
-  k_ent_block_keys<<<grid_for(E, 256), 256, 0, ctx->stream>>>(E, ctx->blk.p, ctx->ent_owned.p, P, ctx->ent_key.p);
+  k_block_keys<<<grid_for(std::max(E, R), 256), 256, 0, ctx->stream>>>(E, R, ctx->blk.p, ctx->link.p, ctx->ent_owned.p,
+                                                                        ctx->rec_owned.p, ctx->rec_class.p, P,
+                                                                        ctx->ent_key.p, ctx->rec_key.p);
   CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, (const int *)ctx->ent_key.p, ctx->blk_sorted.p,
                                            (const int *)ctx->iota.p, ctx->ent_sorted.p, (int)E, 0, pb, ctx->stream));
-  k_rec_block_keys<<<grid_for(R, 256), 256, 0, ctx->stream>>>(R, ctx->link.p, ctx->blk.p, ctx->rec_owned.p,
-                                                              ctx->rec_class.p, P, ctx->rec_key.p);
   tb = ctx->cub_bytes;
   CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, (const int *)ctx->rec_key.p, ctx->rec_key_sorted.p,
                                            (const int *)ctx->iota.p, ctx->rec_sorted.p, (int)R, 0,
                                            pb + REC_CLASS_BITS, ctx->stream));
-  k_segment_ptr<<<grid_for(E + 1, 256), 256, 0, ctx->stream>>>(E, P, ctx->blk_sorted.p, ctx->ent_ptr.p);
-  k_segment_ptr<<<grid_for(R + 1, 256), 256, 0, ctx->stream>>>(R, P, ctx->rec_key_sorted.p, ctx->rec_ptr.p,
-                                                                REC_CLASS_BITS);
-  k_block_scan<<<1, 32, 0, ctx->stream>>>(P, ctx->ent_ptr.p, ctx->rec_ptr.p, ctx->tile_ptr.p, ctx->cta_ptr.p,
-                                          LINK_WARPS, ctx->cta_ptr2.p, MATCH_WARPS, ctx->ctl());
-  CUDA_TRY(cudaMemsetAsync(ctx->tiles.p, 0, ctx->tiles.n * sizeof(int), ctx->stream));
-  CUDA_TRY(cudaMemsetAsync(ctx->qtiles.p, 0, ctx->qtiles.n * sizeof(int), ctx->stream));
-  k_build_tiles<<<grid_for(E, 256), 256, 0, ctx->stream>>>(E, A, ctx->y.p, ctx->entN.p, ctx->blk_sorted.p,
-                                                           ctx->ent_sorted.p, ctx->ent_ptr.p, ctx->tile_ptr.p,
-                                                           ctx->tiles.p, ctx->perm_dev.p, P, ctx->pack_consts,
-                                                           ctx->qtiles.p, ctx->n_str, ctx->qtile_pk);
-  ctx->launches += 11;
+  k_block_ptrs<<<grid_for(std::max(E, R) + 1, 256), 256, 0, ctx->stream>>>(E, R, P, ctx->blk_sorted.p, ctx->ent_ptr.p,
+                                                                            ctx->rec_key_sorted.p, ctx->rec_ptr.p);
+  k_block_scan<<<1, 128, 0, ctx->stream>>>(P, ctx->ent_ptr.p, ctx->rec_ptr.p, ctx->tile_ptr.p, ctx->cta_ptr.p,
+                                           LINK_WARPS, ctx->cta_ptr2.p, MATCH_WARPS, ctx->ctl(),
+                                           (end_of_sweep && ctx->world <= 1) ? ctx->nw : 0, ctx->part(), ctx->glob(),
+                                           end_of_sweep ? 1 : 0);
+  ctx->launches += 9;
   ctx->inv_valid = false;
+  ctx->tiles_valid[0] = ctx->tiles_valid[1] = false;
   ctx->h_owned_ent = ctx->h_owned_rec = -1;  // changed on the device; snapshot() brings them back
+  CUDA_TRY(cudaGetLastError());
+  return DBL_OK;
+}
+
+// tiled copy of the block-sorted entity table in the format the coming link kernel reads (1: attribute-major, 2: quad)
+static int ensure_tiles(dbl_ctx *ctx, int fmt) {
+  if (ctx->tiles_valid[fmt - 1]) return DBL_OK;
+  const int64_t n_slots = (int64_t)((size_t)(ctx->E / TE) + (size_t)ctx->P + 1) * TE;
+  k_build_tiles<<<grid_for(n_slots, 256), 256, 0, ctx->stream>>>(n_slots, fmt, ctx->A, ctx->y.p, ctx->entN.p,
+                                                                 ctx->ent_sorted.p, ctx->ent_ptr.p, ctx->tile_ptr.p,
+                                                                 ctx->tiles.p, ctx->perm_dev.p, ctx->P, ctx->pack_consts,
+                                                                 ctx->qtiles.p, ctx->n_str, ctx->qtile_pk);
+  ctx->launches += 1;
+  ctx->tiles_valid[fmt - 1] = true;
   CUDA_TRY(cudaGetLastError());
   return DBL_OK;
 }
@@ -1646,7 +1704,7 @@ static int relayout(dbl_ctx *ctx) {
 // entity N / block ids / partial summary of the owned rows; in_sweep: prefix mode + distortion draws (GU:324-359)
 static int refresh_summary(dbl_ctx *ctx, bool in_sweep) {
   const int A = ctx->A, F = ctx->F;
-  CUDA_TRY(cudaMemsetAsync(ctx->part(), 0, sizeof(long long) * ctx->nw, ctx->stream));
+  if (!in_sweep) CUDA_TRY(cudaMemsetAsync(ctx->part(), 0, sizeof(long long) * ctx->nw, ctx->stream));  // else: k_theta
   EntPostParams ep;
   ep.rows = in_sweep ? rows_prefix(ctx, true) : rows_masked(ctx, true);
   ep.A = A; ep.y = ctx->y.p; ep.attrs = ctx->attrs.p; ep.tree = ctx->tree; ep.entN = ctx->entN.p; ep.blk = ctx->blk.p;
@@ -1901,24 +1959,62 @@ static int ensure_inverted_index(dbl_ctx *ctx) {
   if (ctx->inv_valid) return DBL_OK;
   const int64_t cap = ctx->E * ctx->A;
   if (cap > 0x7fffffff) { ctx->set_error("inverted index too large"); return DBL_ERR_INVALID; }
+  InvDense &dn = ctx->inv_dense;
+  dn.A = ctx->A; dn.sumV = 0;
+  for (int k = 0; k < ctx->A; ++k) { dn.voff[k] = dn.sumV; dn.sumV += ctx->h_attrs[ctx->perm[k]].V; }
+  const long long n_ids = (long long)ctx->P * dn.sumV;
+  long long dense_max = 1ll << 25;  // entries; DBL_INV_DENSE_MAX overrides (tests force the binary-search path with 0)
+  if (const char *ev = getenv("DBL_INV_DENSE_MAX")) dense_max = atoll(ev);
+  ctx->inv_use_dense = n_ids <= dense_max;
+  int vmax = 1;
+  for (int a = 0; a < ctx->A; ++a) vmax = std::max(vmax, ctx->h_attrs[a].V);
+  ctx->inv_vbits = bits_for(vmax + 1);
+  dn.vbits = ctx->inv_vbits;
+
+  if (ctx->inv_use_dense) {
+    // dense (block, attribute, value) -> posting pointers: the table is small enough (P * sum of vocabulary sizes
+    // entries).  32-bit keys (the dense id), every slot of the sorted table sorted (non-owned rows carry the
+    // sentinel id): no size depends on the shard, nothing is read back.
+    if (ctx->inv_key32.n != (size_t)cap) {
+      CUDA_TRY(ctx->inv_key32_in.alloc(cap));
+      CUDA_TRY(ctx->inv_key32.alloc(cap));
+      if (ctx->inv_pos.n != (size_t)cap) { CUDA_TRY(ctx->inv_pos_in.alloc(cap)); CUDA_TRY(ctx->inv_pos.alloc(cap)); }
+      size_t tb = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, tb, (const unsigned *)nullptr, (unsigned *)nullptr, (const int *)nullptr,
+                                      (int *)nullptr, (int)cap, 0, 32, ctx->stream);
+      if (ctx->inv_tmp_bytes < tb + 256) { ctx->inv_tmp_bytes = tb + 256; CUDA_TRY(ctx->inv_tmp.alloc(ctx->inv_tmp_bytes)); }
+    }
+    if (ctx->inv_vptr.n != (size_t)n_ids + 1) CUDA_TRY(ctx->inv_vptr.alloc((size_t)n_ids + 1));
+    k_inv_keys32<<<grid_for(cap, 256), 256, 0, ctx->stream>>>(ctx->E, ctx->A, ctx->P, dn, n_ids, ctx->y.p,
+                                                             ctx->blk_sorted.p, ctx->ent_sorted.p, ctx->ent_ptr.p,
+                                                             ctx->perm_dev.p, ctx->inv_key32_in.p, ctx->inv_pos_in.p);
+    size_t tb = ctx->inv_tmp_bytes;
+    // stable radix sort on the significant bits only: positions stay ascending inside a key
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->inv_tmp.p, tb, (const unsigned *)ctx->inv_key32_in.p, ctx->inv_key32.p,
+                                             (const int *)ctx->inv_pos_in.p, ctx->inv_pos.p, (int)cap, 0,
+                                             bits_for(n_ids + 1), ctx->stream));
+    k_inv_value_ptr32<<<grid_for(cap + 1, 256), 256, 0, ctx->stream>>>(cap, n_ids, ctx->inv_key32.p, ctx->inv_vptr.p);
+    ctx->launches += 5;
+    ctx->inv_valid = true;
+    CUDA_TRY(cudaGetLastError());
+    return DBL_OK;
+  }
+
+  // too many (block, attribute, value) ids for a dense table: 64-bit keys ((block, attribute) group | value) over the
+  // entities of owned blocks (they come first in ent_sorted), (block, attribute) segment pointers, and a binary
+  // search per record.  The owned count sizes the sort, so a sharded context reads it back once per sweep.
   int64_t owned = 0;
   { int rc = owned_entities_on_host(ctx, &owned); if (rc) return rc; }
-  // only the entities of owned blocks are indexed: they come first in ent_sorted
   const int64_t n = owned * ctx->A;
   if (ctx->inv_key.n != (size_t)cap) {
     CUDA_TRY(ctx->inv_key_in.alloc(cap));
     CUDA_TRY(ctx->inv_key.alloc(cap));
-    CUDA_TRY(ctx->inv_pos_in.alloc(cap));
-    CUDA_TRY(ctx->inv_pos.alloc(cap));
+    if (ctx->inv_pos.n != (size_t)cap) { CUDA_TRY(ctx->inv_pos_in.alloc(cap)); CUDA_TRY(ctx->inv_pos.alloc(cap)); }
     size_t tb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
                                     (const int *)nullptr, (int *)nullptr, (int)cap, 0, 64, ctx->stream);
-    ctx->inv_tmp_bytes = tb + 256;
-    CUDA_TRY(ctx->inv_tmp.alloc(ctx->inv_tmp_bytes));
+    if (ctx->inv_tmp_bytes < tb + 256) { ctx->inv_tmp_bytes = tb + 256; CUDA_TRY(ctx->inv_tmp.alloc(ctx->inv_tmp_bytes)); }
   }
-  int vmax = 1;
-  for (int a = 0; a < ctx->A; ++a) vmax = std::max(vmax, ctx->h_attrs[a].V);
-  ctx->inv_vbits = bits_for(vmax + 1);
   const int nbits = ctx->inv_vbits + bits_for((int64_t)(ctx->P + 1) * ctx->A);
   if (n > 0) {
     k_inv_keys<<<grid_for(n, 256), 256, 0, ctx->stream>>>(owned, ctx->A, ctx->P, ctx->inv_vbits,
@@ -1926,29 +2022,14 @@ static int ensure_inverted_index(dbl_ctx *ctx) {
                                                           ctx->ent_ptr.p, ctx->perm_dev.p, ctx->inv_key_in.p,
                                                           ctx->inv_pos_in.p);
     size_t tb = ctx->inv_tmp_bytes;
-    // stable radix sort on the significant bits only: positions stay ascending inside a key
     CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->inv_tmp.p, tb, (const unsigned long long *)ctx->inv_key_in.p,
                                              ctx->inv_key.p, (const int *)ctx->inv_pos_in.p, ctx->inv_pos.p, (int)n,
                                              0, std::min(64, nbits), ctx->stream));
   }
-  // dense (block, attribute, value) -> posting pointers when the table is small enough (P * sum of vocabulary
-  // sizes entries); otherwise (block, attribute) segment pointers + a binary search per record
-  InvDense &dn = ctx->inv_dense;
-  dn.A = ctx->A; dn.vbits = ctx->inv_vbits; dn.sumV = 0;
-  for (int k = 0; k < ctx->A; ++k) { dn.voff[k] = dn.sumV; dn.sumV += ctx->h_attrs[ctx->perm[k]].V; }
-  const long long n_ids = (long long)ctx->P * dn.sumV;
-  long long dense_max = 1ll << 25;  // entries; DBL_INV_DENSE_MAX overrides (tests force the binary-search path with 0)
-  if (const char *ev = getenv("DBL_INV_DENSE_MAX")) dense_max = atoll(ev);
-  ctx->inv_use_dense = n_ids <= dense_max;
-  if (ctx->inv_use_dense) {
-    if (ctx->inv_vptr.n != (size_t)n_ids + 1) CUDA_TRY(ctx->inv_vptr.alloc((size_t)n_ids + 1));
-    k_inv_value_ptr<<<grid_for(n + 1, 256), 256, 0, ctx->stream>>>(n, n_ids, dn, ctx->inv_key.p, ctx->inv_vptr.p);
-  } else {
-    const int n_groups = (ctx->P + 1) * ctx->A;
-    if (ctx->inv_seg.n != (size_t)n_groups + 1) CUDA_TRY(ctx->inv_seg.alloc((size_t)n_groups + 1));
-    k_inv_segments<<<grid_for(n + 1, 256), 256, 0, ctx->stream>>>(n, n_groups, ctx->inv_vbits, ctx->inv_key.p,
-                                                                  ctx->inv_seg.p);
-  }
+  const int n_groups = (ctx->P + 1) * ctx->A;
+  if (ctx->inv_seg.n != (size_t)n_groups + 1) CUDA_TRY(ctx->inv_seg.alloc((size_t)n_groups + 1));
+  k_inv_segments<<<grid_for(n + 1, 256), 256, 0, ctx->stream>>>(n, n_groups, ctx->inv_vbits, ctx->inv_key.p,
+                                                                ctx->inv_seg.p);
   ctx->launches += 5;
   ctx->inv_valid = true;
   CUDA_TRY(cudaGetLastError());
@@ -1992,15 +2073,24 @@ static int launch_link(dbl_ctx *ctx, int sampler) {
   lp.hslots = ctx->hslots; lp.hshift = ctx->hshift;
   if (mode != 1 && sampler == DBL_PCG_II && pcg2_kernel_fits(ctx)) {
     // persistent CTAs: a few per SM, each takes groups of LINK_WARPS records from the work counter until none is left
-    CUDA_TRY(cudaMemsetAsync(lp.work, 0, sizeof(unsigned long long), ctx->stream));
+    // (k_theta zeroed the counter; the block-level API launches the kernel once per block after one k_theta)
+    if (ctx->in_block_sweep) CUDA_TRY(cudaMemsetAsync(lp.work, 0, sizeof(unsigned long long), ctx->stream));
+    int rc = ensure_tiles(ctx, 2);
+    if (rc) return rc;
     return dispatch_pcg2(ctx, std::min(ctx->max_ctas, ctx->pcg2_grid), lp);
+  }
+  {
+    int rc = ensure_tiles(ctx, 1);  // every other link kernel reads the attribute-major tiles
+    if (rc) return rc;
   }
   if (mode == 0 && sampler != DBL_PCG_II) {  // pruned scoring through the inverted index
     int rc = ensure_inverted_index(ctx);
     if (rc) return rc;
     int64_t owned = 0;
-    rc = owned_entities_on_host(ctx, &owned);
-    if (rc) return rc;
+    if (!ctx->inv_use_dense) {
+      rc = owned_entities_on_host(ctx, &owned);
+      if (rc) return rc;
+    }
     PrunedParams pp;
     pp.lp = lp;
     pp.inv_key = ctx->inv_key.p;
@@ -2038,7 +2128,8 @@ static int launch_link(dbl_ctx *ctx, int sampler) {
 // (1) theta | summary of the previous state (State.scala:83, GU:305-320)
 static int enqueue_theta(dbl_ctx *ctx) {
   k_theta<<<1, 128, 0, ctx->stream>>>(ctx->A, ctx->F, ctx->seed, ctx->ctl(), ctx->glob(), ctx->prior.p,
-                                       ctx->prior.p + ctx->A, ctx->prior.p + 2 * ctx->A, ctx->theta(), ctx->theta_prev());
+                                       ctx->prior.p + ctx->A, ctx->prior.p + 2 * ctx->A, ctx->theta(), ctx->theta_prev(),
+                                       ctx->part(), ctx->nw);
   ctx->launches += 1;
   CUDA_TRY(cudaGetLastError());
   return DBL_OK;
@@ -2065,10 +2156,8 @@ static int update_owned(dbl_ctx *ctx, int sampler) {
   }
   ctx->launches += 1;
   CUDA_TRY(cudaGetLastError());
-  k_commit_links<<<grid_rows(ctx->R, 256), 256, 0, ctx->stream>>>(rows_prefix(ctx, false), ctx->newlink.p, ctx->link.p);
-  ctx->launches += 1;
-  // (3) entity values
-  int rc = build_links_csr(ctx);
+  // (3) entity values (the links are committed by the first kernel of the CSR build)
+  int rc = build_links_csr(ctx, true);
   if (rc) return rc;
   ValParams vp;
   vp.A = A; vp.F = F; vp.sampler = sampler; vp.seed = ctx->seed; vp.rows = rows_prefix(ctx, true);
@@ -2112,14 +2201,11 @@ static int enqueue_sweep(dbl_ctx *ctx, int sampler) {
   if (rc) return rc;
   rc = update_owned(ctx, sampler);
   if (rc) return rc;
-  rc = (ctx->world > 1) ? exchange_p2p(ctx) : adopt_local_summary(ctx);
-  if (rc) return rc;
-  rc = relayout(ctx);
-  if (rc) return rc;
-  k_finish<<<1, 32, 0, ctx->stream>>>(ctx->ctl());
-  ctx->launches += 1;
-  CUDA_TRY(cudaGetLastError());
-  return DBL_OK;
+  if (ctx->world > 1) {
+    rc = exchange_p2p(ctx);
+    if (rc) return rc;
+  }
+  return relayout(ctx, true);  // + global summary of a single rank, + iteration count
 }
 
 static int check_sweep_args(dbl_ctx *ctx, int sampler, int32_t n_sweeps) {
@@ -2139,8 +2225,9 @@ static int check_sweep_args(dbl_ctx *ctx, int sampler, int32_t n_sweeps) {
 // enqueueing it again: nothing in a sweep depends on the host, every varying quantity is read from device memory.
 static bool graph_allowed(const dbl_ctx *ctx, int sampler) {
   if (ctx->graph_mode == 1) return false;
-  // the pruned link update of a SHARDED context reads the owned-entity count back every sweep (sizes a sort)
-  if (ctx->world > 1 && sampler != DBL_PCG_II && ctx->link_mode == 0) return false;
+  // the pruned link update of a SHARDED context without the dense posting table reads the owned-entity count back
+  // every sweep (it sizes a sort)
+  if (ctx->world > 1 && sampler != DBL_PCG_II && ctx->link_mode == 0 && !ctx->inv_use_dense) return false;
   if (ctx->graph_mode == 2) return true;
   return ctx->R + ctx->E <= 400000;
 }
@@ -2350,12 +2437,12 @@ extern "C" int dbl_set_rebalance(dbl_ctx *ctx, int32_t period, double threshold)
 static int preload_kernels(dbl_ctx *ctx) {
   cudaFuncAttributes fa;
 #define DBL_LOAD(k) CUDA_TRY(cudaFuncGetAttributes(&fa, k))
-  DBL_LOAD(k_theta); DBL_LOAD(k_commit_links); DBL_LOAD(k_values); DBL_LOAD(k_entity_post); DBL_LOAD(k_dist);
+  DBL_LOAD(k_theta); DBL_LOAD(k_commit_link_keys); DBL_LOAD(k_build_tiles); DBL_LOAD(k_values); DBL_LOAD(k_entity_post); DBL_LOAD(k_dist);
   DBL_LOAD(k_reduce_local); DBL_LOAD(k_finish); DBL_LOAD(k_move_ent); DBL_LOAD(k_move_rec); DBL_LOAD(k_publish_barrier);
   DBL_LOAD(k_unpack_ent_p2p); DBL_LOAD(k_unpack_rec_p2p); DBL_LOAD(k_reduce_peers); DBL_LOAD(k_lpt);
   DBL_LOAD(k_link_generic); DBL_LOAD(k_link_match); DBL_LOAD(k_link_pruned); DBL_LOAD(k_state_hash);
   DBL_LOAD(k_gather_ent); DBL_LOAD(k_gather_rec); DBL_LOAD(k_export_ent); DBL_LOAD(k_export_rec);
-  DBL_LOAD(k_inv_keys); DBL_LOAD(k_inv_value_ptr); DBL_LOAD(k_inv_segments);
+  DBL_LOAD(k_inv_keys); DBL_LOAD(k_inv_keys32); DBL_LOAD(k_inv_value_ptr32); DBL_LOAD(k_inv_segments);
 #undef DBL_LOAD
   if (pcg2_kernel_fits(ctx)) {
     LinkParams lp;

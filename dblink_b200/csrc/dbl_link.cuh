@@ -594,6 +594,35 @@ __global__ void k_inv_value_ptr(int64_t n, long long n_ids, InvDense d, const un
   for (long long g = prev + 1; g <= cur; ++g) vptr[g] = (int)i;
 }
 
+// The same index with 32-bit keys = the dense (block, attribute, value) id itself, over ALL E * A slots of the sorted
+// entity table: rows of blocks this rank does not own get the sentinel id n_ids and sort to the end.  Nothing here
+// depends on how many entities the rank owns, so a sharded sweep needs no read-back to size the sort.
+__global__ void k_inv_keys32(int64_t E, int A, int P, InvDense d, long long n_ids, const int *__restrict__ y,
+                             const int *__restrict__ blk_sorted, const int *__restrict__ ent_sorted,
+                             const int *__restrict__ ent_ptr, const int *__restrict__ perm,
+                             unsigned *__restrict__ key, int *__restrict__ pos) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= E * A) return;
+  const int64_t i = t / A;
+  const int k = (int)(t % A);
+  const int b = blk_sorted[i];
+  if (b < P) {
+    const int e = ent_sorted[i];
+    key[t] = (unsigned)((long long)b * d.sumV + d.voff[k] + y[(int64_t)e * A + perm[k]]);
+    pos[t] = (int)(i - ent_ptr[b]);
+  } else {
+    key[t] = (unsigned)n_ids;
+    pos[t] = -1;
+  }
+}
+__global__ void k_inv_value_ptr32(int64_t n, long long n_ids, const unsigned *__restrict__ key, int *__restrict__ vptr) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  const long long cur = (i < n) ? min((long long)key[i], n_ids) : n_ids;
+  const long long prev = (i > 0) ? min((long long)key[i - 1], n_ids) : -1;
+  for (long long g = prev + 1; g <= cur; ++g) vptr[g] = (int)i;
+}
+
 __device__ __forceinline__ int64_t inv_lower_bound(const unsigned long long *__restrict__ key, int64_t lo, int64_t hi,
                                                    unsigned long long want) {
   while (lo < hi) {
