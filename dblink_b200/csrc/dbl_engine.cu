@@ -518,6 +518,11 @@ __device__ int value_update(const ValParams &p, uint32_t iter, int64_t e, int a)
       const int r = rec[i];
       const int xr = p.x[(int64_t)r * p.A + a];
       if (xr < 0) continue;
+      // an earlier record with the same value has already introduced every value of this record's similarity row
+      // (the usual case inside a cluster: duplicates agree): nothing new to add, and no pairwise searches
+      bool repeated = false;
+      for (int j = lo; j < i && !repeated; ++j) repeated = (p.x[(int64_t)rec[j] * p.A + a] == xr);
+      if (repeated) continue;
       const int nv = at.is_const ? 1 : (at.rowptr[xr + 1] - at.rowptr[xr]);
       const int *vals = at.is_const ? nullptr : (at.col + at.rowptr[xr]);
       for (int q = 0; q < nv; ++q) {

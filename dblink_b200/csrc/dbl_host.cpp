@@ -57,41 +57,49 @@ double host_similarity_from_distance(int dist, int la, int lb, double threshold,
 // AttributeIndex.scala:107-245
 // ---------------------------------------------------------------------------------------------------
 void dbl_index::finish() {
-  norm.assign(V, 1.0);
-  invnorm.assign(V, 1.0);
-  if (!is_const) {
-    for (int v = 0; v < V; ++v) {  // computeSimNormalizations, :234-245
-      double acc = 0.0;
-      int p = rowptr[v];
-      const int pe = rowptr[v + 1];
-      for (int w = 0; w < V; ++w) {
-        double e = 1.0;
-        if (p < pe && col[p] == w) e = expsim[p++];
-        acc += probs[w] * e;
+  // DBL_INDEX_GPU: "0" = host loops, "1" = GPU whenever there is one, unset = GPU for vocabularies where the O(V^2)
+  // normalisation loop matters.  Both give the same tables (same sums in the same order).
+  const char *env = std::getenv("DBL_INDEX_GPU");
+  const bool want_gpu = env ? (env[0] == '1') : (V >= 2048);
+  if (want_gpu && gpu_index_tables(V, kmax, is_const, probs, rowptr, col, expsim, norm, invnorm, pk, cdf)) {
+    // tables built on the device
+  } else {
+    norm.assign(V, 1.0);
+    invnorm.assign(V, 1.0);
+    if (!is_const) {
+      for (int v = 0; v < V; ++v) {  // computeSimNormalizations, :234-245
+        double acc = 0.0;
+        int p = rowptr[v];
+        const int pe = rowptr[v + 1];
+        for (int w = 0; w < V; ++w) {
+          double e = 1.0;
+          if (p < pe && col[p] == w) e = expsim[p++];
+          acc += probs[w] * e;
+        }
+        invnorm[v] = acc;
+        norm[v] = 1.0 / acc;
       }
-      invnorm[v] = acc;
-      norm[v] = 1.0 / acc;
     }
-  }
-  // base pmfs: weight_k(v) = probs(v) * norm(v)^k by k successive multiplications, normalised
-  // like DiscreteDist does (random/IndexNonUniformDiscreteDist.scala:66-88); cdf = running sum.
-  pk.assign((size_t)(kmax + 1) * V, 0.0);
-  cdf.assign((size_t)(kmax + 1) * V, 0.0);
-  for (int k = 0; k <= kmax; ++k) {
-    double *p = pk.data() + (size_t)k * V, *c = cdf.data() + (size_t)k * V;
-    double z = 0.0;
-    for (int v = 0; v < V; ++v) {
-      double w = probs[v];
-      if (!is_const)
-        for (int i = 0; i < k; ++i) w = w * norm[v];
-      p[v] = w;
-      z += w;
-    }
-    double run = 0.0;
-    for (int v = 0; v < V; ++v) {
-      p[v] = p[v] / z;
-      run += p[v];
-      c[v] = run;
+    // base pmfs: weight_k(v) = probs(v) * norm(v)^k by k successive multiplications, normalised
+    // like DiscreteDist does (random/IndexNonUniformDiscreteDist.scala:66-88); cdf = running sum.
+    pk.assign((size_t)(kmax + 1) * V, 0.0);
+    cdf.assign((size_t)(kmax + 1) * V, 0.0);
+    for (int k = 0; k <= kmax; ++k) {
+      double *p = pk.data() + (size_t)k * V, *c = cdf.data() + (size_t)k * V;
+      double z = 0.0;
+      for (int v = 0; v < V; ++v) {
+        double w = probs[v];
+        if (!is_const)
+          for (int i = 0; i < k; ++i) w = w * norm[v];
+        p[v] = w;
+        z += w;
+      }
+      double run = 0.0;
+      for (int v = 0; v < V; ++v) {
+        p[v] = p[v] / z;
+        run += p[v];
+        c[v] = run;
+      }
     }
   }
   phi.assign(pk.begin(), pk.begin() + V);

@@ -240,4 +240,9 @@ int host_levenshtein(const char *a, int la, const char *b, int lb);
 // GPU all-pairs candidate distances for the attribute index (dbl_index_gpu.cu); false = not applicable
 bool gpu_levenshtein_candidates(const std::vector<std::string> &values, double threshold, double max_sim,
                                 std::vector<int> &oi, std::vector<int> &oj, std::vector<int> &od);
+// norm / invnorm / pk / cdf on the device (dbl_index_gpu.cu), same values as the host loops; false = not applicable
+bool gpu_index_tables(int V, int kmax, bool is_const, const std::vector<double> &probs,
+                      const std::vector<int32_t> &rowptr, const std::vector<int32_t> &col,
+                      const std::vector<double> &expsim, std::vector<double> &norm, std::vector<double> &invnorm,
+                      std::vector<double> &pk, std::vector<double> &cdf);
 double host_similarity_from_distance(int dist, int la, int lb, double threshold, double max_sim);

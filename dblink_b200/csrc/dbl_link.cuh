@@ -19,7 +19,10 @@
 #include "dbl_internal.h"
 
 constexpr int TE = 128;          // entities per tile of the block-sorted entity table
-constexpr int LINK_WARPS = 8;    // consumer warps (= records) per CTA
+#ifndef DBL_LINK_WARPS
+#define DBL_LINK_WARPS 8
+#endif
+constexpr int LINK_WARPS = DBL_LINK_WARPS;  // consumer warps (= records) per CTA
 constexpr int MATCH_WARPS = 16;  // ... of k_link_match, which is bound by L2 -> shared-memory tile traffic
 constexpr int LINK_STAGES = 4;   // tile ring depth (8 measured: no gain)
 constexpr int LINK_MAX_UNROLL_A = 16;

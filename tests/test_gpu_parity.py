@@ -165,13 +165,15 @@ def test_block_size_many_tiles(oracle):
 
 
 def test_attribute_index_gpu_build_equals_host(monkeypatch):
-    """the all-pairs Levenshtein kernel (csrc/dbl_index_gpu.cu) and the host loop build identical tables"""
+    """the tiled bit-parallel Levenshtein kernel, the normalisation and the base-pmf kernels (csrc/dbl_index_gpu.cu)
+    build the tables the host loops build, bit for bit"""
     import dblink_b200 as D
     from dblink_b200 import synth
 
     rng = np.random.default_rng(3)
     strings, _ = synth._string_vocab(rng, 1600)
-    strings += ["", "A", "AB", "BB", "John Smith", "Jane Smith"]
+    strings += ["", "A", "AB", "BB", "John Smith", "Jane Smith", "Zo\u00eb", "Zoe", "Jos\u00e9", "Jose", "x" * 64,
+                "x" * 63 + "y", "ab" * 32, "ba" * 32, "a" * 33 + "b" * 31]
     vw = {s: float(1 + (i * 7919) % 13) for i, s in enumerate(dict.fromkeys(strings))}
     for thr in (7.0, 5.0, 0.0):
         monkeypatch.setenv("DBL_INDEX_GPU", "0")
@@ -182,6 +184,28 @@ def test_attribute_index_gpu_build_equals_host(monkeypatch):
             np.testing.assert_array_equal(host[k], dev[k])
         if thr == 0.0:
             assert len(host["col"]) > 0.5 * len(vw) ** 2  # no truncation: nearly all pairs are "similar"
+    # the chain that follows only sees the tables: a sweep with GPU-built and host-built indexes is the same sweep
+    from helpers import synth_problem
+
+    g = synth_problem(seed=2, R=300)
+    states = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("DBL_INDEX_GPU", flag)
+        rc = D.RecordsCache.build(g["values"], g["files"], g["attributes"])
+        x, file = rc.transform_records(g["values"], g["files"])
+        eng = D.GibbsEngine(rc.indexes, [a.alpha for a in g["attributes"]], [a.beta for a in g["attributes"]], None, 5,
+                            len(rc.file_ids))
+        eng.init_state(x, file)
+        eng.sweep("PCG-II", 3)
+        states.append(eng.download_state())
+        eng.close()
+    for k in ("link", "y", "z", "theta"):
+        np.testing.assert_array_equal(states[0][k], states[1][k])
+    # a string longer than 64 bytes: the device path declines, the host loop builds the index
+    vw2 = dict(list(vw.items())[:50])
+    vw2["q" * 80] = 2.0
+    monkeypatch.setenv("DBL_INDEX_GPU", "1")
+    assert D.AttributeIndex.build(vw2, "levenshtein", 7.0, 10.0).num_values == 51
 
 
 @pytest.mark.parametrize("n_const,n_str", [(1, 0), (0, 1), (3, 0), (0, 6), (7, 5), (8, 8), (14, 3)])
