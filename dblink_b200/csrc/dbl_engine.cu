@@ -496,6 +496,42 @@ __device__ int value_update(const ValParams &p, uint32_t iter, int64_t e, int a)
       }
       return base_prob(b, v) * (G - 1.0);  // GU:567 / 724
     };
+    constexpr int CH = 8;
+    if (nv <= CH) {
+      // short rows (nearly all of them): every load of the row is issued before the first is used (two levels of
+      // memory latency for the whole row instead of two per entry), and the masses are kept for the selection;
+      // the sums run in the same order as the loops below
+      int vv[CH];
+      double ee[CH], bp[CH], W[CH];
+#pragma unroll
+      for (int q = 0; q < CH; ++q) {
+        vv[q] = xr; ee[q] = 0.0;
+        if (q < nv && !at.is_const) { vv[q] = at.col[q0 + q]; ee[q] = at.expsim[q0 + q]; }
+      }
+#pragma unroll
+      for (int q = 0; q < CH; ++q) bp[q] = (q < nv) ? base_prob(b, vv[q]) : 0.0;
+#pragma unroll
+      for (int q = 0; q < CH; ++q) {
+        double G = 1.0;
+        if (at.is_const) { if (collapsed) G = G * (1.0 + extra); }
+        else G = G * ((collapsed && vv[q] == xr) ? ee[q] + extra : ee[q]);
+        W[q] = bp[q] * (G - 1.0);  // GU:567 / 724
+        if (q < nv) total += W[q];
+      }
+      if (u.u0 < 1.0 / (1.0 + total)) return base_draw(b, u.u1);  // GU:593-594
+      target = u.u1 * total;
+#pragma unroll
+      for (int q = 0; q < CH; ++q) {
+        if (q < nv && picked < 0) {
+          cum += W[q];
+          if (W[q] > 0.0) last_pos = vv[q];
+          if (cum > target) picked = vv[q];
+        }
+      }
+      if (picked < 0) picked = last_pos;
+      if (picked < 0) picked = base_draw(b, u.u1);
+      return picked;
+    }
     for (int q = 0; q < nv; ++q) {
       int v;
       total += weight(q, v);
@@ -1268,6 +1304,7 @@ struct dbl_ctx {
   // layout
   DevBuf<int> iota, blk_sorted, ent_sorted, rec_key, rec_key_sorted, rec_sorted;
   DevBuf<int> ent_ptr, tile_ptr, rec_ptr, cta_ptr, cta_ptr2, tiles, qtiles;
+  DevBuf<double> lane_sums;  // k_link_pcg2 scratch: pass-1 lane sums per chunk of every resident warp
   int qtile_pk = 0;  // quad tiles carry the packed constants (PK instantiations of k_link_pcg2)
   bool tiles_valid[2] = {false, false};  // attribute-major / quad tiles match the current layout
   // inverted index of the block tables for the pruned PCG-I link kernel (built on demand, once per sweep)
@@ -1577,6 +1614,7 @@ static int alloc_blocks(dbl_ctx *ctx) {
   const size_t max_tiles = (size_t)(ctx->E / TE) + (size_t)P + 1;
   CUDA_TRY(ctx->tiles.alloc(max_tiles * tile_words(ctx->A)));
   ctx->qtile_pk = (ctx->pack_consts && ctx->hslots == 32) ? 1 : 0;
+  if (!ctx->lane_sums.p) CUDA_TRY(ctx->lane_sums.alloc((size_t)ctx->pcg2_grid * LINK_WARPS * 1024));
   CUDA_TRY(ctx->qtiles.alloc(max_tiles * qtile_words(qtile_nv(ctx->A, ctx->n_str, ctx->qtile_pk != 0)) * TE));
   ctx->max_ctas = (int)((ctx->R + LINK_WARPS - 1) / LINK_WARPS) + P;
   return alloc_control(ctx);
@@ -2068,6 +2106,7 @@ static int launch_link(dbl_ctx *ctx, int sampler) {
   lp.tiles = ctx->tiles.p; lp.newlink = ctx->newlink.p;
   lp.qtiles = ctx->qtiles.p; lp.qtile_pk = ctx->qtile_pk;
   lp.work = reinterpret_cast<unsigned long long *>(ctx->ctl() + CTL_WORK);
+  lp.lane_sums = ctx->lane_sums.p;
   lp.status = reinterpret_cast<unsigned long long *>(ctx->ctl() + CTL_STATUS);
   lp.pairs = reinterpret_cast<unsigned long long *>(ctx->ctl() + CTL_PAIRS);
   for (int k = 0; k < A; ++k) lp.perm[k] = ctx->perm[k];

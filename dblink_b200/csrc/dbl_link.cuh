@@ -24,7 +24,10 @@ constexpr int TE = 128;          // entities per tile of the block-sorted entity
 #endif
 constexpr int LINK_WARPS = DBL_LINK_WARPS;  // consumer warps (= records) per CTA
 constexpr int MATCH_WARPS = 16;  // ... of k_link_match, which is bound by L2 -> shared-memory tile traffic
-constexpr int LINK_STAGES = 4;   // tile ring depth (8 measured: no gain)
+#ifndef DBL_LINK_STAGES
+#define DBL_LINK_STAGES 4
+#endif
+constexpr int LINK_STAGES = DBL_LINK_STAGES;  // tile ring depth
 constexpr int LINK_MAX_UNROLL_A = 16;
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -77,6 +80,7 @@ struct LinkParams {
   const int *qtiles;         // quad tiles (k_link_pcg2)
   int qtile_pk;              // quad tiles hold the non-constant values + the byte-packed constants (else all A values)
   unsigned long long *work;  // k_link_pcg2: next group of records to take (persistent CTAs); zeroed before the launch
+  double *lane_sums;         // k_link_pcg2: scratch, [CTA][consumer warp][32 chunks][32 lanes] pass-1 lane sums
   int *newlink;
   unsigned long long *status;  // &ctl[CTL_STATUS]
   unsigned long long *pairs;   // &ctl[CTL_PAIRS]
@@ -133,9 +137,11 @@ __device__ __forceinline__ int find_block(const LinkParams &p, int cta) {
 // Second half of the draw: given the check-pointed running totals Q (lane c = end of
 // chunk c) locate u*total: chunk -> lane (Kogge-Stone scan of the chunk's lane sums) -> step.  wf(j) must
 // reproduce the pass-1 weight of candidate j bit for bit (0 for j >= n).
+// lane_sums (optional): the lane sums of EVERY chunk as pass 1 produced them ([chunk][lane], this warp's scratch):
+// the chosen chunk's sums are read back instead of being recomputed (1/nchunks of pass 1 per record otherwise).
 template <class WeightFn>
 __device__ __forceinline__ int finish_draw(int lane, int n, int nsteps, int spc, int nchunks, double Q, double total,
-                                           double u, WeightFn wf) {
+                                           double u, WeightFn wf, const double *lane_sums = nullptr) {
   const double t = u * total;
   unsigned m = __ballot_sync(FULL, lane < nchunks && Q > t);
   const int chunk = m ? (__ffs(m) - 1) : (nchunks - 1);
@@ -143,7 +149,9 @@ __device__ __forceinline__ int finish_draw(int lane, int n, int nsteps, int spc,
   if (chunk == 0) r = 0.0;
   const int s0 = chunk * spc, s1 = min(s0 + spc, nsteps);
   double ls = 0.0;
-  for (int s = s0; s < s1; ++s) ls = ls + wf((s << 5) + lane);
+  if (lane_sums) ls = lane_sums[chunk * 32 + lane];
+  else
+    for (int s = s0; s < s1; ++s) ls = ls + wf((s << 5) + lane);
   double P = ls;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {

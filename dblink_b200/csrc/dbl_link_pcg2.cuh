@@ -267,6 +267,7 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, DBL_PCG2_CTAS_PER_SM) k
     // loop body without the gather of 1/n(y): straight-line code the compiler can overlap across the steps of a tile
     double run = 0.0, Q = 0.0, acc = 0.0;
     int chunk = 0, tile_in_chunk = 0;
+    double *my_sums = p.lane_sums + ((size_t)blockIdx.x * LINK_WARPS + warp) * 1024;  // [chunk][lane]
     auto pass1 = [&](auto missing_tag) {
       constexpr bool MISSING = decltype(missing_tag)::value;
       for (int t = 0; t < ntiles; ++t) {
@@ -282,6 +283,7 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, DBL_PCG2_CTAS_PER_SM) k
             acc = acc + pcg2_weight<A, NS, HC, true, PK, MISSING>(rc, p, tab, ctab, cd);
           }
           if (++tile_in_chunk == tpc || t + 1 == ntiles) {
+            my_sums[chunk * 32 + lane] = acc;  // pass 2 reads the chosen chunk's sums back (same thread, same bits)
             run = run + butterfly_sum(acc);
             if (lane == chunk) Q = run;
             ++chunk;
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, DBL_PCG2_CTAS_PER_SM) k
       return pcg2_weight<A, NS, HC, false, PK>(rc, p, tab, ctab, cd);
     };
     const U2 u = uniform2(p.seed, PH_LINK, link_iter(p), (uint32_t)r, 0u);
-    const int j = finish_draw(lane, n, nsteps, spc, nchunks, Q, run, u.u0, wf);
+    const int j = finish_draw(lane, n, nsteps, spc, nchunks, Q, run, u.u0, wf, my_sums);
     store_link(p, lane, r, b, n, j);
   }
 }

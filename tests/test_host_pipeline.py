@@ -359,3 +359,42 @@ def test_array_summaries_edge_cases(tmp_path):
     ca = aa.read_chain_arrays(path2)
     got = {frozenset(c) for c in aa.labels_to_clusters(aa.shared_most_probable_clusters(ca), ca.record_ids)}
     assert got == {frozenset("ab"), frozenset("c")}
+
+
+def test_run_txt_describes_the_project_and_its_steps(tmp_path):
+    """Run.main writes Project.mkString and ProjectSteps.mkString to run.txt before executing (Run.scala:38-43)"""
+    from dblink_b200 import config
+    from dblink_b200.project import Project
+
+    data = os.path.join(GOLDEN, "RLdata500.csv.gz")
+    out = str(tmp_path) + "/"
+    p = Project(config.parse_string(make_conf(data, out, 1, '["fname_c1"]')), base_dir="")
+    p.write_run_txt()
+    txt = open(os.path.join(out, "run.txt")).read()
+    for needle in ("Data settings", "  * The record identifier attribute is 'rec_id'", "  * There is no file identifier",
+                   "  * The matching attributes are 'by', 'bm', 'bd', 'fname_c1', 'lname_c1'",
+                   "  * 'fname_c1' (id=3) with LevenshteinSimilarityFn(threshold=7.0, maxSimilarity=10.0) and "
+                   "BetaShapeParameters(alpha=0.5, beta=50.0)",
+                   "  * KDTreePartitioner(numLevels=1, attributeIds=[3])", "  * Using randomSeed=319158",
+                   "Scheduled steps",
+                   "  * SampleStep: Evolving the chain from new initial state with sampleSize=100, burninInterval=0, "
+                   "thinningInterval=10 and sampler=PCG-I",
+                   "  * SummarizeStep: Calculating summary quantities", "  * EvaluateStep: Evaluating sMPC clusters"):
+        assert needle in txt, needle
+
+
+def test_saved_state_fingerprint_covers_seed_and_partitioner(tmp_path):
+    """a state saved under another randomSeed / populationSize / partitioner must not be continued (it would run on
+    another Philox key or another partition function)"""
+    from dblink_b200 import config
+    from dblink_b200.project import Project
+
+    data = os.path.join(GOLDEN, "RLdata500.csv.gz")
+    base = make_conf(data, str(tmp_path) + "/", 1, '["fname_c1"]')
+    fp = Project(config.parse_string(base), base_dir="").fingerprint()
+    assert Project(config.parse_string(base), base_dir="").fingerprint() == fp
+    for changed in (base.replace("randomSeed : 319158", "randomSeed : 7"),
+                    base.replace("numLevels : 1", "numLevels : 0").replace('["fname_c1"]', "[]"),
+                    base.replace('matchingAttributes : ["fname_c1"]', 'matchingAttributes : ["lname_c1"]')):
+        assert changed != base
+        assert Project(config.parse_string(changed), base_dir="").fingerprint() != fp
