@@ -496,42 +496,6 @@ __device__ int value_update(const ValParams &p, uint32_t iter, int64_t e, int a)
       }
       return base_prob(b, v) * (G - 1.0);  // GU:567 / 724
     };
-    constexpr int CH = 8;
-    if (nv <= CH) {
-      // short rows (nearly all of them): every load of the row is issued before the first is used (two levels of
-      // memory latency for the whole row instead of two per entry), and the masses are kept for the selection;
-      // the sums run in the same order as the loops below
-      int vv[CH];
-      double ee[CH], bp[CH], W[CH];
-#pragma unroll
-      for (int q = 0; q < CH; ++q) {
-        vv[q] = xr; ee[q] = 0.0;
-        if (q < nv && !at.is_const) { vv[q] = at.col[q0 + q]; ee[q] = at.expsim[q0 + q]; }
-      }
-#pragma unroll
-      for (int q = 0; q < CH; ++q) bp[q] = (q < nv) ? base_prob(b, vv[q]) : 0.0;
-#pragma unroll
-      for (int q = 0; q < CH; ++q) {
-        double G = 1.0;
-        if (at.is_const) { if (collapsed) G = G * (1.0 + extra); }
-        else G = G * ((collapsed && vv[q] == xr) ? ee[q] + extra : ee[q]);
-        W[q] = bp[q] * (G - 1.0);  // GU:567 / 724
-        if (q < nv) total += W[q];
-      }
-      if (u.u0 < 1.0 / (1.0 + total)) return base_draw(b, u.u1);  // GU:593-594
-      target = u.u1 * total;
-#pragma unroll
-      for (int q = 0; q < CH; ++q) {
-        if (q < nv && picked < 0) {
-          cum += W[q];
-          if (W[q] > 0.0) last_pos = vv[q];
-          if (cum > target) picked = vv[q];
-        }
-      }
-      if (picked < 0) picked = last_pos;
-      if (picked < 0) picked = base_draw(b, u.u1);
-      return picked;
-    }
     for (int q = 0; q < nv; ++q) {
       int v;
       total += weight(q, v);
@@ -601,7 +565,8 @@ __global__ void __launch_bounds__(128) k_values(ValParams p) {
   if (p.rows.dead()) return;
   const uint32_t iter = (uint32_t)(p.rows.ctl[CTL_ITER] + 1);
   const int64_t n = p.rows.count() * p.A;
-  GRID_STRIDE(t, n) {
+  GRID_STRIDE(t, n) {  // entity-major: the attributes of an entity share its record list (an attribute-major mapping,
+                       // one code path per warp, measured slower: 1.11 vs 0.88 ms at 1M)
     const int64_t e = p.rows.row(t / p.A);
     if (e < 0) continue;
     const int a = (int)(t % p.A);
