@@ -619,10 +619,8 @@ __global__ void __launch_bounds__(256) k_dist(DistParams p) {
           const U2 u = uniform2(p.seed, PH_DIST, iter, (uint32_t)r, (uint32_t)a);
           double pr1 = th * at.phi[xv];
           if (!at.is_const) {
-            double ediag = 1.0;
-            row_find(at, xv, xv, ediag);
             pr1 = pr1 * at.norm[xv];
-            pr1 = pr1 * ediag;
+            pr1 = pr1 * at.diag[xv];
           }
           const double pr0 = 1.0 - th;
           const double den = pr1 + pr0;
@@ -1264,7 +1262,7 @@ struct dbl_ctx {
   DevBuf<double> lpt_dscratch;
   int rebalance_period = 16;
   double rebalance_threshold = 1.03;
-  long long barrier_timeout_cycles = 20000000000LL;  // ~10 s at 1.9 GHz
+  long long barrier_timeout_cycles = 120000000000LL;  // ~60 s at 1.9 GHz: ranks may reach their first sweep far apart
 
   // layout
   DevBuf<int> iota, blk_sorted, ent_sorted, rec_key, rec_key_sorted, rec_sorted;
@@ -1379,7 +1377,7 @@ static int upload_tree(dbl_ctx *ctx, const dbl_kdtree *t) {
 static int upload_model(dbl_ctx *ctx, const dbl_model_desc *d) {
   const int A = d->num_attrs;
   ctx->h_attrs.resize(A);
-  ctx->dtab.resize((size_t)A * 10);
+  ctx->dtab.resize((size_t)A * 11);
   ctx->itab.resize((size_t)A * 4);
   auto up_d = [&](DevBuf<double> &b, const std::vector<double> &v) -> cudaError_t {
     cudaError_t e = b.alloc(v.size());
@@ -1410,7 +1408,7 @@ static int upload_model(dbl_ctx *ctx, const dbl_model_desc *d) {
       if (rehashed[a].hsize != Hmax) hash_ok = false;
       ix = &rehashed[a];
     }
-    DevBuf<double> *t = &ctx->dtab[(size_t)a * 10];
+    DevBuf<double> *t = &ctx->dtab[(size_t)a * 11];
     DevBuf<int> *ti = &ctx->itab[(size_t)a * 4];
     CUDA_TRY(up_d(t[0], ix->phi));
     CUDA_TRY(up_d(t[1], ix->probs));
@@ -1424,6 +1422,13 @@ static int upload_model(dbl_ctx *ctx, const dbl_model_desc *d) {
     CUDA_TRY(up_i(ti[0], ix->rowptr));
     CUDA_TRY(up_i(ti[1], ix->col));
     CUDA_TRY(up_d(t[9], ix->hvals));
+    {
+      std::vector<double> diag(ix->V, 1.0);  // E(v, v) (AttributeIndex.expSimOf(v, v)); 1 when the row has no entry
+      for (int v = 0; v < ix->V && !ix->is_const; ++v)
+        for (int q = ix->rowptr[v]; q < ix->rowptr[v + 1]; ++q)
+          if (ix->col[q] == v) diag[v] = ix->expsim[q];
+      CUDA_TRY(up_d(t[10], diag));
+    }
     CUDA_TRY(up_i(ti[2], ix->hkeys));
     {
       std::vector<int32_t> hm(ix->hmult.begin(), ix->hmult.end());
@@ -1434,7 +1439,7 @@ static int upload_model(dbl_ctx *ctx, const dbl_model_desc *d) {
     h.hshift = ix->hshift; h.pad0 = h.pad1 = h.pad2 = 0;
     h.hvals = t[9].p; h.hkeys = ti[2].p; h.hmult = reinterpret_cast<const unsigned *>(ti[3].p);
     h.phi = t[0].p; h.probs = t[1].p; h.norm = t[2].p; h.invnorm = t[3].p; h.pk = t[4].p; h.cdf = t[5].p;
-    h.logphi = t[6].p; h.lognorm = t[7].p; h.expsim = t[8].p;
+    h.logphi = t[6].p; h.lognorm = t[7].p; h.expsim = t[8].p; h.diag = t[10].p;
     h.rowptr = ti[0].p; h.col = ti[1].p;
   }
   CUDA_TRY(ctx->attrs.alloc(A));

@@ -46,6 +46,7 @@ struct AttrDev {
   int V, is_const, kmax, hsize;
   int hshift, pad0, pad1, pad2;
   const double *phi, *probs, *norm, *invnorm, *pk, *cdf, *logphi, *lognorm, *expsim, *hvals;
+  const double *diag;  // E(v, v) of every value (1 when the sparse row has no diagonal entry): no search per record
   const int *rowptr, *col, *hkeys;
   const unsigned *hmult;
 };
@@ -219,8 +220,7 @@ __device__ __forceinline__ void prep_rec_attr(const LinkParams &p, int r, int k,
         c.rmatch = (c.rmatch - 1.0) + 1.0;  // see k_link_pcg2: the multiplier is rebuilt from (rmatch - 1)
       } else {
         d = d * at.norm[xv];
-        double ediag = 1.0;
-        row_find(at, xv, xv, ediag);
+        const double ediag = at.diag[xv];
         c.kind = 2;
         c.rmatch = ediag + (1.0 - th) / d;
         c.rmatch = (c.rmatch - 1.0) + 1.0;

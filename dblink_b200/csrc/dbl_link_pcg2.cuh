@@ -209,9 +209,7 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, DBL_PCG2_CTAS_PER_SM) k
             rmv = 1.0 + (1.0 - th) / d;
           } else {
             d = d * at.norm[xv];
-            double ediag = 1.0;
-            row_find(at, xv, xv, ediag);
-            rmv = ediag + (1.0 - th) / d;
+            rmv = at.diag[xv] + (1.0 - th) / d;
             hmv = at.hmult[xv];
           }
         }
