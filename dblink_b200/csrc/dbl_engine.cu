@@ -260,22 +260,24 @@ __global__ void k_block_ptrs(int64_t E, int64_t R, int P, const int *__restrict_
 // (finish), unless the sweep was abandoned.
 __global__ void k_block_scan(int P, const int *__restrict__ ent_ptr, const int *__restrict__ rec_ptr,
                              int *__restrict__ tile_ptr, int *__restrict__ cta_ptr, int warps_per_cta,
-                             int *__restrict__ cta_ptr2, int warps_per_cta2, long long *__restrict__ ctl,
+                             int *__restrict__ cta_ptr2, int warps_per_cta2, int *__restrict__ cta_ptr3,
+                             int recs_per_item3, long long *__restrict__ ctl,
                              int adopt_nw, const unsigned long long *__restrict__ part, long long *__restrict__ glob,
                              int finish) {
   const bool dead = sweep_dead(ctl);
   if (adopt_nw > 0 && !dead)
     for (int i = threadIdx.x; i < adopt_nw; i += blockDim.x) glob[i] = (long long)part[i];
   if (threadIdx.x == 0) {
-    int t = 0, c = 0, c2 = 0;
+    int t = 0, c = 0, c2 = 0, c3 = 0;
     for (int b = 0; b < P; ++b) {
-      tile_ptr[b] = t; cta_ptr[b] = c; cta_ptr2[b] = c2;
+      tile_ptr[b] = t; cta_ptr[b] = c; cta_ptr2[b] = c2; cta_ptr3[b] = c3;
       t += (ent_ptr[b + 1] - ent_ptr[b] + TE - 1) / TE;
       const int nr = rec_ptr[b + 1] - rec_ptr[b];
       c += (nr + warps_per_cta - 1) / warps_per_cta;
       c2 += (nr + warps_per_cta2 - 1) / warps_per_cta2;
+      c3 += (nr + recs_per_item3 - 1) / recs_per_item3;
     }
-    tile_ptr[P] = t; cta_ptr[P] = c; cta_ptr2[P] = c2;
+    tile_ptr[P] = t; cta_ptr[P] = c; cta_ptr2[P] = c2; cta_ptr3[P] = c3;
     ctl[CTL_OWNED_ENT] = ent_ptr[P];
     ctl[CTL_OWNED_REC] = rec_ptr[P];
     if (finish && !dead) ctl[CTL_ITER] += 1;
@@ -1266,7 +1268,7 @@ struct dbl_ctx {
 
   // layout
   DevBuf<int> iota, blk_sorted, ent_sorted, rec_key, rec_key_sorted, rec_sorted;
-  DevBuf<int> ent_ptr, tile_ptr, rec_ptr, cta_ptr, cta_ptr2, tiles, qtiles;
+  DevBuf<int> ent_ptr, tile_ptr, rec_ptr, cta_ptr, cta_ptr2, cta_ptr3, tiles, qtiles;
   DevBuf<double> lane_sums;  // k_link_pcg2 scratch: pass-1 lane sums per chunk of every resident warp
   int qtile_pk = 0;  // quad tiles carry the packed constants (PK instantiations of k_link_pcg2)
   bool tiles_valid[2] = {false, false};  // attribute-major / quad tiles match the current layout
@@ -1299,7 +1301,9 @@ struct dbl_ctx {
   int64_t link_launches = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_events, event_pool;
   size_t pcg2_smem_cfg = 0, match_smem_cfg = 0;  // dynamic shared memory opted in on THIS device
+  int sm_count = 148;
   int pcg2_grid = 148 * DBL_PCG2_CTAS_PER_SM;   // persistent CTAs of k_link_pcg2
+  int pcg2_recs = LINK_WARPS;                   // records per work item of k_link_pcg2
   bool async_open = false;  // sweeps enqueued by dbl_sweep_async, not yet collected by dbl_sync
   // CUDA graphs of one sweep (launch-bound problem sizes): key = sampler * 4 + link mode
   struct SweepGraph { cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
@@ -1520,7 +1524,7 @@ extern "C" int dbl_ctx_create(dbl_ctx **out, const dbl_model_desc *d) {
   {
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device) == cudaSuccess && sms > 0)
-      ctx->pcg2_grid = sms * DBL_PCG2_CTAS_PER_SM;
+      ctx->sm_count = sms;
   }
   *out = ctx;
   CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -1579,12 +1583,20 @@ static int alloc_blocks(dbl_ctx *ctx) {
   CUDA_TRY(ctx->rec_ptr.alloc(P + 1));
   CUDA_TRY(ctx->cta_ptr.alloc(P + 1));
   CUDA_TRY(ctx->cta_ptr2.alloc(P + 1));
+  CUDA_TRY(ctx->cta_ptr3.alloc(P + 1));
   CUDA_TRY(ctx->lpt_scratch.alloc(2 * (size_t)P));
   CUDA_TRY(ctx->lpt_dscratch.alloc((size_t)P + MAX_WORLD));
   const size_t max_tiles = (size_t)(ctx->E / TE) + (size_t)P + 1;
   CUDA_TRY(ctx->tiles.alloc(max_tiles * tile_words(ctx->A)));
   ctx->qtile_pk = (ctx->pack_consts && ctx->hslots == 32) ? 1 : 0;
-  if (!ctx->lane_sums.p) CUDA_TRY(ctx->lane_sums.alloc((size_t)ctx->pcg2_grid * LINK_WARPS * 1024));
+  {
+    // work item and grid of the persistent PCG-II kernel for this model shape (see pcg2_rpw)
+    const int hc = ctx->hslots == 32 ? 32 : 0;
+    ctx->pcg2_recs = LINK_WARPS * pcg2_rpw(hc, ctx->n_str);
+    ctx->pcg2_grid = ctx->sm_count * pcg2_ctas_per_sm(hc, ctx->n_str);
+    const size_t need = (size_t)ctx->pcg2_grid * ctx->pcg2_recs * 1024;
+    if (ctx->lane_sums.n < need) CUDA_TRY(ctx->lane_sums.alloc(need));
+  }
   CUDA_TRY(ctx->qtiles.alloc(max_tiles * qtile_words(qtile_nv(ctx->A, ctx->n_str, ctx->qtile_pk != 0)) * TE));
   ctx->max_ctas = (int)((ctx->R + LINK_WARPS - 1) / LINK_WARPS) + P;
   return alloc_control(ctx);
@@ -1689,7 +1701,7 @@ static int relayout(dbl_ctx *ctx, bool end_of_sweep = false) {
   k_block_ptrs<<<grid_for(std::max(E, R) + 1, 256), 256, 0, ctx->stream>>>(E, R, P, ctx->blk_sorted.p, ctx->ent_ptr.p,
                                                                             ctx->rec_key_sorted.p, ctx->rec_ptr.p);
   k_block_scan<<<1, 128, 0, ctx->stream>>>(P, ctx->ent_ptr.p, ctx->rec_ptr.p, ctx->tile_ptr.p, ctx->cta_ptr.p,
-                                           LINK_WARPS, ctx->cta_ptr2.p, MATCH_WARPS, ctx->ctl(),
+                                           LINK_WARPS, ctx->cta_ptr2.p, MATCH_WARPS, ctx->cta_ptr3.p, ctx->pcg2_recs, ctx->ctl(),
                                            (end_of_sweep && ctx->world <= 1) ? ctx->nw : 0, ctx->part(), ctx->glob(),
                                            end_of_sweep ? 1 : 0);
   ctx->launches += 9;
@@ -2091,6 +2103,7 @@ static int launch_link(dbl_ctx *ctx, int sampler) {
     if (ctx->in_block_sweep) CUDA_TRY(cudaMemsetAsync(lp.work, 0, sizeof(unsigned long long), ctx->stream));
     int rc = ensure_tiles(ctx, 2);
     if (rc) return rc;
+    lp.cta_ptr = ctx->cta_ptr3.p;  // work items of PCG2_RECS records
     return dispatch_pcg2(ctx, std::min(ctx->max_ctas, ctx->pcg2_grid), lp);
   }
   {

@@ -145,8 +145,22 @@ __device__ __forceinline__ double pcg2_weight(const Pcg2Rec<A, NS> &rc, const Li
 #define DBL_PCG2_CTAS_PER_SM 3
 #endif
 
+// Records per consumer warp.  With 2, a lane fetches its candidate once and scores it for both records: half the
+// tile loads and half the tile traffic through shared memory per (record, candidate) pair, two independent
+// dependency chains per warp; the price is registers (96 instead of 72: 2 CTAs per SM instead of 3) and twice the
+// per-record tables in shared memory -- so it is used for the 32-slot instantiations with up to 8 non-constant
+// attributes (measured at A = 10, NS = 6: 48.4 -> 44.7 ms; three records per warp spill: 61 ms).
+#ifndef DBL_PCG2_RPW_MAX
+#define DBL_PCG2_RPW_MAX 2
+#endif
+__host__ __device__ constexpr int pcg2_rpw(int HC, int NS) { return (HC == 32 && NS >= 1 && NS <= 8) ? DBL_PCG2_RPW_MAX : 1; }
+// 3 CTAs per SM (72 registers) only where one record per warp fits them: few non-constant attributes
+__host__ __device__ constexpr int pcg2_ctas_per_sm(int HC, int NS) {
+  return (pcg2_rpw(HC, NS) >= 2 || NS > 6) ? 2 : DBL_PCG2_CTAS_PER_SM;
+}
+
 template <int A, int NS, int HC, bool PK>
-__global__ void __launch_bounds__((LINK_WARPS + 1) * 32, DBL_PCG2_CTAS_PER_SM) k_link_pcg2(LinkParams p) {
+__global__ void __launch_bounds__((LINK_WARPS + 1) * 32, pcg2_ctas_per_sm(HC, NS)) k_link_pcg2(LinkParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ int s_cta;
   if (sweep_dead(p.ctl)) return;
@@ -154,17 +168,19 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, DBL_PCG2_CTAS_PER_SM) k
   constexpr int NV = qtile_nv(A, NS, PK);
   constexpr int TW = qtile_words(NV) * TE;
   constexpr int NC = A - NS;
+  constexpr int RPW = pcg2_rpw(HC, NS);
+  constexpr int PCG2_RECS = LINK_WARPS * RPW;  // records per work item (= per "CTA" of cta_ptr)
   TileRing rg;
   rg.tiles = reinterpret_cast<int *>(smem);
   rg.full = reinterpret_cast<uint64_t *>(smem + (size_t)LINK_STAGES * TW * 4);
   rg.empty = rg.full + LINK_STAGES;
   rg.tw = TW;
   static_assert(2 * LINK_STAGES * 8 <= 128, "barrier area");
-  char *tab = reinterpret_cast<char *>(smem) + (size_t)LINK_STAGES * TW * 4 + 128 +
-              (size_t)warp * (NS > 0 ? NS : 1) * pcg2_tab_bytes(HC ? HC : p.hslots);
-  double *ctab = reinterpret_cast<double *>(reinterpret_cast<char *>(smem) + (size_t)LINK_STAGES * TW * 4 + 128 +
-                                           (size_t)LINK_WARPS * (NS > 0 ? NS : 1) * pcg2_tab_bytes(HC ? HC : p.hslots)) +
-                 warp * 16;  // PK: products of the matching constant attributes, by match mask
+  const int tabrec = (NS > 0 ? NS : 1) * pcg2_tab_bytes(HC ? HC : p.hslots);  // bytes of one record's hash tables
+  char *tab0 = reinterpret_cast<char *>(smem) + (size_t)LINK_STAGES * TW * 4 + 128 + (size_t)warp * RPW * tabrec;
+  // PK: products of the matching constant attributes, by match mask, 16 entries per record
+  double *ctab0 = reinterpret_cast<double *>(reinterpret_cast<char *>(smem) + (size_t)LINK_STAGES * TW * 4 + 128 +
+                                            (size_t)PCG2_RECS * tabrec) + warp * RPW * 16;
   ring_init(rg, LINK_WARPS);
   const int total_ctas = p.cta_ptr[p.P];
   int tbase = 0;  // tiles this CTA has streamed so far: stage and phase of the ring continue across work items
@@ -185,18 +201,24 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, DBL_PCG2_CTAS_PER_SM) k
       tbase += ntiles;
       continue;
     }
-    const int ridx = p.rec_ptr[b] + (cta - p.cta_ptr[b]) * LINK_WARPS + warp;
-    const bool active = ridx < p.rec_ptr[b + 1];
-    const int r = active ? p.rec_sorted[ridx] : -1;
 
     // ---- per-record constants: lane k prepares kernel-order attribute k, then everything is broadcast
-    Pcg2Rec<A, NS> rc;
-    {
+    Pcg2Rec<A, NS> rc[RPW];
+    int rr[RPW];
+    bool act[RPW];
+#pragma unroll
+    for (int ri = 0; ri < RPW; ++ri) {
+      const int ridx = p.rec_ptr[b] + (cta - p.cta_ptr[b]) * PCG2_RECS + warp * RPW + ri;
+      act[ri] = ridx < p.rec_ptr[b + 1];
+      rr[ri] = act[ri] ? p.rec_sorted[ridx] : -1;
+      const int r = rr[ri];
+      char *tab = tab0 + ri * tabrec;
+      double *ctab = ctab0 + ri * 16;
       int xv = -1;
       double rmv = 1.0;
       unsigned hmv = 0;
       bool is_m = false;
-      if (active && lane < A) {
+      if (act[ri] && lane < A) {
         const int a = p.perm[lane];
         const AttrDev &at = p.attrs[a];
         xv = p.x[(int64_t)r * A + a];
@@ -215,14 +237,14 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, DBL_PCG2_CTAS_PER_SM) k
         }
       }
       rmv = (rmv - 1.0) + 1.0;  // protocol: the multiplier is defined through (r - 1) (identity below ~2^53)
-      rc.mmask = __ballot_sync(FULL, is_m);
+      rc[ri].mmask = __ballot_sync(FULL, is_m);
 #pragma unroll
       for (int k = 0; k < A; ++k) {
-        rc.x[k] = __shfl_sync(FULL, xv, k);
-        rc.rm[k] = shfl_d(rmv, k);
+        rc[ri].x[k] = __shfl_sync(FULL, xv, k);
+        rc[ri].rm[k] = shfl_d(rmv, k);
       }
 #pragma unroll
-      for (int q = 0; q < NS; ++q) rc.hm[q] = __shfl_sync(FULL, hmv, A - NS + q);
+      for (int q = 0; q < NS; ++q) rc[ri].hm[q] = __shfl_sync(FULL, hmv, A - NS + q);
       // hash tables of the record's similarity rows -> shared memory (all-empty table when the value is missing);
       // the entry of the record's own value gets the exact-match multiplier (it depends on theta of the record's file)
       const int H = HC ? HC : p.hslots;
@@ -232,29 +254,30 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, DBL_PCG2_CTAS_PER_SM) k
         const AttrDev &at = p.attrs[p.perm[A - NS + q]];
         int *kd = reinterpret_cast<int *>(tab + q * pcg2_tab_bytes(H));
         double *vd = reinterpret_cast<double *>(tab + q * pcg2_tab_bytes(H) + H * 4);
-        const int xq = rc.x[A - NS + q];
-        const unsigned own = (xq >= 0) ? (((unsigned)xq * rc.hm[q]) >> hshift) : 0xFFFFFFFFu;
+        const int xq = rc[ri].x[A - NS + q];
+        const unsigned own = (xq >= 0) ? (((unsigned)xq * rc[ri].hm[q]) >> hshift) : 0xFFFFFFFFu;
         for (int i = lane; i < H; i += 32) {
           kd[i] = (xq >= 0) ? at.hkeys[(size_t)xq * H + i] : -1;
-          vd[i] = ((unsigned)i == own) ? rc.rm[A - NS + q] : ((xq >= 0) ? at.hvals[(size_t)xq * H + i] : 1.0);
+          vd[i] = ((unsigned)i == own) ? rc[ri].rm[A - NS + q] : ((xq >= 0) ? at.hvals[(size_t)xq * H + i] : 1.0);
         }
       }
-      rc.xpack = 0xFFFFFFFFu;
+      rc[ri].xpack = 0xFFFFFFFFu;
       if constexpr (PK) {
         static_assert(!PK || (NC >= 1 && NC <= 4), "PK packs 1..4 constant attributes");
 #pragma unroll
         for (int k = 0; k < NC; ++k)
-          rc.xpack = (rc.xpack & ~(0xFFu << (8 * k))) | ((unsigned)(rc.x[k] < 0 ? 0xFF : rc.x[k]) << (8 * k));
+          rc[ri].xpack = (rc[ri].xpack & ~(0xFFu << (8 * k))) |
+                         ((unsigned)(rc[ri].x[k] < 0 ? 0xFF : rc[ri].x[k]) << (8 * k));
         if (lane < 16) {
           double c = 1.0;
 #pragma unroll
           for (int k = 0; k < NC; ++k)
-            if ((lane >> k) & 1) c = c * rc.rm[k];
+            if ((lane >> k) & 1) c = c * rc[ri].rm[k];
           ctab[lane] = c;
         }
       }
-      __syncwarp();
     }
+    __syncwarp();
 
     const int nsteps = ntiles * (TE / 32);          // steps beyond the last candidate add zeros
     const int tpc = max(1, (ntiles + 31) >> 5);     // a chunk is a whole number of tiles
@@ -263,29 +286,38 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, DBL_PCG2_CTAS_PER_SM) k
 
     // ---- pass 1 over the TMA-staged tiles.  Records without a missing non-constant attribute (most of them) take a
     // loop body without the gather of 1/n(y): straight-line code the compiler can overlap across the steps of a tile
-    double run = 0.0, Q = 0.0, acc = 0.0;
+    double run[RPW], Q[RPW], acc[RPW];
+    unsigned any_missing = 0;
+#pragma unroll
+    for (int ri = 0; ri < RPW; ++ri) { run[ri] = 0.0; Q[ri] = 0.0; acc[ri] = 0.0; any_missing |= rc[ri].mmask; }
     int chunk = 0, tile_in_chunk = 0;
-    double *my_sums = p.lane_sums + ((size_t)blockIdx.x * LINK_WARPS + warp) * 1024;  // [chunk][lane]
+    double *my_sums = p.lane_sums + ((size_t)blockIdx.x * LINK_WARPS + warp) * RPW * 1024;  // [record][chunk][lane]
     auto pass1 = [&](auto missing_tag) {
       constexpr bool MISSING = decltype(missing_tag)::value;
       for (int t = 0; t < ntiles; ++t) {
         const int g = tbase + t;
         const int s = g % LINK_STAGES;
         mbar_wait(&rg.full[s], (g / LINK_STAGES) & 1);
-        if (active) {
+        if (act[0]) {  // (the second record of a warp is only there when the first is)
           const int *tile = rg.tiles + (size_t)s * TW;
 #pragma unroll
           for (int q = 0; q < TE / 32; ++q) {
             Pcg2Cand<A, NS, PK> cd;
             pcg2_load<A, NS, PK>(cd, tile, q * 32 + lane);
-            acc = acc + pcg2_weight<A, NS, HC, true, PK, MISSING>(rc, p, tab, ctab, cd);
+#pragma unroll
+            for (int ri = 0; ri < RPW; ++ri)
+              acc[ri] = acc[ri] + pcg2_weight<A, NS, HC, true, PK, MISSING>(rc[ri], p, tab0 + ri * tabrec,
+                                                                          ctab0 + ri * 16, cd);
           }
           if (++tile_in_chunk == tpc || t + 1 == ntiles) {
-            my_sums[chunk * 32 + lane] = acc;  // pass 2 reads the chosen chunk's sums back (same thread, same bits)
-            run = run + butterfly_sum(acc);
-            if (lane == chunk) Q = run;
+#pragma unroll
+            for (int ri = 0; ri < RPW; ++ri) {
+              my_sums[ri * 1024 + chunk * 32 + lane] = acc[ri];  // pass 2 reads the chosen chunk's sums back
+              run[ri] = run[ri] + butterfly_sum(acc[ri]);
+              if (lane == chunk) Q[ri] = run[ri];
+              acc[ri] = 0.0;
+            }
             ++chunk;
-            acc = 0.0;
             tile_in_chunk = 0;
           }
         }
@@ -293,27 +325,32 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, DBL_PCG2_CTAS_PER_SM) k
         if (lane == 0) mbar_arrive(&rg.empty[s]);
       }
     };
-    if (rc.mmask) pass1(std::true_type{}); else pass1(std::false_type{});
+    if (any_missing) pass1(std::true_type{}); else pass1(std::false_type{});
     tbase += ntiles;
-    if (!active) continue;
-    if (!(run > 0.0) || isinf(run)) { fail_link(p, lane, r); continue; }
 
-    // ---- pass 2 from the L2-resident copy of the tiles
-    auto wf = [&](int j) -> double {
-      if (j >= n) return 0.0;
-      Pcg2Cand<A, NS, PK> cd;
-      pcg2_load<A, NS, PK>(cd, gtiles + (size_t)(j / TE) * TW, j % TE);
-      return pcg2_weight<A, NS, HC, false, PK>(rc, p, tab, ctab, cd);
-    };
-    const U2 u = uniform2(p.seed, PH_LINK, link_iter(p), (uint32_t)r, 0u);
-    const int j = finish_draw(lane, n, nsteps, spc, nchunks, Q, run, u.u0, wf, my_sums);
-    store_link(p, lane, r, b, n, j);
+    // ---- pass 2 from the L2-resident copy of the tiles, one record after the other
+#pragma unroll
+    for (int ri = 0; ri < RPW; ++ri) {
+      if (!act[ri]) continue;
+      const int r = rr[ri];
+      if (!(run[ri] > 0.0) || isinf(run[ri])) { fail_link(p, lane, r); continue; }
+      auto wf = [&](int j) -> double {
+        if (j >= n) return 0.0;
+        Pcg2Cand<A, NS, PK> cd;
+        pcg2_load<A, NS, PK>(cd, gtiles + (size_t)(j / TE) * TW, j % TE);
+        return pcg2_weight<A, NS, HC, false, PK>(rc[ri], p, tab0 + ri * tabrec, ctab0 + ri * 16, cd);
+      };
+      const U2 u = uniform2(p.seed, PH_LINK, link_iter(p), (uint32_t)r, 0u);
+      const int j = finish_draw(lane, n, nsteps, spc, nchunks, Q[ri], run[ri], u.u0, wf, my_sums + ri * 1024);
+      store_link(p, lane, r, b, n, j);
+    }
   }
 }
 
 inline size_t pcg2_smem_bytes(int A, int NS, int H, bool PK) {
+  const size_t recs = (size_t)LINK_WARPS * pcg2_rpw(H == 32 ? 32 : 0, NS);
   return (size_t)LINK_STAGES * qtile_words(qtile_nv(A, NS, PK)) * TE * 4 + 128 +
-         (size_t)LINK_WARPS * (NS > 0 ? NS : 1) * pcg2_tab_bytes(H) + (size_t)LINK_WARPS * 16 * sizeof(double);
+         recs * (NS > 0 ? NS : 1) * pcg2_tab_bytes(H) + recs * 16 * sizeof(double);
 }
 
 // launch k_link_pcg2<A, NS, HC> for a runtime NS in [0, A]; HC = 32 (compile-time table size) when the model's
