@@ -1074,9 +1074,6 @@ __global__ void k_unpack_rec(int64_t n, const int *__restrict__ buf, int *__rest
   zmask[r] = (unsigned)m[2];
   rec_owned[r] = 1;
 }
-__global__ void k_set_words(int n, const long long *__restrict__ src, long long *__restrict__ dst) {
-  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
-}
 
 // ---- read-out of a sharded state --------------------------------------------------------------------------
 // owned rows of the state into caller-provided device buffers, zeros elsewhere (summing over ranks = full state)

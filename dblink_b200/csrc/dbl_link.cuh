@@ -589,21 +589,6 @@ struct InvDense {
   int A, sumV, vbits;
   int voff[DBL_MAX_ATTRS];
 };
-__global__ void k_inv_value_ptr(int64_t n, long long n_ids, InvDense d, const unsigned long long *__restrict__ key,
-                                int *__restrict__ vptr) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > n) return;
-  auto dense = [&](unsigned long long k) -> long long {
-    const unsigned long long g = k >> d.vbits;
-    const long long b = (long long)(g / (unsigned)d.A);
-    const int a = (int)(g % (unsigned)d.A);
-    const long long id = b * d.sumV + d.voff[a] + (long long)(k & ((1ull << d.vbits) - 1ull));
-    return id < n_ids ? id : n_ids;  // the dummy block (rows of other ranks) is not addressable
-  };
-  const long long cur = (i < n) ? dense(key[i]) : n_ids;
-  const long long prev = (i > 0) ? dense(key[i - 1]) : -1;
-  for (long long g = prev + 1; g <= cur; ++g) vptr[g] = (int)i;
-}
 
 // The same index with 32-bit keys = the dense (block, attribute, value) id itself, over ALL E * A slots of the sorted
 // entity table: rows of blocks this rank does not own get the sentinel id n_ids and sort to the end.  Nothing here
