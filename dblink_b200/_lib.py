@@ -112,6 +112,7 @@ SIGNATURES = {
     "dbl_set_graph_mode": (C.c_int, [vp, C.c_int]),
     "dbl_last_sweep_ms": (C.c_double, [vp]),
     "dbl_link_kernel_ms": (C.c_double, [vp, i64p]),
+    "dbl_phase_ms": (C.c_int64, [vp, C.POINTER(C.c_double)]),
     "dbl_version": (C.c_char_p, []),
 }
 

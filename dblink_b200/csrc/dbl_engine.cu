@@ -350,7 +350,7 @@ __global__ void k_theta(int A, int F, uint64_t seed, long long *__restrict__ ctl
     theta_prev[i] = theta[i];
     theta[i] = draw_theta_one(seed, it, (uint32_t)i, alpha[a], beta[a], (double)glob[i], file_size[f]);
   }
-  if (threadIdx.x == 0) { ctl[CTL_MOVED_ENT] = 0; ctl[CTL_MOVED_REC] = 0; ctl[CTL_WORK] = 0; }
+  if (threadIdx.x == 0) { ctl[CTL_MOVED_ENT] = 0; ctl[CTL_MOVED_REC] = 0; ctl[CTL_WORK] = 0; ctl[CTL_HEAVY] = 0; }
 }
 // single rank: the partial summary is the global one
 __global__ void k_reduce_local(int nw, const long long *__restrict__ ctl, const unsigned long long *__restrict__ part,
@@ -445,7 +445,10 @@ __device__ __forceinline__ bool in_support(const ValParams &p, const AttrDev &at
   return row_find(at, xr, v, e);
 }
 
-// new value of attribute a of entity e
+// new value of attribute a of entity e.  UB > 1: the loop over the similarity row of a single linked record fetches
+// UB candidates at a time (independent loads, same sums in the same order): for problems too small to fill the GPU
+// the kernel's time is the longest dependent-load chain of one thread, not throughput
+template <int UB>
 __device__ int value_update(const ValParams &p, uint32_t iter, int64_t e, int a) {
   const AttrDev &at = p.attrs[a];
   const bool collapsed = (p.sampler == DBL_PCG_I || p.sampler == DBL_PCG_II);
@@ -498,18 +501,62 @@ __device__ int value_update(const ValParams &p, uint32_t iter, int64_t e, int a)
       }
       return base_prob(b, v) * (G - 1.0);  // GU:567 / 724
     };
-    for (int q = 0; q < nv; ++q) {
-      int v;
-      total += weight(q, v);
-    }
-    if (u.u0 < 1.0 / (1.0 + total)) return base_draw(b, u.u1);  // GU:593-594
-    target = u.u1 * total;
-    for (int q = 0; q < nv && picked < 0; ++q) {
-      int v;
-      const double W = weight(q, v);
-      cum += W;
-      if (W > 0.0) last_pos = v;
-      if (cum > target) picked = v;
+    if constexpr (UB > 1) {
+      // same weights, same order of the sums; the loads of UB consecutive candidates are issued together
+      auto batch = [&](int q, int (&v)[UB], double (&W)[UB]) {
+        double ex[UB], bp[UB];
+#pragma unroll
+        for (int i = 0; i < UB; ++i) {
+          const int qq = min(q + i, nv - 1);
+          v[i] = at.is_const ? xr : at.col[q0 + qq];
+          ex[i] = at.is_const ? 0.0 : at.expsim[q0 + qq];
+        }
+#pragma unroll
+        for (int i = 0; i < UB; ++i) bp[i] = base_prob(b, v[i]);
+#pragma unroll
+        for (int i = 0; i < UB; ++i) {
+          double G = 1.0;
+          if (at.is_const) { if (collapsed) G = G * (1.0 + extra); }
+          else G = G * ((collapsed && v[i] == xr) ? ex[i] + extra : ex[i]);
+          W[i] = bp[i] * (G - 1.0);
+        }
+      };
+      for (int q = 0; q < nv; q += UB) {
+        int v[UB];
+        double W[UB];
+        batch(q, v, W);
+#pragma unroll
+        for (int i = 0; i < UB; ++i)
+          if (q + i < nv) total += W[i];
+      }
+      if (u.u0 < 1.0 / (1.0 + total)) return base_draw(b, u.u1);  // GU:593-594
+      target = u.u1 * total;
+      for (int q = 0; q < nv && picked < 0; q += UB) {
+        int v[UB];
+        double W[UB];
+        batch(q, v, W);
+#pragma unroll
+        for (int i = 0; i < UB; ++i)
+          if (q + i < nv && picked < 0) {
+            cum += W[i];
+            if (W[i] > 0.0) last_pos = v[i];
+            if (cum > target) picked = v[i];
+          }
+      }
+    } else {
+      for (int q = 0; q < nv; ++q) {
+        int v;
+        total += weight(q, v);
+      }
+      if (u.u0 < 1.0 / (1.0 + total)) return base_draw(b, u.u1);  // GU:593-594
+      target = u.u1 * total;
+      for (int q = 0; q < nv && picked < 0; ++q) {
+        int v;
+        const double W = weight(q, v);
+        cum += W;
+        if (W > 0.0) last_pos = v;
+        if (cum > target) picked = v;
+      }
     }
     if (picked < 0) picked = last_pos;
     if (picked < 0) picked = base_draw(b, u.u1);
@@ -539,9 +586,23 @@ __device__ int value_update(const ValParams &p, uint32_t iter, int64_t e, int a)
         double G = 1.0;
         for (int j = i; j < hi; ++j) {
           const int rj = rec[j];
-          if (p.x[(int64_t)rj * p.A + a] < 0) continue;
+          const int xj = p.x[(int64_t)rj * p.A + a];
+          if (xj < 0) continue;
           double g;
-          if (g_factor(p, at, a, rj, collapsed, v, g)) G = G * g;
+          if (!at.is_const && xj == xr) {
+            // a record observing the same value as record i (record i itself; duplicates that agree): v sits at
+            // position q of that value's row, so the search of g_factor would return exactly this element
+            const double ex = at.expsim[at.rowptr[xr] + q];
+            if (collapsed && v == xr) {
+              const double th = p.theta[a * p.F + p.file[rj]];
+              g = ex + (1.0 / th - 1.0) / (at.phi[xr] * at.norm[xr]);  // GU:557,560
+            } else {
+              g = ex;
+            }
+            G = G * g;
+          } else if (g_factor(p, at, a, rj, collapsed, v, g)) {
+            G = G * g;
+          }
         }
         const double W = base_prob(b, v) * (G - 1.0);  // GU:567 / 724
         if (pass == 0) {
@@ -563,6 +624,7 @@ __device__ int value_update(const ValParams &p, uint32_t iter, int64_t e, int a)
   return picked;
 }
 
+template <int UB>
 __global__ void __launch_bounds__(128) k_values(ValParams p) {
   if (p.rows.dead()) return;
   const uint32_t iter = (uint32_t)(p.rows.ctl[CTL_ITER] + 1);
@@ -572,7 +634,7 @@ __global__ void __launch_bounds__(128) k_values(ValParams p) {
     const int64_t e = p.rows.row(t / p.A);
     if (e < 0) continue;
     const int a = (int)(t % p.A);
-    p.y[e * p.A + a] = value_update(p, iter, e, a);
+    p.y[e * p.A + a] = value_update<UB>(p, iter, e, a);
   }
 }
 
@@ -1272,7 +1334,7 @@ struct dbl_ctx {
   // inverted index of the block tables for the pruned PCG-I link kernel (built on demand, once per sweep)
   DevBuf<unsigned long long> inv_key_in, inv_key;
   DevBuf<unsigned> inv_key32_in, inv_key32;
-  DevBuf<int> inv_pos_in, inv_pos, inv_seg, inv_vptr;
+  DevBuf<int> inv_pos_in, inv_pos, inv_seg, inv_vptr, heavy_list;
   InvDense inv_dense;
   bool inv_use_dense = false;
   DevBuf<unsigned char> inv_tmp;
@@ -1296,7 +1358,14 @@ struct dbl_ctx {
   int link_mode = 0;  // 0 auto, 1 generic kernel everywhere, 2 dense TMA kernels everywhere (no pruning)
   double last_sweep_ms = 0.0;
   int64_t link_launches = 0;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_events, event_pool;
+  // eager sweeps are timed phase by phase: events before / after the link kernel, after the value / distortion /
+  // summary kernels, after the exchange, after the re-layout
+  struct PhaseEvents { cudaEvent_t e[5]; };
+  std::vector<PhaseEvents> pending_events, event_pool;
+  PhaseEvents cur_events{};
+  bool cur_timed = false;
+  double phase_ms[4] = {0, 0, 0, 0};
+  int64_t phase_sweeps = 0;
   size_t pcg2_smem_cfg = 0, match_smem_cfg = 0;  // dynamic shared memory opted in on THIS device
   int sm_count = 148;
   int pcg2_grid = 148 * DBL_PCG2_CTAS_PER_SM;   // persistent CTAs of k_link_pcg2
@@ -1554,8 +1623,8 @@ extern "C" void dbl_ctx_destroy(dbl_ctx *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   comm_close(ctx);
   ctx->drop_graphs();
-  for (auto &pe : ctx->pending_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
-  for (auto &pe : ctx->event_pool) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
+  for (auto &pe : ctx->pending_events) for (cudaEvent_t e : pe.e) cudaEventDestroy(e);
+  for (auto &pe : ctx->event_pool) for (cudaEvent_t e : pe.e) cudaEventDestroy(e);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1589,7 +1658,7 @@ static int alloc_blocks(dbl_ctx *ctx) {
   {
     // work item and grid of the persistent PCG-II kernel for this model shape (see pcg2_rpw)
     const int hc = ctx->hslots == 32 ? 32 : 0;
-    ctx->pcg2_recs = LINK_WARPS * pcg2_rpw(hc, ctx->n_str);
+    ctx->pcg2_recs = pcg2_warps(hc, ctx->n_str) * pcg2_rpw(hc, ctx->n_str);
     ctx->pcg2_grid = ctx->sm_count * pcg2_ctas_per_sm(hc, ctx->n_str);
     const size_t need = (size_t)ctx->pcg2_grid * ctx->pcg2_recs * 1024;
     if (ctx->lane_sums.n < need) CUDA_TRY(ctx->lane_sums.alloc(need));
@@ -1756,10 +1825,14 @@ static int adopt_local_summary(dbl_ctx *ctx) {
 
 static void recycle_events(dbl_ctx *ctx) {
   for (auto &pe : ctx->pending_events) {
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, pe.first, pe.second) == cudaSuccess) {
-      ctx->link_ms += ms;
+    float ms[4] = {0.f, 0.f, 0.f, 0.f};
+    bool ok = true;
+    for (int i = 0; i < 4; ++i) ok = ok && cudaEventElapsedTime(&ms[i], pe.e[i], pe.e[i + 1]) == cudaSuccess;
+    if (ok) {
+      ctx->link_ms += ms[0];
       ctx->link_launches += 1;
+      for (int i = 0; i < 4; ++i) ctx->phase_ms[i] += ms[i];
+      ctx->phase_sweeps += 1;
     }
     ctx->event_pool.push_back(pe);
   }
@@ -2128,7 +2201,15 @@ static int launch_link(dbl_ctx *ctx, int sampler) {
     pp.inv_vptr = ctx->inv_use_dense ? ctx->inv_vptr.p : nullptr;
     pp.sumV = ctx->inv_dense.sumV;
     for (int k = 0; k < A; ++k) pp.voff[k] = ctx->inv_dense.voff[k];
+    if (ctx->heavy_list.n != (size_t)ctx->R) CUDA_TRY(ctx->heavy_list.alloc((size_t)ctx->R));
+    pp.heavy_list = ctx->heavy_list.p;
+    if (ctx->in_block_sweep)  // the block-level API launches once per block after one k_theta
+      CUDA_TRY(cudaMemsetAsync(ctx->ctl() + CTL_HEAVY, 0, sizeof(long long), ctx->stream));
     k_link_pruned<<<grid_for(ctx->R, LINK_WARPS), LINK_WARPS * 32, 0, ctx->stream>>>(pp);
+    // records whose whole block has to be scored (no must-match attribute), a CTA each; usually none: the kernel
+    // reads the count and returns
+    k_link_heavy<<<ctx->sm_count * 2, HEAVY_WARPS * 32, 0, ctx->stream>>>(pp);
+    ctx->launches += 1;
     return DBL_OK;
   }
   if (mode != 1 && sampler != DBL_PCG_II && ring <= 160 * 1024) {
@@ -2163,21 +2244,13 @@ static int enqueue_theta(dbl_ctx *ctx) {
 static int update_owned(dbl_ctx *ctx, int sampler) {
   const int A = ctx->A, F = ctx->F;
   // (2) links
-  std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
-  const bool timed = !ctx->capturing && ctx->pending_events.size() < 256;  // per-launch timing (eager sweeps only)
-  if (timed) {
-    if (!ctx->event_pool.empty()) { ev = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
-    else { CUDA_TRY(cudaEventCreate(&ev.first)); CUDA_TRY(cudaEventCreate(&ev.second)); }
-    CUDA_TRY(cudaEventRecord(ev.first, ctx->stream));
-  }
+  const bool timed = ctx->cur_timed;
+  if (timed) CUDA_TRY(cudaEventRecord(ctx->cur_events.e[0], ctx->stream));
   {
     int rc = launch_link(ctx, sampler);
-    if (rc) { if (timed) ctx->event_pool.push_back(ev); return rc; }
+    if (rc) return rc;
   }
-  if (timed) {
-    CUDA_TRY(cudaEventRecord(ev.second, ctx->stream));
-    ctx->pending_events.push_back(ev);
-  }
+  if (timed) CUDA_TRY(cudaEventRecord(ctx->cur_events.e[1], ctx->stream));
   ctx->launches += 1;
   CUDA_TRY(cudaGetLastError());
   // (3) entity values (the links are committed by the first kernel of the CSR build)
@@ -2187,7 +2260,9 @@ static int update_owned(dbl_ctx *ctx, int sampler) {
   vp.A = A; vp.F = F; vp.sampler = sampler; vp.seed = ctx->seed; vp.rows = rows_prefix(ctx, true);
   vp.attrs = ctx->attrs.p; vp.x = ctx->x.p; vp.file = ctx->file.p; vp.zmask = ctx->zmask.p; vp.theta = ctx->theta();
   vp.ent_rec_ptr = ctx->ent_rec_ptr.p; vp.rec_by_ent = ctx->rec_by_ent.p; vp.y = ctx->y.p;
-  k_values<<<grid_rows(ctx->E * A, 128), 128, 0, ctx->stream>>>(vp);
+  // latency-bound sizes (the grid does not fill the GPU a few times over): the variant with batched loads
+  if (ctx->E * A <= (int64_t)ctx->sm_count * 2048 * 4) k_values<8><<<grid_rows(ctx->E * A, 128), 128, 0, ctx->stream>>>(vp);
+  else k_values<1><<<grid_rows(ctx->E * A, 128), 128, 0, ctx->stream>>>(vp);
   ctx->launches += 1;
   // (4) N(e), new block ids, distortions, partial summary
   return refresh_summary(ctx, true);
@@ -2220,16 +2295,34 @@ static int exchange_p2p(dbl_ctx *ctx) {
   return DBL_OK;
 }
 
-static int enqueue_sweep(dbl_ctx *ctx, int sampler) {
+static int enqueue_sweep_phases(dbl_ctx *ctx, int sampler) {
+  const bool timed = ctx->cur_timed;
   int rc = enqueue_theta(ctx);
   if (rc) return rc;
   rc = update_owned(ctx, sampler);
   if (rc) return rc;
+  if (timed) CUDA_TRY(cudaEventRecord(ctx->cur_events.e[2], ctx->stream));
   if (ctx->world > 1) {
     rc = exchange_p2p(ctx);
     if (rc) return rc;
   }
-  return relayout(ctx, true);  // + global summary of a single rank, + iteration count
+  if (timed) CUDA_TRY(cudaEventRecord(ctx->cur_events.e[3], ctx->stream));
+  rc = relayout(ctx, true);  // + global summary of a single rank, + iteration count
+  if (rc) return rc;
+  if (timed) CUDA_TRY(cudaEventRecord(ctx->cur_events.e[4], ctx->stream));
+  return DBL_OK;
+}
+
+static int enqueue_sweep(dbl_ctx *ctx, int sampler) {
+  ctx->cur_timed = !ctx->capturing && ctx->pending_events.size() < 256;  // per-phase timing (eager sweeps only)
+  if (ctx->cur_timed) {
+    if (!ctx->event_pool.empty()) { ctx->cur_events = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
+    else for (cudaEvent_t &e : ctx->cur_events.e) CUDA_TRY(cudaEventCreate(&e));
+  }
+  const int rc = enqueue_sweep_phases(ctx, sampler);
+  if (ctx->cur_timed) (rc ? ctx->event_pool : ctx->pending_events).push_back(ctx->cur_events);
+  ctx->cur_timed = false;
+  return rc;
 }
 
 static int check_sweep_args(dbl_ctx *ctx, int sampler, int32_t n_sweeps) {
@@ -2461,7 +2554,7 @@ extern "C" int dbl_set_rebalance(dbl_ctx *ctx, int32_t period, double threshold)
 static int preload_kernels(dbl_ctx *ctx) {
   cudaFuncAttributes fa;
 #define DBL_LOAD(k) CUDA_TRY(cudaFuncGetAttributes(&fa, k))
-  DBL_LOAD(k_theta); DBL_LOAD(k_commit_link_keys); DBL_LOAD(k_build_tiles); DBL_LOAD(k_values); DBL_LOAD(k_entity_post); DBL_LOAD(k_dist);
+  DBL_LOAD(k_theta); DBL_LOAD(k_link_heavy); DBL_LOAD(k_commit_link_keys); DBL_LOAD(k_build_tiles); DBL_LOAD(k_values<1>); DBL_LOAD(k_values<8>); DBL_LOAD(k_entity_post); DBL_LOAD(k_dist);
   DBL_LOAD(k_reduce_local); DBL_LOAD(k_finish); DBL_LOAD(k_move_ent); DBL_LOAD(k_move_rec); DBL_LOAD(k_publish_barrier);
   DBL_LOAD(k_unpack_ent_p2p); DBL_LOAD(k_unpack_rec_p2p); DBL_LOAD(k_reduce_peers); DBL_LOAD(k_lpt);
   DBL_LOAD(k_link_generic); DBL_LOAD(k_link_match); DBL_LOAD(k_link_pruned); DBL_LOAD(k_state_hash);
@@ -2801,6 +2894,14 @@ extern "C" double dbl_link_kernel_ms(dbl_ctx *ctx, int64_t *launches) {
   ctx->link_ms = 0.0;
   ctx->link_launches = 0;
   return ms;
+}
+
+extern "C" int64_t dbl_phase_ms(dbl_ctx *ctx, double *out4) {
+  if (!ctx || !out4) return 0;
+  const int64_t n = ctx->phase_sweeps;
+  for (int i = 0; i < 4; ++i) { out4[i] = ctx->phase_ms[i]; ctx->phase_ms[i] = 0.0; }
+  ctx->phase_sweeps = 0;
+  return n;
 }
 
 extern "C" int dbl_summary(dbl_ctx *ctx, dbl_summary_head *head, int64_t *agg_dist, int64_t *rec_dist, double *theta) {

@@ -64,6 +64,7 @@ enum : int {
   CTL_EPOCH = 7,      // barriers passed (peer-to-peer exchange)
   CTL_REPLACED = 8,   // block -> rank placements adopted by the device-side LPT
   CTL_WORK = 9,       // work counter of the persistent link kernel
+  CTL_HEAVY = 10,     // records the pruned link kernel handed to k_link_heavy in the running sweep
   CTL_WORDS = 16
 };
 constexpr long long ST_ZERO_MASS = 1, ST_PEER_TIMEOUT = 2, ST_PEER_ERROR = 4;
@@ -641,7 +642,15 @@ struct PrunedParams {
   int sumV;
   int voff[DBL_MAX_ATTRS];
   const int *inv_seg;  // (P+1)*A + 1 group offsets
+  int *heavy_list;     // positions (in rec_sorted) of the records left to k_link_heavy; count in ctl[CTL_HEAVY]
 };
+
+// A record without any must-match attribute (every observed attribute distorted) has to score its whole block.  One
+// warp doing that is the tail of the whole kernel (RLdata10000 in steady state: one such record in a 2 500-entity
+// block = 0.75 ms against 25 us for everything else), so blocks beyond this size leave those records to k_link_heavy,
+// a CTA per record.
+constexpr int HEAVY_MIN_CANDIDATES = 256;
+constexpr int HEAVY_WARPS = 16;
 
 __global__ void __launch_bounds__(LINK_WARPS * 32) k_link_pruned(PrunedParams pp) {
   __shared__ RecAttr s_ra[LINK_WARPS][DBL_MAX_ATTRS];
@@ -712,6 +721,10 @@ __global__ void __launch_bounds__(LINK_WARPS * 32) k_link_pruned(PrunedParams pp
       phi = plo + bl;
     }
     __syncwarp();
+  }
+  if (nmm == 0 && n > HEAVY_MIN_CANDIDATES) {
+    if (lane == 0) pp.heavy_list[atomicAdd(reinterpret_cast<unsigned long long *>(const_cast<long long *>(p.ctl) + CTL_HEAVY), 1ull)] = (int)ridx;
+    return;
   }
   const int *mma = s_mm_attr[warp];
   const int *mmx = s_mm_x[warp];
@@ -878,5 +891,64 @@ __global__ void __launch_bounds__(LINK_WARPS * 32) k_link_pruned(PrunedParams pp
   }
   if (pick < 0) pick = last_pos >= 0 ? last_pos : (chunk * cand_per_chunk + L < n ? chunk * cand_per_chunk + L : n - 1);
   store_link(p, lane, r, b, phi - plo, pick);
+}
+
+// The records k_link_pruned left aside, one CTA each: the warps share out the chunks of the block (a chunk's lane sums
+// only depend on the chunk), warp 0 accumulates the check-points in chunk order and finishes the draw from the stored
+// sums -- the same numbers, operation for operation, as one warp walking the block.
+__global__ void __launch_bounds__(HEAVY_WARPS * 32) k_link_heavy(PrunedParams pp) {
+  __shared__ RecAttr s_ra[DBL_MAX_ATTRS];
+  __shared__ double s_sums[32 * 32];
+  const LinkParams &p = pp.lp;
+  if (sweep_dead(p.ctl)) return;
+  const int nh = (int)p.ctl[CTL_HEAVY];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int A = p.A;
+  for (int h = blockIdx.x; h < nh; h += gridDim.x) {
+    const int ridx = pp.heavy_list[h];
+    const int r = p.rec_sorted[ridx];
+    const int b = pp.rec_key_sorted[ridx] >> pp.rec_key_shift;
+    const int n = p.ent_ptr[b + 1] - p.ent_ptr[b];
+    const int ntiles = p.tile_ptr[b + 1] - p.tile_ptr[b];
+    const size_t tw = tile_words(A);
+    const int *tiles = p.tiles + (size_t)p.tile_ptr[b] * tw;
+    __syncthreads();  // the previous record's tables and sums are no longer read
+    if (warp == 0 && lane < A) {
+      RecAttr c;
+      prep_rec_attr(p, r, lane, c);
+      s_ra[lane] = c;
+    }
+    __syncthreads();
+    const int nsteps = ntiles * (TE / 32);
+    const int spc = (TE / 32) * max(1, (ntiles + 31) >> 5);
+    const int nchunks = (nsteps + spc - 1) / spc;
+    auto wf = [&](int j) -> double {
+      if (j >= n) return 0.0;
+      const int *tile = tiles + (size_t)(j / TE) * tw;
+      const int slot = j % TE;
+      return generic_weight(s_ra, A, false, tile + slot, reinterpret_cast<const double *>(tile + (size_t)A * TE)[slot]);
+    };
+    for (int c = warp; c < nchunks; c += HEAVY_WARPS) {
+      double acc = 0.0;
+      const int s1 = min((c + 1) * spc, nsteps);
+      for (int st = c * spc; st < s1; ++st) acc = acc + wf((st << 5) + lane);
+      s_sums[c * 32 + lane] = acc;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double run = 0.0, Q = 0.0;
+      for (int c = 0; c < nchunks; ++c) {
+        run = run + butterfly_sum(s_sums[c * 32 + lane]);
+        if (lane == c) Q = run;
+      }
+      if (!(run > 0.0) || isinf(run)) {
+        fail_link(p, lane, r);
+      } else {
+        const U2 u = uniform2(p.seed, PH_LINK, link_iter(p), (uint32_t)r, 0u);
+        const int j = finish_draw(lane, n, nsteps, spc, nchunks, Q, run, u.u0, wf, s_sums);
+        store_link(p, lane, r, b, n, j);
+      }
+    }
+  }
 }
 #endif  // DBL_ENGINE_TU

@@ -154,13 +154,22 @@ __device__ __forceinline__ double pcg2_weight(const Pcg2Rec<A, NS> &rc, const Li
 #define DBL_PCG2_RPW_MAX 2
 #endif
 __host__ __device__ constexpr int pcg2_rpw(int HC, int NS) { return (HC == 32 && NS >= 1 && NS <= 8) ? DBL_PCG2_RPW_MAX : 1; }
+// Consumer warps per CTA of the two-record shapes.  Every 32-byte sector a bulk copy lands in shared memory costs
+// the L1 data pipe about two wavefronts (ncu, profiles/r2o_link_pcg2.md: 2.4e9 of the kernel's 10.4e9 shared-memory
+// wavefronts are the tile writes, with that pipe 84 % busy), so more records per staged tile should help -- but ONE
+// CTA of 16 consumer warps per SM measured 45.5 ms against 44.6 ms for two CTAs of 8 (one ring per SM: every warp
+// waits for the slowest at each stage), so 8 it stays.
+#ifndef DBL_PCG2_WARPS2
+#define DBL_PCG2_WARPS2 8
+#endif
+__host__ __device__ constexpr int pcg2_warps(int HC, int NS) { return pcg2_rpw(HC, NS) >= 2 ? DBL_PCG2_WARPS2 : LINK_WARPS; }
 // 3 CTAs per SM (72 registers) only where one record per warp fits them: few non-constant attributes
 __host__ __device__ constexpr int pcg2_ctas_per_sm(int HC, int NS) {
-  return (pcg2_rpw(HC, NS) >= 2 || NS > 6) ? 2 : DBL_PCG2_CTAS_PER_SM;
+  return pcg2_rpw(HC, NS) >= 2 ? (pcg2_warps(HC, NS) > 8 ? 1 : 2) : (NS > 6 ? 2 : DBL_PCG2_CTAS_PER_SM);
 }
 
 template <int A, int NS, int HC, bool PK>
-__global__ void __launch_bounds__((LINK_WARPS + 1) * 32, pcg2_ctas_per_sm(HC, NS)) k_link_pcg2(LinkParams p) {
+__global__ void __launch_bounds__((pcg2_warps(HC, NS) + 1) * 32, pcg2_ctas_per_sm(HC, NS)) k_link_pcg2(LinkParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ int s_cta;
   if (sweep_dead(p.ctl)) return;
@@ -169,7 +178,8 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, pcg2_ctas_per_sm(HC, NS
   constexpr int TW = qtile_words(NV) * TE;
   constexpr int NC = A - NS;
   constexpr int RPW = pcg2_rpw(HC, NS);
-  constexpr int PCG2_RECS = LINK_WARPS * RPW;  // records per work item (= per "CTA" of cta_ptr)
+  constexpr int WARPS = pcg2_warps(HC, NS);   // consumer warps; warp WARPS is the producer
+  constexpr int PCG2_RECS = WARPS * RPW;      // records per work item (= per "CTA" of cta_ptr)
   TileRing rg;
   rg.tiles = reinterpret_cast<int *>(smem);
   rg.full = reinterpret_cast<uint64_t *>(smem + (size_t)LINK_STAGES * TW * 4);
@@ -181,7 +191,7 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, pcg2_ctas_per_sm(HC, NS
   // PK: products of the matching constant attributes, by match mask, 16 entries per record
   double *ctab0 = reinterpret_cast<double *>(reinterpret_cast<char *>(smem) + (size_t)LINK_STAGES * TW * 4 + 128 +
                                             (size_t)PCG2_RECS * tabrec) + warp * RPW * 16;
-  ring_init(rg, LINK_WARPS);
+  ring_init(rg, WARPS);
   const int total_ctas = p.cta_ptr[p.P];
   int tbase = 0;  // tiles this CTA has streamed so far: stage and phase of the ring continue across work items
 
@@ -196,7 +206,7 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, pcg2_ctas_per_sm(HC, NS
     const int ntiles = p.tile_ptr[b + 1] - p.tile_ptr[b];
     const int *gtiles = p.qtiles + (size_t)p.tile_ptr[b] * TW;
 
-    if (warp == LINK_WARPS) {  // producer warp
+    if (warp == WARPS) {  // producer warp
       if (lane == 0) ring_produce<true>(rg, gtiles, ntiles, tbase);
       tbase += ntiles;
       continue;
@@ -291,7 +301,7 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, pcg2_ctas_per_sm(HC, NS
 #pragma unroll
     for (int ri = 0; ri < RPW; ++ri) { run[ri] = 0.0; Q[ri] = 0.0; acc[ri] = 0.0; any_missing |= rc[ri].mmask; }
     int chunk = 0, tile_in_chunk = 0;
-    double *my_sums = p.lane_sums + ((size_t)blockIdx.x * LINK_WARPS + warp) * RPW * 1024;  // [record][chunk][lane]
+    double *my_sums = p.lane_sums + ((size_t)blockIdx.x * WARPS + warp) * RPW * 1024;  // [record][chunk][lane]
     auto pass1 = [&](auto missing_tag) {
       constexpr bool MISSING = decltype(missing_tag)::value;
       for (int t = 0; t < ntiles; ++t) {
@@ -348,7 +358,7 @@ __global__ void __launch_bounds__((LINK_WARPS + 1) * 32, pcg2_ctas_per_sm(HC, NS
 }
 
 inline size_t pcg2_smem_bytes(int A, int NS, int H, bool PK) {
-  const size_t recs = (size_t)LINK_WARPS * pcg2_rpw(H == 32 ? 32 : 0, NS);
+  const size_t recs = (size_t)pcg2_warps(H == 32 ? 32 : 0, NS) * pcg2_rpw(H == 32 ? 32 : 0, NS);
   return (size_t)LINK_STAGES * qtile_words(qtile_nv(A, NS, PK)) * TE * 4 + 128 +
          recs * (NS > 0 ? NS : 1) * pcg2_tab_bytes(H) + recs * 16 * sizeof(double);
 }
@@ -368,7 +378,7 @@ int pcg2_launch_one(int grid, cudaStream_t stream, const LinkParams &lp, size_t 
     cudaFuncAttributes fa;
     return (int)cudaFuncGetAttributes(&fa, k_link_pcg2<A, NS, HC, PK>);
   }
-  k_link_pcg2<A, NS, HC, PK><<<grid, (LINK_WARPS + 1) * 32, smem, stream>>>(lp);
+  k_link_pcg2<A, NS, HC, PK><<<grid, (pcg2_warps(HC, NS) + 1) * 32, smem, stream>>>(lp);
   return (int)cudaGetLastError();
 }
 

@@ -301,6 +301,9 @@ class ShardedGibbs:
     def link_kernel_ms(self):
         return self.eng.link_kernel_ms()
 
+    def phase_ms(self):
+        return self.eng.phase_ms()
+
     @property
     def iteration(self):
         return self.eng.iteration

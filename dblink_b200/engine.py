@@ -458,6 +458,13 @@ class GibbsEngine:
         ms = _lib.load().dbl_link_kernel_ms(self._h, C.byref(n))
         return ms, n.value
 
+    def phase_ms(self):
+        """Per-phase CUDA-event time of the eager sweeps since the last call: ({phase: ms per sweep}, sweeps)."""
+        out = (C.c_double * 4)()
+        n = _lib.load().dbl_phase_ms(self._h, out)
+        names = ("link", "values_distortions_summary", "exchange", "relayout")
+        return {k: (out[i] / n if n else 0.0) for i, k in enumerate(names)}, int(n)
+
 
 def combine_state_hash(ent_hash, rec_hash, theta, iteration):
     """One hex string for a whole state: the (summed) row fingerprints, theta's bits and the iteration."""

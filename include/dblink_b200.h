@@ -260,6 +260,10 @@ int dbl_set_graph_mode(dbl_ctx *, int mode);
 double dbl_last_sweep_ms(const dbl_ctx *);
 /* CUDA-event time (ms) spent in the link-scoring kernel since the last call; resets the accumulator */
 double dbl_link_kernel_ms(dbl_ctx *, int64_t *launches);
+/* CUDA-event time (ms) of the eagerly enqueued sweeps since the last call, by phase: out4 = {link update GU:186-199,
+ * entity values + distortions + partial summary GU:201-210, exchange of moved clusters + summary reduction GU:144 (0
+ * on one rank), re-layout by block}; returns the number of sweeps summed; resets the accumulators */
+int64_t dbl_phase_ms(dbl_ctx *, double *out4);
 const char *dbl_version(void);
 
 #ifdef __cplusplus

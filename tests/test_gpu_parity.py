@@ -79,6 +79,35 @@ def test_random_states(oracle, sampler):
         assert_same_state(eng, st)
 
 
+@pytest.mark.parametrize("sampler", ["PCG-I", "Gibbs", "Gibbs-Sequential"])
+def test_records_without_a_must_match_attribute(oracle, sampler):
+    """every observed attribute of a record distorted: nothing prunes its candidates, the whole block is scored.  In
+    blocks beyond 256 entities the pruned kernel hands such records to k_link_heavy (a CTA per record); same draws"""
+    g = synth_problem(seed=21, R=1500, n_files=2, missing=0.05, distortion=0.2)
+    eng, rc, x, file = product_setup(g, 5)
+    m, st0, tree, ox, ofile = oracle_setup(oracle, g, 5)
+    Vs = [ix.num_values for ix in rc.indexes]
+    rng = np.random.default_rng(77)
+    for trial, E in enumerate([1500, 700]):
+        y, link, z = random_state(rng, x, E, Vs)
+        heavy = rng.choice(x.shape[0], 120, replace=False)
+        z[heavy] = 1
+        theta = rng.uniform(0.01, 0.3, (len(Vs), 2))
+        eng.upload_state(x, file, z, link, y, theta, iteration=3 * trial)
+        st = oracle.State.from_arrays(m, x, file, z, link, y, theta, 3 * trial)
+        for mode in (0, 2):  # pruned + heavy kernels / dense kernel
+            eng.upload_state(x, file, z, link, y, theta, iteration=3 * trial)
+            eng.set_link_mode(mode)
+            eng.sweep(sampler, 1)
+            if mode == 0:
+                assert st.sweep(oracle.SAMPLERS[sampler], 1) == 0
+            assert_same_state(eng, st)
+        eng.set_link_mode(0)
+        eng.sweep(sampler, 2)
+        assert st.sweep(oracle.SAMPLERS[sampler], 2) == 0
+        assert_same_state(eng, st)
+
+
 @pytest.mark.parametrize("pop", [150, 450, 1000])
 def test_population_sizes(oracle, pop):
     """populationSize below / above the number of records (State.scala:221-250, 296-301)"""
