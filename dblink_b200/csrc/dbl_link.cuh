@@ -411,9 +411,9 @@ struct TileRing {
   int tw;              // words per tile
 };
 
-__device__ __forceinline__ void ring_init(const TileRing &rg, int consumers) {
+__device__ __forceinline__ void ring_init(const TileRing &rg, int consumers, int producers = 1) {
   if (threadIdx.x == 0) {
-    for (int s = 0; s < LINK_STAGES; ++s) { mbar_init(&rg.full[s], 1); mbar_init(&rg.empty[s], consumers); }
+    for (int s = 0; s < LINK_STAGES; ++s) { mbar_init(&rg.full[s], producers); mbar_init(&rg.empty[s], consumers); }
     mbar_fence_init();
   }
   __syncthreads();
@@ -434,6 +434,22 @@ __device__ __forceinline__ void ring_produce(const TileRing &rg, const int *gsrc
     }
     mbar_arrive_expect_tx(&rg.full[s], bytes);
     tma_load_1d(rg.tiles + (size_t)s * rg.tw, gsrc + (size_t)t * rg.tw, bytes, &rg.full[s]);
+  }
+}
+
+// The same ring filled with 16-byte cp.async copies by all 32 lanes of the producer warp (SASS LDGSTS) instead of one
+// bulk copy per tile: every lane's copies arrive on the stage's barrier (initialised with 32 producers).
+__device__ __forceinline__ void ring_produce_ldgsts(const TileRing &rg, const int *gsrc, int ntiles, int base, int lane) {
+  const int vecs = rg.tw / 4;  // 16-byte pieces per tile
+  for (int t = 0; t < ntiles; ++t) {
+    const int g = base + t;
+    const int s = g % LINK_STAGES;
+    if (g >= LINK_STAGES) mbar_wait_relaxed(&rg.empty[s], ((g / LINK_STAGES) - 1) & 1);
+    const int *src = gsrc + (size_t)t * rg.tw;
+    int *dst = rg.tiles + (size_t)s * rg.tw;
+    for (int i = lane; i < vecs; i += 32)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + i * 4)), "l"(src + i * 4) : "memory");
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&rg.full[s])) : "memory");
   }
 }
 

@@ -191,7 +191,10 @@ __global__ void __launch_bounds__((pcg2_warps(HC, NS) + 1) * 32, pcg2_ctas_per_s
   // PK: products of the matching constant attributes, by match mask, 16 entries per record
   double *ctab0 = reinterpret_cast<double *>(reinterpret_cast<char *>(smem) + (size_t)LINK_STAGES * TW * 4 + 128 +
                                             (size_t)PCG2_RECS * tabrec) + warp * RPW * 16;
-  ring_init(rg, WARPS);
+#ifndef DBL_PCG2_LDGSTS
+#define DBL_PCG2_LDGSTS 0
+#endif
+  ring_init(rg, WARPS, DBL_PCG2_LDGSTS ? 32 : 1);
   const int total_ctas = p.cta_ptr[p.P];
   int tbase = 0;  // tiles this CTA has streamed so far: stage and phase of the ring continue across work items
 
@@ -207,7 +210,11 @@ __global__ void __launch_bounds__((pcg2_warps(HC, NS) + 1) * 32, pcg2_ctas_per_s
     const int *gtiles = p.qtiles + (size_t)p.tile_ptr[b] * TW;
 
     if (warp == WARPS) {  // producer warp
+#if DBL_PCG2_LDGSTS
+      ring_produce_ldgsts(rg, gtiles, ntiles, tbase, lane);
+#else
       if (lane == 0) ring_produce<true>(rg, gtiles, ntiles, tbase);
+#endif
       tbase += ntiles;
       continue;
     }

@@ -163,6 +163,23 @@ def test_tiny_and_degenerate_inputs(oracle):
         assert_same_state(eng, st)
 
 
+def test_phase_times_add_up():
+    """dbl_phase_ms: CUDA-event time of the eagerly enqueued sweeps by phase; the phases tile the sweep"""
+    g = synth_problem(seed=4, R=2000)
+    eng, rc, x, file = product_setup(g, 3, 2, (0, 1))
+    eng.set_graph_mode(1)
+    eng.sweep("PCG-II", 2)
+    eng.phase_ms()
+    eng.sweep("PCG-II", 5)
+    ph, n = eng.phase_ms()
+    assert n == 5
+    assert ph["link"] > 0 and ph["values_distortions_summary"] > 0 and ph["relayout"] > 0
+    assert ph["exchange"] < 0.05  # one rank: nothing to exchange
+    assert sum(ph.values()) * n <= eng.last_sweep_ms() * 1.02
+    assert sum(ph.values()) * n >= eng.last_sweep_ms() * 0.5
+    assert eng.phase_ms()[1] == 0  # the call resets the accumulators
+
+
 def test_error_conventions():
     import dblink_b200 as D
 
