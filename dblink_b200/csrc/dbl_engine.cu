@@ -211,19 +211,21 @@ __global__ void k_block_keys(int64_t E, int64_t R, const int *__restrict__ blk, 
                              int *__restrict__ rec_key) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < E) ent_key[i] = ent_owned[i] ? blk[i] : P;
-  if (i < R) rec_key[i] = rec_owned[i] ? ((blk[link[i]] << REC_CLASS_BITS) | rec_class[i]) : (P << REC_CLASS_BITS);
+  if (i < R)  // not owned: behind every owned key, spread over the class bits (see sentinel_spread)
+    rec_key[i] = rec_owned[i] ? ((blk[link[i]] << REC_CLASS_BITS) | rec_class[i])
+                              : ((P << REC_CLASS_BITS) | (int)(i & ((1 << REC_CLASS_BITS) - 1)));
 }
 __global__ void k_rec_link_keys(int64_t R, const int *__restrict__ link, const unsigned char *__restrict__ rec_owned,
-                                int E, int *__restrict__ key) {
+                                int E, int spread, int *__restrict__ key) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < R) key[r] = rec_owned[r] ? link[r] : E;
+  if (r < R) key[r] = rec_owned[r] ? link[r] : E + (int)(r % spread);  // see sentinel_spread
 }
 // the same inside a sweep, fused with the commit of the link draws: the link kernels wrote them to newlink; they
 // become the state only if no categorical of the sweep was without mass (the reference fails the task and no new
 // state exists, IndexNonUniformDiscreteDist.scala:78-79)
 __global__ void k_commit_link_keys(int64_t R, const long long *__restrict__ ctl, const int *__restrict__ newlink,
                                    int *__restrict__ link, const unsigned char *__restrict__ rec_owned, int E,
-                                   int *__restrict__ key) {
+                                   int spread, int *__restrict__ key) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
   int l = link[r];
@@ -232,7 +234,7 @@ __global__ void k_commit_link_keys(int64_t R, const long long *__restrict__ ctl,
     l = newlink[r];
     link[r] = l;
   }
-  key[r] = own ? l : E;
+  key[r] = own ? l : E + (int)(r % spread);  // see sentinel_spread
 }
 // offsets from sorted keys: ptr[k] = first position whose key is >= k, for k = 0..n_keys (keys beyond the data
 // point at n).  One pass over the sorted array; replaces an atomic histogram + scan.
@@ -1730,18 +1732,32 @@ static int bits_for(int64_t n) {
   return b;
 }
 
+// Sort keys of rows a shard does not own must sort behind every real key.  One sentinel value would put 7/8 of the
+// items of an 8-rank shard into the same radix bin, and a radix sort serialises on a bin that takes everything; so
+// they are spread over the unused top of the key range: `spread` values above n_keys, in a key of `bits` bits.
+static void sentinel_spread(int64_t n_keys, int world, int *bits, long long *spread) {
+  int b = bits_for(n_keys + 1);
+  long long sp = ((long long)1 << b) - n_keys;
+  if (world > 1 && sp < 256) { ++b; sp = ((long long)1 << b) - n_keys; }
+  *bits = b;
+  *spread = world > 1 ? sp : 1;
+}
+
 // CSR entity -> linked records in ascending record id (LinksIndex, GU:84-119)
 static int build_links_csr(dbl_ctx *ctx, bool commit_newlinks = false) {
   const int64_t R = ctx->R, E = ctx->E;
   size_t tb = ctx->cub_bytes;
+  int bits;
+  long long spread;
+  sentinel_spread(E, ctx->world, &bits, &spread);
   if (commit_newlinks)  // inside a sweep: the draws of the link kernel become the links (unless the sweep was abandoned)
     k_commit_link_keys<<<grid_for(R, 256), 256, 0, ctx->stream>>>(R, ctx->ctl(), ctx->newlink.p, ctx->link.p,
-                                                                 ctx->rec_owned.p, (int)E, ctx->link_key.p);
+                                                                 ctx->rec_owned.p, (int)E, (int)spread, ctx->link_key.p);
   else
-    k_rec_link_keys<<<grid_for(R, 256), 256, 0, ctx->stream>>>(R, ctx->link.p, ctx->rec_owned.p, (int)E, ctx->link_key.p);
+    k_rec_link_keys<<<grid_for(R, 256), 256, 0, ctx->stream>>>(R, ctx->link.p, ctx->rec_owned.p, (int)E, (int)spread,
+                                                              ctx->link_key.p);
   CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, (const int *)ctx->link_key.p, ctx->link_sorted.p,
-                                           (const int *)ctx->iota.p, ctx->rec_by_ent.p, (int)R, 0, bits_for(E + 1),
-                                           ctx->stream));
+                                           (const int *)ctx->iota.p, ctx->rec_by_ent.p, (int)R, 0, bits, ctx->stream));
   k_segment_ptr<<<grid_for(R + 1, 256), 256, 0, ctx->stream>>>(R, (int)E, ctx->link_sorted.p, ctx->ent_rec_ptr.p);
   ctx->launches += 3;
   return DBL_OK;
@@ -2080,14 +2096,17 @@ static int ensure_inverted_index(dbl_ctx *ctx) {
       if (ctx->inv_tmp_bytes < tb + 256) { ctx->inv_tmp_bytes = tb + 256; CUDA_TRY(ctx->inv_tmp.alloc(ctx->inv_tmp_bytes)); }
     }
     if (ctx->inv_vptr.n != (size_t)n_ids + 1) CUDA_TRY(ctx->inv_vptr.alloc((size_t)n_ids + 1));
-    k_inv_keys32<<<grid_for(cap, 256), 256, 0, ctx->stream>>>(ctx->E, ctx->A, ctx->P, dn, n_ids, ctx->y.p,
+    int ibits;
+    long long ispread;
+    sentinel_spread(n_ids, ctx->world, &ibits, &ispread);
+    k_inv_keys32<<<grid_for(cap, 256), 256, 0, ctx->stream>>>(ctx->E, ctx->A, ctx->P, dn, n_ids, ispread, ctx->y.p,
                                                              ctx->blk_sorted.p, ctx->ent_sorted.p, ctx->ent_ptr.p,
                                                              ctx->perm_dev.p, ctx->inv_key32_in.p, ctx->inv_pos_in.p);
     size_t tb = ctx->inv_tmp_bytes;
     // stable radix sort on the significant bits only: positions stay ascending inside a key
     CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->inv_tmp.p, tb, (const unsigned *)ctx->inv_key32_in.p, ctx->inv_key32.p,
                                              (const int *)ctx->inv_pos_in.p, ctx->inv_pos.p, (int)cap, 0,
-                                             bits_for(n_ids + 1), ctx->stream));
+                                             ibits, ctx->stream));
     k_inv_value_ptr32<<<grid_for(cap + 1, 256), 256, 0, ctx->stream>>>(cap, n_ids, ctx->inv_key32.p, ctx->inv_vptr.p);
     ctx->launches += 5;
     ctx->inv_valid = true;
@@ -2346,7 +2365,11 @@ static bool graph_allowed(const dbl_ctx *ctx, int sampler) {
   // every sweep (it sizes a sort)
   if (ctx->world > 1 && sampler != DBL_PCG_II && ctx->link_mode == 0 && !ctx->inv_use_dense) return false;
   if (ctx->graph_mode == 2) return true;
-  return ctx->R + ctx->E <= 400000;
+  // PCG-II at large sizes: tens of milliseconds of GPU time per sweep hide the ~35 launches.  The pruned samplers
+  // do not: their sweep is ~3 ms of GPU time at 1 M records and shrinks with the rank count while the host's share
+  // (launches, CUB set-up) does not -- measured on 8 GPUs with 8 processes on a 16-CPU quota: 280 sweeps/s eagerly
+  // (430 on 4 GPUs), host-bound.
+  return ctx->R + ctx->E <= 400000 || sampler != DBL_PCG_II;
 }
 
 static int run_sweeps(dbl_ctx *ctx, int sampler, int32_t n_sweeps) {
