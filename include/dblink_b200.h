@@ -253,8 +253,9 @@ int dbl_set_link_mode(dbl_ctx *, int mode);
  * back to the generic kernel runs an order of magnitude slower: benches and tests assert what they expect. */
 int dbl_link_kernel(const dbl_ctx *, int sampler);
 /* How dbl_sweep / dbl_sweep_async enqueue several sweeps: 0 = automatic (problems small enough to be bound by kernel
- * launches replay a captured CUDA graph of one sweep), 1 = every sweep enqueued kernel by kernel (and the link kernel
- * timed per launch, dbl_link_kernel_ms), 2 = graphs whenever possible.  Same chain either way. */
+ * launches, and the index-pruned samplers at every size, replay a captured CUDA graph of one sweep), 1 = every sweep
+ * enqueued kernel by kernel (and timed phase by phase, dbl_link_kernel_ms / dbl_phase_ms), 2 = graphs whenever
+ * possible.  Same chain either way. */
 int dbl_set_graph_mode(dbl_ctx *, int mode);
 /* CUDA-event time (ms) of the last dbl_sweep call, first operation to last operation on the context's stream */
 double dbl_last_sweep_ms(const dbl_ctx *);
