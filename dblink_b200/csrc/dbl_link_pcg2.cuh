@@ -85,6 +85,11 @@ __device__ __forceinline__ void pcg2_load(Pcg2Cand<A, NS, PK> &c, const int *til
 #ifndef DBL_PCG2_VOTE
 #define DBL_PCG2_VOTE 0
 #endif
+// PK kernels: 1 = the product of the matching constant attributes comes from the record's 16-entry table in shared
+// memory (index from a SWAR byte compare), 0 = predicated multiplies
+#ifndef DBL_PCG2_CTAB
+#define DBL_PCG2_CTAB 1
+#endif
 template <int A, int NS, int HC, bool CONVERGED, bool PK, bool MISSING = true>
 __device__ __forceinline__ double pcg2_weight(const Pcg2Rec<A, NS> &rc, const LinkParams &p, const char *tab,
                                               const double *ctab, const Pcg2Cand<A, NS, PK> &cd) {
@@ -96,7 +101,16 @@ __device__ __forceinline__ double pcg2_weight(const Pcg2Rec<A, NS> &rc, const Li
   if constexpr (NS < A) {  // protocol 4.1: the constant attributes form their own product c; w = N * c
     double c = 1.0;
     if constexpr (PK) {
+#if DBL_PCG2_CTAB
       c = ctab[pcg2_const_index(cd.ypack, rc.xpack)];
+#else
+      // the same product, multiplied out: byte k of d is zero <=> constant attribute k matches (a missing record
+      // value is 0xFF and matches nothing); no table look-up, i.e. two shared-memory wavefronts less per candidate
+      const unsigned d = cd.ypack ^ rc.xpack;
+#pragma unroll
+      for (int k = 0; k < A - NS; ++k)
+        if ((d & (0xFFu << (8 * k))) == 0u) c = c * rc.rm[k];
+#endif
     } else {
 #pragma unroll
       for (int k = 0; k < A - NS; ++k) mul_if_eq(c, y[k], rc.x[k], rc.rm[k]);
