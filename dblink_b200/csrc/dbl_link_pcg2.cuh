@@ -179,7 +179,11 @@ __host__ __device__ constexpr int pcg2_rpw(int HC, int NS) { return (HC == 32 &&
 __host__ __device__ constexpr int pcg2_warps(int HC, int NS) { return pcg2_rpw(HC, NS) >= 2 ? DBL_PCG2_WARPS2 : LINK_WARPS; }
 // 3 CTAs per SM (72 registers) only where one record per warp fits them: few non-constant attributes
 __host__ __device__ constexpr int pcg2_ctas_per_sm(int HC, int NS) {
+#ifdef DBL_PCG2_CTAS2
+  return pcg2_rpw(HC, NS) >= 2 ? DBL_PCG2_CTAS2 : (NS > 6 ? 2 : DBL_PCG2_CTAS_PER_SM);
+#else
   return pcg2_rpw(HC, NS) >= 2 ? (pcg2_warps(HC, NS) > 8 ? 1 : 2) : (NS > 6 ? 2 : DBL_PCG2_CTAS_PER_SM);
+#endif
 }
 
 template <int A, int NS, int HC, bool PK>
