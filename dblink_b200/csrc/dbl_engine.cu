@@ -2224,7 +2224,8 @@ static int launch_link(dbl_ctx *ctx, int sampler) {
     pp.heavy_list = ctx->heavy_list.p;
     if (ctx->in_block_sweep)  // the block-level API launches once per block after one k_theta
       CUDA_TRY(cudaMemsetAsync(ctx->ctl() + CTL_HEAVY, 0, sizeof(long long), ctx->stream));
-    k_link_pruned<<<grid_for(ctx->R, LINK_WARPS), LINK_WARPS * 32, 0, ctx->stream>>>(pp);
+    k_link_pruned<<<(int)std::min<int64_t>(grid_for(ctx->R, LINK_WARPS), (int64_t)ctx->sm_count * 16), LINK_WARPS * 32, 0,
+                    ctx->stream>>>(pp);
     // records whose whole block has to be scored (no must-match attribute), a CTA each; usually none: the kernel
     // reads the count and returns
     k_link_heavy<<<ctx->sm_count * 2, HEAVY_WARPS * 32, 0, ctx->stream>>>(pp);

@@ -671,17 +671,24 @@ struct PrunedParams {
 constexpr int HEAVY_MIN_CANDIDATES = 256;
 constexpr int HEAVY_WARPS = 16;
 
-__global__ void __launch_bounds__(LINK_WARPS * 32) k_link_pruned(PrunedParams pp) {
-  __shared__ RecAttr s_ra[LINK_WARPS][DBL_MAX_ATTRS];
-  __shared__ int s_mm_attr[LINK_WARPS][DBL_MAX_ATTRS];
-  __shared__ int s_mm_x[LINK_WARPS][DBL_MAX_ATTRS];
-  constexpr int SCAP = 48;  // survivors kept for pass 2 (more than that: pass 2 walks the postings again)
-  __shared__ int s_sj[LINK_WARPS][SCAP];
-  __shared__ double s_sw[LINK_WARPS][SCAP];
+constexpr int PRUNED_SCAP = 48;  // survivors kept for pass 2 (more than that: pass 2 walks the postings again)
+struct PrunedShared {
+  RecAttr ra[LINK_WARPS][DBL_MAX_ATTRS];
+  int mm_attr[LINK_WARPS][DBL_MAX_ATTRS];
+  int mm_x[LINK_WARPS][DBL_MAX_ATTRS];
+  int sj[LINK_WARPS][PRUNED_SCAP];
+  double sw[LINK_WARPS][PRUNED_SCAP];
+};
+
+// one record (position ridx of rec_sorted) by one warp
+__device__ __forceinline__ void pruned_record(const PrunedParams &pp, PrunedShared &sh, long long ridx, int warp, int lane) {
+  constexpr int SCAP = PRUNED_SCAP;
+  RecAttr (&s_ra)[LINK_WARPS][DBL_MAX_ATTRS] = sh.ra;
+  int (&s_mm_attr)[LINK_WARPS][DBL_MAX_ATTRS] = sh.mm_attr;
+  int (&s_mm_x)[LINK_WARPS][DBL_MAX_ATTRS] = sh.mm_x;
+  int (&s_sj)[LINK_WARPS][SCAP] = sh.sj;
+  double (&s_sw)[LINK_WARPS][SCAP] = sh.sw;
   const LinkParams &p = pp.lp;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long ridx = (long long)blockIdx.x * LINK_WARPS + warp;
-  if (sweep_dead(p.ctl) || ridx >= p.rec_ptr[p.P]) return;  // records of blocks this rank owns come first in rec_sorted
   const int r = p.rec_sorted[ridx];
   const int b = pp.rec_key_sorted[ridx] >> pp.rec_key_shift;  // the sort key of the record: block id above the cost class
   const int A = p.A;
@@ -910,6 +917,21 @@ __global__ void __launch_bounds__(LINK_WARPS * 32) k_link_pruned(PrunedParams pp
   }
   if (pick < 0) pick = last_pos >= 0 ? last_pos : (chunk * cand_per_chunk + L < n ? chunk * cand_per_chunk + L : n - 1);
   store_link(p, lane, r, b, phi - plo, pick);
+}
+
+// A fixed grid of warps strides over the records of the blocks this rank owns (they come first in rec_sorted; the
+// count is read on the device).  One CTA per 8 records of the WHOLE data set, most of them returning at once on a
+// shard, cost more than it looks: 0.2 ms of a 0.9 ms kernel on 2 GPUs, and growing with the rank count.
+__global__ void __launch_bounds__(LINK_WARPS * 32) k_link_pruned(PrunedParams pp) {
+  __shared__ PrunedShared sh;
+  const LinkParams &p = pp.lp;
+  if (sweep_dead(p.ctl)) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long nrec = p.rec_ptr[p.P];
+  for (long long ridx = (long long)blockIdx.x * LINK_WARPS + warp; ridx < nrec; ridx += (long long)gridDim.x * LINK_WARPS) {
+    pruned_record(pp, sh, ridx, warp, lane);
+    __syncwarp();  // the warp's shared tables are rewritten by the next record
+  }
 }
 
 // The records k_link_pruned left aside, one CTA each: the warps share out the chunks of the block (a chunk's lane sums
