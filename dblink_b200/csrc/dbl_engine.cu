@@ -368,6 +368,11 @@ __global__ void k_finish(long long *__restrict__ ctl) {
 // k_values: one thread per (entity, attribute).  updateEntityValueCollapsed GU:576-599 +
 // perturbedDistYCollapsed GU:534-570 (PCG-I/II); updateEntityValue GU:605-646 + perturbedDistY GU:702-727.
 // ---------------------------------------------------------------------------------------------------
+// batched loads of k_values on sizes that fill the GPU (see value_update): value phase of a 1M sweep 1.129 ms with
+// none (1), 1.089 with pairs (2), 1.151 with four at a time (64 registers either way: the spills grow)
+#ifndef DBL_VALUES_UB_LARGE
+#define DBL_VALUES_UB_LARGE 2
+#endif
 struct ValParams {
   int A, F, sampler;
   uint64_t seed;
@@ -2282,7 +2287,7 @@ static int update_owned(dbl_ctx *ctx, int sampler) {
   vp.ent_rec_ptr = ctx->ent_rec_ptr.p; vp.rec_by_ent = ctx->rec_by_ent.p; vp.y = ctx->y.p;
   // latency-bound sizes (the grid does not fill the GPU a few times over): the variant with batched loads
   if (ctx->E * A <= (int64_t)ctx->sm_count * 2048 * 4) k_values<8><<<grid_rows(ctx->E * A, 128), 128, 0, ctx->stream>>>(vp);
-  else k_values<1><<<grid_rows(ctx->E * A, 128), 128, 0, ctx->stream>>>(vp);
+  else k_values<DBL_VALUES_UB_LARGE><<<grid_rows(ctx->E * A, 128), 128, 0, ctx->stream>>>(vp);
   ctx->launches += 1;
   // (4) N(e), new block ids, distortions, partial summary
   return refresh_summary(ctx, true);
@@ -2578,7 +2583,7 @@ extern "C" int dbl_set_rebalance(dbl_ctx *ctx, int32_t period, double threshold)
 static int preload_kernels(dbl_ctx *ctx) {
   cudaFuncAttributes fa;
 #define DBL_LOAD(k) CUDA_TRY(cudaFuncGetAttributes(&fa, k))
-  DBL_LOAD(k_theta); DBL_LOAD(k_link_heavy); DBL_LOAD(k_commit_link_keys); DBL_LOAD(k_build_tiles); DBL_LOAD(k_values<1>); DBL_LOAD(k_values<8>); DBL_LOAD(k_entity_post); DBL_LOAD(k_dist);
+  DBL_LOAD(k_theta); DBL_LOAD(k_link_heavy); DBL_LOAD(k_commit_link_keys); DBL_LOAD(k_build_tiles); DBL_LOAD(k_values<DBL_VALUES_UB_LARGE>); DBL_LOAD(k_values<8>); DBL_LOAD(k_entity_post); DBL_LOAD(k_dist);
   DBL_LOAD(k_reduce_local); DBL_LOAD(k_finish); DBL_LOAD(k_move_ent); DBL_LOAD(k_move_rec); DBL_LOAD(k_publish_barrier);
   DBL_LOAD(k_unpack_ent_p2p); DBL_LOAD(k_unpack_rec_p2p); DBL_LOAD(k_reduce_peers); DBL_LOAD(k_lpt);
   DBL_LOAD(k_link_generic); DBL_LOAD(k_link_match); DBL_LOAD(k_link_pruned); DBL_LOAD(k_state_hash);
