@@ -2112,7 +2112,8 @@ static int ensure_inverted_index(dbl_ctx *ctx) {
     CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->inv_tmp.p, tb, (const unsigned *)ctx->inv_key32_in.p, ctx->inv_key32.p,
                                              (const int *)ctx->inv_pos_in.p, ctx->inv_pos.p, (int)cap, 0,
                                              ibits, ctx->stream));
-    k_inv_value_ptr32<<<grid_for(cap + 1, 256), 256, 0, ctx->stream>>>(cap, n_ids, ctx->inv_key32.p, ctx->inv_vptr.p);
+    k_inv_value_ptr32<<<grid_for(cap + 1, 256), 256, 0, ctx->stream>>>(cap, n_ids, (long long)dn.sumV, ctx->inv_key32.p,
+                                                                       ctx->inv_vptr.p);
     ctx->launches += 5;
     ctx->inv_valid = true;
     CUDA_TRY(cudaGetLastError());

@@ -631,12 +631,27 @@ __global__ void k_inv_keys32(int64_t E, int A, int P, InvDense d, long long n_id
     pos[t] = -1;
   }
 }
-__global__ void k_inv_value_ptr32(int64_t n, long long n_ids, const unsigned *__restrict__ key, int *__restrict__ vptr) {
+// vptr[id] = first sorted entry whose key is >= id.  The thread at a boundary between two different keys fills the ids
+// in between.  On a shard the keys of whole blocks are missing (7/8 of the id space on 8 ranks): a boundary thread
+// filled up to ~2 million entries one after the other, and the sharded PCG-I sweep got SLOWER with every rank added
+// (link phase 1.2 ms on 2 GPUs, 1.4-1.7 ms on 4).  Nothing ever looks up an id of a block without entities (a record
+// queries ids of its own block b, and id + 1 <= (b + 1) * sumV), so the gap is filled only to the first id of the
+// block after the previous key's and from the first id of the current key's block.
+__global__ void k_inv_value_ptr32(int64_t n, long long n_ids, long long sumV, const unsigned *__restrict__ key,
+                                  int *__restrict__ vptr) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i > n) return;
   const long long cur = (i < n) ? min((long long)key[i], n_ids) : n_ids;
   const long long prev = (i > 0) ? min((long long)key[i - 1], n_ids) : -1;
-  for (long long g = prev + 1; g <= cur; ++g) vptr[g] = (int)i;
+  if (cur == prev) return;
+  const long long pb = prev >= 0 ? prev / sumV : -1, cb = cur / sumV;
+  if (cb > pb + 1) {
+    const long long e1 = min((pb + 1) * sumV, cur);
+    for (long long g = prev + 1; g <= e1; ++g) vptr[g] = (int)i;
+    for (long long g = max(cb * sumV, e1 + 1); g <= cur; ++g) vptr[g] = (int)i;
+  } else {
+    for (long long g = prev + 1; g <= cur; ++g) vptr[g] = (int)i;
+  }
 }
 
 __device__ __forceinline__ int64_t inv_lower_bound(const unsigned long long *__restrict__ key, int64_t lo, int64_t hi,
