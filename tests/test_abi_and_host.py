@@ -241,3 +241,20 @@ def test_theta_draw_of_the_product_equals_the_oracle_bit_for_bit(oracle):
                               out.ctypes.data_as(_lib.f64p))
         assert rc == 0
         np.testing.assert_array_equal(out, ref)
+
+
+def test_bench_finds_the_counters_of_the_final_link_kernel():
+    """bench.py turns the committed ncu counters of the link kernel into roofline.issue / roofline.l1_data_pipe: the
+    latest entry must be the capture of the shipped kernel and hold every counter the bench reads"""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    key, c = bench.ncu_constants("link_pcg2")
+    assert key == "r2o_link_pcg2" and os.path.exists(os.path.join(ROOT, "profiles", key + ".md"))
+    for k in ("pairs", "warp_instructions", "smem_wavefronts", "dram_bytes", "l1_data_pipe_wavefronts"):
+        assert c[k] > 0
+    steps = c["pairs"] / 32.0
+    assert 60 < c["warp_instructions"] / steps < 80      # 71.4 warp-instructions per 32-candidate record-step
+    assert 18 < c["l1_data_pipe_wavefronts"] / steps < 25  # 21.4 wavefronts
